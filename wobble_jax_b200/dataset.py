@@ -1,0 +1,126 @@
+"""Host-side data containers: ragged per-row spectra -> padded (E, Pmax) blocks.
+
+Mirror of the reference's ``jabble/dataset.py:111-237`` (``DataBlock``, ``Data``, ``DataFrame``,
+``blockify``).  Arrays are numpy float64 on the host; the device copy is made once per plan by the
+C-ABI library (``jb_plan_create``), which replaces ``jax.device_put``.  HDF5 I/O and continuum
+fitting (dataset.py:19-109, 239-277) are out of scope.
+"""
+
+import numpy as np
+
+
+class DataBlock:
+    """dataset.py:111-137 -- attribute bag of equally-long arrays, hashed by identity."""
+
+    def __init__(self, **kwargs):
+        self.__dict__.update(kwargs)
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    def __getitem__(self, key):
+        return self.__dict__[key]
+
+    def __len__(self):
+        return self.__dict__[list(self.__dict__.keys())[0]].shape[0]
+
+    def keys(self):
+        return self.__dict__.keys()
+
+    def slice(self, start, stop):
+        return DataBlock(**{k: v[start:stop] for k, v in self.__dict__.items()})
+
+    def ele(self, i):
+        return DataBlock(**{k: v[i] for k, v in self.__dict__.items()})
+
+    def to_device(self, device):
+        """No-op: device residency is owned by the plan (one upload per plan)."""
+        return self
+
+
+class DataFrame:
+    """dataset.py:280-291 -- one row (epoch x order) of a spectrum."""
+
+    def __init__(self, xs, ys, yivar, mask):
+        self.xs = np.asarray(xs, dtype=np.float64)
+        self.ys = np.asarray(ys, dtype=np.float64)
+        self.yivar = np.asarray(yivar, dtype=np.float64)
+        self.mask = np.asarray(mask).astype(bool)
+
+    def to_device(self, device):
+        return self
+
+
+class Data:
+    """dataset.py:147-237."""
+
+    def __init__(self, frames, *args):
+        self.dataframes = frames
+        self.metadata = {}
+        self.metakeys = {}
+
+    def __getitem__(self, i):
+        return self.dataframes[i]
+
+    def __len__(self):
+        return len(self.dataframes)
+
+    @property
+    def xs(self):
+        return [f.xs for f in self.dataframes]
+
+    @property
+    def ys(self):
+        return [f.ys for f in self.dataframes]
+
+    @property
+    def yivar(self):
+        return [f.yivar for f in self.dataframes]
+
+    @property
+    def mask(self):
+        return [f.mask for f in self.dataframes]
+
+    @property
+    def yerr(self):
+        return [1 / np.sqrt(f.yivar) for f in self.dataframes]
+
+    @staticmethod
+    def from_lists(xs, ys, yivar, ma):
+        """dataset.py:183-187."""
+        return Data([DataFrame(xs[i], ys[i], yivar[i], ma[i]) for i in range(len(xs))])
+
+    def to_device(self, device):
+        return self
+
+    def blockify(self, device=None):
+        """dataset.py:192-237 -- pad every row to the longest one (x = y = ivar = 0, mask = True)
+        and turn every metadata key into dense integer ids.  Returns (datablock, metablock)."""
+        E = len(self)
+        max_ind = int(np.max([len(f.xs) for f in self.dataframes]))
+        xs = np.zeros((E, max_ind))
+        ys = np.zeros((E, max_ind))
+        yivar = np.zeros((E, max_ind))
+        mask = np.ones((E, max_ind), dtype=bool)
+        for i, f in enumerate(self.dataframes):
+            n = len(f.xs)
+            xs[i, :n] = f.xs
+            ys[i, :n] = f.ys
+            yivar[i, :n] = f.yivar
+            mask[i, :n] = f.mask
+        index_span = np.arange(0, E, dtype=int)
+        metablock = {"index": index_span}
+        for key in self.metadata:
+            if key in self.metakeys:
+                epoch_indices = np.zeros(index_span.shape)
+                for i, ele in enumerate(self.metakeys[key]):
+                    epoch_indices[np.asarray(self.metadata[key]) == ele] = i
+                epoch_uniques = self.metakeys[key]
+            else:
+                epoch_uniques, epoch_indices = np.unique(self.metadata[key], return_inverse=True)
+            self.metakeys[key] = epoch_uniques
+            metablock[key] = np.asarray(epoch_indices).astype(int)
+        return DataBlock(xs=xs, ys=ys, yivar=yivar, mask=mask), DataBlock(**metablock)

@@ -1,0 +1,375 @@
+"""Model tree with the reference's API; every evaluation runs in the sm_100a CUDA library.
+
+Host-side mirror of ``jabble/model.py`` for the hot path:
+the classes, ``_fit`` flags, ``fit/fix``, ``get_parameters``/``_unpack`` ordering, ``display``,
+``optimize`` and ``f_info`` keep the reference's names, argument meaning and results, so a
+script written against ``jabble.model`` runs unchanged.  What is different is underneath:
+instead of ``jax.jit``/``vmap``/``grad`` the tree is compiled into a flat plan
+(``wobble_jax_b200.engine``) and evaluated by hand-written CUDA kernels through the C ABI
+in ``include/jabble_b200.h``.  There is no CPU path: without the CUDA library every
+evaluation raises.
+
+Parameters are numpy float64 arrays (the reference's are jnp arrays under
+``jax_enable_x64``).
+"""
+
+import copy
+import math
+
+import numpy as np
+import scipy.optimize
+
+from . import physics
+
+_RESULTS_DTYPE = [("task", "U64"), ("funcalls", int), ("nit", int), ("warnflag", int),
+                  ("f", np.double), ("loss", "U64")]
+
+
+def get_submodel_indices(self, i, j=None, *args):
+    """model.py:23-33 -- positions, inside ``self``'s fit vector, of the parameters of the
+    sub-model reached by the index path (i, j, ...)."""
+    s_temp = self.get_indices(i)
+    if j is not None:
+        temp = get_submodel_indices(self[i], j, *args)
+        return s_temp[temp]
+    return s_temp
+
+
+def create_x_grid(xs, vel_padding, resolution):
+    """model.py:85-111 -- evenly spaced log-wavelength knot grid, one step per resolution
+    element, padded by ``vel_padding`` (m/s) on both sides."""
+    xs = np.asarray(xs)
+    x_min = xs.min()
+    x_max = xs.max()
+    step = physics.shifts(physics.SPEED_OF_LIGHT / resolution)
+    x_padding = physics.shifts(vel_padding)
+    size = int(math.ceil((x_max - x_min + 2 * x_padding) / step))
+    return np.linspace(x_min - x_padding, x_max + x_padding, size)
+
+
+def _as_param(p):
+    return np.array(p, dtype=np.float64).reshape(-1)
+
+
+class Model:
+    """model.py:114-416 -- base class: ``_fit`` flag, ``optimize``, parameter plumbing."""
+
+    def __init__(self, *args, **kwargs):
+        self._fit = False
+        self.results = np.empty(shape=(0), dtype=_RESULTS_DTYPE)
+        self.metadata = {}
+
+    # ------------------------------------------------------------------ evaluation
+    def __call__(self, p, x, meta, margs=()):
+        """model.py:138-160 -- ``model(p, x, meta)`` for one row: ``p`` empty => stored
+        parameters (model must be fixed), else ``p`` is the fit vector (model must be in
+        fit mode).  ``x`` is (P,), ``meta`` maps key name -> integer id of that row."""
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        if len(p) == 0:
+            assert self._fit == False  # noqa: E712  (same assertion as the reference)
+        else:
+            assert self._fit == True  # noqa: E712
+        return self.call(p, x, meta, margs)
+
+    def call(self, p, x, meta, margs=()):
+        """Evaluate this (sub-)tree for one row on the GPU; an empty ``p`` means "use the stored
+        parameters" at every level, exactly like the reference's per-node ``len(p) == 0`` test."""
+        from . import engine
+        return engine.evaluate_row(self, p, x, meta)
+
+    # -------------------------------------------------------------------- optimiser
+    def optimize(self, loss, data, device_store=None, device_op=None, batch_size=None, options={}):
+        """model.py:195-238 -- L-BFGS-B over every parameter in fit mode.
+
+        Same contract as the reference: blockify the data, hand scipy ``func`` and ``fprime``,
+        append one record to ``self.results`` and write the solution back with ``_unpack``;
+        returns ``(x, f, d)``.  ``func`` and ``fprime`` share ONE fused CUDA evaluation per
+        parameter vector (the reference runs a forward for ``func`` and a second forward plus a
+        backward for ``fprime``).  ``device_store``/``device_op``/
+        ``batch_size`` are accepted for signature compatibility; the data are uploaded once into
+        HBM by the plan and never re-batched.
+        """
+        from . import engine
+
+        datablock, metablock = data.blockify(device_store)
+        loss.ready_indices(self)
+        x0 = np.asarray(self.get_parameters(), dtype=np.float64)
+        objective = engine.Objective(loss, self, datablock, metablock)
+        x, f, d = scipy.optimize.fmin_l_bfgs_b(
+            func=objective.value, fprime=objective.gradient, x0=x0, **options)
+        self.results = np.append(
+            self.results,
+            np.array([(d["task"], d["funcalls"], d["nit"], d["warnflag"], f, repr(loss))],
+                     dtype=_RESULTS_DTYPE), axis=0)
+        self._unpack(np.asarray(x, dtype=np.float64))
+        return x, f, d
+
+    # ------------------------------------------------------------------- composition
+    def __add__(self, x):
+        if isinstance(x, AdditiveModel):
+            return AdditiveModel(models=[self, *x.models])
+        return AdditiveModel(models=[self, x])
+
+    def __radd__(self, model):
+        return AdditiveModel(models=[self, model])
+
+    def composite(self, model):
+        """model.py:261-275 -- y = model(self(x))."""
+        return CompositeModel(models=[self, model])
+
+    def evaluate(self, x, i):
+        self.fit()
+        return self(self.p, x, i)
+
+    # ------------------------------------------------------------------ fit / fix
+    def fix(self):
+        self._fit = False
+
+    def fit(self):
+        self._fit = True
+
+    def to_device(self, device):
+        """No-op: parameters live on the host and are uploaded per evaluation."""
+
+    def get_parameters(self):
+        """model.py:299-311."""
+        if self._fit:
+            return _as_param(self.p)
+        return np.zeros(0)
+
+    def _unpack(self, p):
+        if len(p) != 0:
+            self.p = _as_param(p)
+
+    def display(self, string=""):
+        """model.py:317-329 -- one line per node with the number of parameters in fit mode."""
+        out = string + "-" + self.__class__.__name__ + "-"
+        out += "-----------------------------------"
+        params = str(len(self.get_parameters()))
+        while len(out + params) % 17 != 0:
+            out += "-"
+        out += params
+        print(out)
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+
+class ContainerModel(Model):
+    """model.py:418-593 -- a node holding sub-models and the slices of the fit vector they own."""
+
+    def __init__(self, models, *args, **kwargs):
+        super(ContainerModel, self).__init__()
+        self.models = list(models)
+        self.size = len(self.models)
+        self._parameters_per_model = np.zeros(len(self.models), dtype=int)
+        for i in range(self.size):
+            self._parameters_per_model[i] = len(self.models[i].get_parameters())
+        self.create_param_indices()
+
+    def append(self, model):
+        self.models.append(model)
+        self.size = len(self.models)
+        self._parameters_per_model = np.concatenate(
+            (self._parameters_per_model, [len(model.get_parameters())]))
+        self.create_param_indices()
+
+    def __call__(self, p, x, meta, margs=()):
+        """model.py:456-462 -- containers pass an empty vector down when nothing is fit."""
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        return self.call(p, x, meta, margs)
+
+    def __getitem__(self, i):
+        return self.models[i]
+
+    def _unpack(self, p):
+        """model.py:470-476."""
+        p = np.asarray(p, dtype=np.float64)
+        for k, model in enumerate(self.models):
+            model._unpack(p[self.get_indices(k)])
+
+    def get_parameters(self):
+        """model.py:478-495 -- DFS concatenation; refreshes the per-child index ranges."""
+        parts = []
+        for i in range(self.size):
+            params = self.models[i].get_parameters()
+            self._parameters_per_model[i] = params.shape[0]
+            parts.append(params)
+        self.create_param_indices()
+        return np.concatenate(parts) if parts else np.zeros(0)
+
+    def create_param_indices(self):
+        """model.py:497-502."""
+        self._param_indices = []
+        for i in range(len(self.models)):
+            start = int(np.sum(self._parameters_per_model[:i]))
+            stop = int(np.sum(self._parameters_per_model[:i + 1]))
+            self._param_indices.append(np.arange(start, stop))
+
+    def get_indices(self, i):
+        return self._param_indices[i]
+
+    def split_p(self, p):
+        return [p[self.get_indices(k)] for k in range(len(self._parameters_per_model))]
+
+    def fit(self, i=None, *args):
+        """model.py:512-532 -- ``fit()`` everything, or ``fit(i, j, ...)`` one sub-model by path."""
+        if i is None:
+            for j in range(self.size):
+                self.models[j].fit()
+                self._parameters_per_model[j] = self.models[j].get_parameters().shape[0]
+        else:
+            self[i].fit(*args)
+            self._parameters_per_model[i] = self[i].get_parameters().shape[0]
+        self.create_param_indices()
+
+    def fix(self, i=None, *args):
+        """model.py:534-550."""
+        if i is None:
+            for j, model in enumerate(self.models):
+                model.fix()
+                self._parameters_per_model[j] = 0
+        else:
+            self[i].fix(*args)
+            self._parameters_per_model[i] = 0
+        self.create_param_indices()
+
+    @property
+    def _fit(self):
+        return any(m._fit for m in self.models)
+
+    @_fit.setter
+    def _fit(self, value):
+        pass  # a container has no flag of its own (reference keeps an unused one)
+
+    def to_device(self, device):
+        for model in self.models:
+            model.to_device(device)
+
+    def display(self, string=""):
+        """model.py:559-567."""
+        self.get_parameters()
+        super(ContainerModel, self).display(string)
+        for i, model in enumerate(self.models):
+            tab = "  {}".format(i)
+            string += tab
+            model.display(string)
+            string = string[: -len(tab)]
+
+    def copy(self):
+        return self.__class__(models=copy.deepcopy(self.models))
+
+
+class CompositeModel(ContainerModel):
+    """model.py:664-681 -- f = g_n(...g_1(g_0(x)))."""
+
+    def composite(self, x):
+        if isinstance(x, CompositeModel):
+            return CompositeModel(models=[*self.models, *x.models])
+        return CompositeModel(models=[*self.models, x])
+
+
+class AdditiveModel(ContainerModel):
+    """model.py:684-709 -- f = sum_k g_k(x)."""
+
+    def __add__(self, x):
+        if isinstance(x, AdditiveModel):
+            return AdditiveModel(models=[*self.models, *x.models])
+        return AdditiveModel(models=[*self.models, x])
+
+    def __radd__(self, x):
+        if isinstance(x, AdditiveModel):
+            return AdditiveModel(models=[*self.models, *x.models])
+        return AdditiveModel(models=[*self.models, x])
+
+
+class EpochSpecificModel(Model):
+    """model.py:712-909 -- one scalar per epoch key."""
+
+    def __init__(self, p, which_key="index", *args, **kwargs):
+        super(EpochSpecificModel, self).__init__()
+        self.p = _as_param(p)
+        self.n = len(self.p)
+        self._epoches = slice(0, self.n)
+        self.which_key = which_key
+
+    def __call__(self, p, x, meta, margs=()):
+        """model.py:730-736 -- no fit-mode assertion here in the reference either."""
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        return self.call(p, x, meta, margs)
+
+    def add_component(self, value=0.0, n=1):
+        self.p = np.concatenate((self.p, value * np.ones(n)))
+        self.n = len(self.p)
+
+    def fix(self, epoches=None):
+        self._fit = False
+        if epoches is not None:
+            self._epoches = epoches
+
+    def fit(self, epoches=None):
+        self._fit = True
+        if epoches is not None:
+            self._epoches = epoches
+
+    def f_info(self, model, data, device=None):
+        """model.py:857-901 -- diagonal Fisher information of this model's per-epoch parameters,
+        F_k = sum_{rows r with key k} sum_pix where(~mask, (d model/d p_k)^2 * yivar, 0).
+
+        The reference builds a dense (P, N) ``jax.jacfwd`` Jacobian per row in a Python loop
+        (O(E*P*N)); here F falls out of the fused loss+gradient kernel in O(E*P).  Like the
+        reference this puts the whole model in fixed mode and ``self`` in fit mode.
+        """
+        from . import engine
+
+        model.fix()
+        self.fit()
+        model.display()
+        datablock, metablock = data.blockify(device)
+        return engine.fisher_information(model, self, datablock, metablock)
+
+    def grid_search(self, *args, **kwargs):
+        raise NotImplementedError("grid_search is outside the accelerated hot path (SURVEY.md section 8f-3)")
+
+    def parabola_fit(self, *args, **kwargs):
+        raise NotImplementedError("parabola_fit is outside the accelerated hot path (SURVEY.md section 8f-3)")
+
+
+class ShiftingModel(EpochSpecificModel):
+    """model.py:911-927 -- f(p, x, i) = x - p[meta[which_key]]  (the code subtracts)."""
+
+
+class StretchingModel(EpochSpecificModel):
+    """model.py:930-946 -- f(p, x, i) = p[meta[which_key]] * x."""
+
+
+class CardinalSplineMixture(Model):
+    """model.py:991-1037 -- cardinal B-spline template: knot centres ``xs`` (evenly spaced),
+    control points ``p`` (same shape), degree ``p_val``; basis = p_val! * Irwin-Hall
+    (cardinalspline.py), so control points carry that scaling."""
+
+    def __init__(self, xs, p_val=2, p=None, *args, **kwargs):
+        super(CardinalSplineMixture, self).__init__()
+        self.p_val = int(p_val)
+        self.xs = np.asarray(xs, dtype=np.float64)
+        if p is not None:
+            p = np.asarray(p, dtype=np.float64)
+            if p.shape == self.xs.shape:
+                self.p = p.copy()
+            else:
+                raise ValueError("p {} must be the same shape as x_grid {}".format(p.shape, self.xs.shape))
+        else:
+            self.p = np.zeros(self.xs.shape)
+
+
+class NormalizationModel(Model):
+    """model.py:1110-1157 -- f(p, x, i) = inner(p.reshape(size, K)[meta[which_key]], x): a private
+    small spline per row."""
+
+    def __init__(self, p, model, size, which_key="index"):
+        super(NormalizationModel, self).__init__()
+        self.p = _as_param(p)
+        self.model = model
+        self.which_key = which_key
+        self.model_p_size = len(model.p)
+        self.size = int(size)

@@ -1,0 +1,90 @@
+"""Model builders and the staged training recipe, mirroring ``jabble/quickplay.py:131-403``.
+
+These are callers of the hot path with no arithmetic of their own:
+they assemble the model trees the CUDA plan compiler recognises and drive ``Model.optimize``.
+RV post-processing / HDF summaries (quickplay.py:15-129, 405-553) are out of scope.
+"""
+
+import numpy as np
+
+from . import model as jmodel
+from . import physics
+
+
+def _magnitudes(v):
+    """Accept plain arrays or astropy quantities (the reference multiplies by ``u.m/u.s``)."""
+    return np.asarray(getattr(v, "value", v), dtype=np.float64)
+
+
+def get_stellar_model(init_rvs, model_grid, p_val, which_key="index"):
+    """quickplay.py:131-150 -- Composite[Shifting(shifts(init_rvs)), CardinalSplineMixture]."""
+    return jmodel.CompositeModel([
+        jmodel.ShiftingModel(physics.shifts(_magnitudes(init_rvs)), which_key=which_key),
+        jmodel.CardinalSplineMixture(model_grid, p_val)])
+
+
+def get_tellurics_model(init_airmass, model_grid, p_val, rest_vels=None, which_key="index"):
+    """quickplay.py:152-176 -- Composite[Shifting(rest), CardinalSplineMixture, Stretching(airmass)]."""
+    init_airmass = _magnitudes(init_airmass)
+    if rest_vels is None:
+        rest_vels = np.zeros(init_airmass.shape)
+    return jmodel.CompositeModel([
+        jmodel.ShiftingModel(physics.shifts(_magnitudes(rest_vels)), which_key=which_key),
+        jmodel.CardinalSplineMixture(model_grid, p_val),
+        jmodel.StretchingModel(init_airmass, which_key=which_key)])
+
+
+def get_wobble_model(init_rvs, init_airmass, model_grid, p_val, rest_vels=None, which_key="index"):
+    """quickplay.py:178-202 -- stellar + telluric."""
+    return get_stellar_model(init_rvs, model_grid, p_val, which_key=which_key) + \
+        get_tellurics_model(init_airmass, model_grid, p_val, rest_vels, which_key=which_key)
+
+
+def get_normalization_model(dataset, norm_p_val, norm_pts):
+    """quickplay.py:204-236 -- Shifting(row start offsets) o Normalization(per-row small spline);
+    (norm_pts + norm_p_val + 1) control points per row."""
+    len_xs = np.max([np.max(f.xs) - np.min(f.xs) for f in dataset])
+    min_xs = np.min([np.min(f.xs) for f in dataset])
+    shifts = np.array([f.xs.min() - min_xs for f in dataset])
+    x_spacing = len_xs / norm_pts
+    x_grid = np.linspace(-x_spacing * ((norm_p_val + 1) // 2),
+                         len_xs + (x_spacing * ((norm_p_val + 1) // 2)),
+                         norm_pts + norm_p_val + 1) + min_xs
+    inner = jmodel.CardinalSplineMixture(x_grid, norm_p_val)
+    size = len(dataset)
+    p = np.tile(inner.p, size)
+    norm_model = jmodel.NormalizationModel(p, inner, size)
+    return jmodel.ShiftingModel(shifts).composite(norm_model)
+
+
+def train_cycle(model, dataset, loss, device_store=None, device_op=None, batch_size=None,
+                options={"maxiter": 100_000}, parabola_fit=False):
+    """quickplay.py:287-380 -- the staged fit: stellar template; stellar+telluric templates; RVs;
+    everything; RVs; everything.  RV is model[0][0], templates model[0][1] and model[1][1]."""
+    if parabola_fit:
+        raise NotImplementedError("parabola_fit is SURVEY.md section 8f-3 (not built yet)")
+    stages = [
+        [(0, 1)],
+        [(0, 1), (1, 1)],
+        [(0, 0)],
+        [(0, 0), (0, 1), (1, 1)],
+        [(0, 0)],
+        [(0, 0), (0, 1), (1, 1)],
+    ]
+    for fits in stages:
+        model.fix()
+        for f in fits:
+            model.fit(*f)
+        model.display()
+        res = model.optimize(loss, dataset, device_store, device_op, batch_size, options=options)
+        print(res)
+    return model
+
+
+def get_RV_error_fisher(model, dataset, device=None, rv_ind=[0, 0]):
+    """quickplay.py:382-403 -- per-epoch RV error bar sqrt(1/F) * dv/d(shift), in m/s."""
+    rv_model = model
+    for xx in rv_ind:
+        rv_model = rv_model[xx]
+    f_info = rv_model.f_info(model, dataset, device)
+    return np.sqrt(1 / f_info) * physics.dvelocities(rv_model.p)
