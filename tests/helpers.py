@@ -32,6 +32,7 @@ def stellar_from_golden(g):
     meta = json.loads(str(g["meta"]))
     model = jabble.quickplay.get_stellar_model(g["init_v"], g["grid"], meta["p_val"])
     model[1].p = g["spline_p"].copy()
+    model[0].p = g["shift_p"].copy()      # bit-identical inputs (see test_oracle_golden._check_cases)
     return model, meta
 
 
@@ -41,7 +42,17 @@ def wobble_from_golden(g):
                                               rest_vels=g["rest_v"], which_key=meta["which_key"])
     model[0][1].p = g["S"].copy()
     model[1][1].p = g["T"].copy()
+    _set_epoch_params(model, g)
     return model, meta
+
+
+def _set_epoch_params(model, g):
+    """Overwrite the shift/stretch vectors with the golden ones AFTER checking the shim's own
+    conversion agrees to an ulp: x ~ 8.5 has ulp 1.8e-15 = 2e-10 knots, so a last-bit difference
+    in a shift moves the model by ~1e-10 relative -- parity needs bit-identical inputs."""
+    for attr, (i, j) in (("shift_p", (0, 0)), ("tshift_p", (1, 0)), ("stretch_p", (1, 2))):
+        assert np.allclose(model[i][j].p, g[attr], rtol=4e-16, atol=5e-16), attr
+        model[i][j].p = g[attr].copy()
 
 
 def pseudonormal_from_golden(g, data):
@@ -51,6 +62,9 @@ def pseudonormal_from_golden(g, data):
     model[0][1].p = g["S"].copy()
     model[1][1].p = g["T"].copy()
     model[2][1].p = g["norm_p"].copy()
+    _set_epoch_params(model, g)
+    assert np.allclose(model[2][0].p, g["norm_shift_p"], rtol=1e-13, atol=1e-18)
+    model[2][0].p = g["norm_shift_p"].copy()
     return model, meta
 
 

@@ -110,7 +110,6 @@ def test_golden_stellar():
     g = load_golden("stellar.npz")
     data = dataset_from_golden(g)
     model, meta = stellar_from_golden(g)
-    assert rel_err(model[0].p, g["shift_p"]) < 1e-15
     dbd, mbd = _check_cases(model, data, g, "st", [[(1,)], [(0,)], [(0,), (1,)]])
     model.fix(); model[0].fit()
     F = O.f_info(model[0].p, dbd, mbd, model)
@@ -123,8 +122,6 @@ def test_golden_wobble(name):
     g = load_golden(name)
     data = dataset_from_golden(g)
     model, meta = wobble_from_golden(g)
-    for attr, path in (("shift_p", (0, 0)), ("tshift_p", (1, 0)), ("stretch_p", (1, 2))):
-        assert rel_err(model[path[0]][path[1]].p, g[attr]) < 1e-15
     db, mb = data.blockify()
     assert np.array_equal(db["xs"], g["block_xs"]) and np.array_equal(db["mask"], g["block_mask"])
     for k in mb.keys():
@@ -146,7 +143,6 @@ def test_golden_pseudonormal():
     g = load_golden("pseudonormal.npz")
     data = dataset_from_golden(g)
     model, meta = pseudonormal_from_golden(g, data)
-    assert rel_err(model[2][0].p, g["norm_shift_p"]) < 1e-13
     assert rel_err(model[2][1].model.xs, g["norm_xs"]) < 1e-15
     dbd, mbd = _check_cases(model, data, g, "pn", json.loads(str(g["cases"])))
     model.fix(); model[0][0].fit()
