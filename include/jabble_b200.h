@@ -1,0 +1,159 @@
+/*
+ * jabble_b200.h -- C ABI of libjabble_b200.so: the B200 (sm_100a) implementation of Jabble's
+ * loss / gradient / RV-Fisher hot path.
+ *
+ * The reference (mdd423/wobble_jax) has no FFI layer: the seam this library replaces is the pair
+ * of Python callables handed to scipy in jabble/model.py:226-232
+ *     func   = loss.loss_all                  (jabble/loss.py:47-75)
+ *     fprime = jax.grad(loss.loss_all)        (jabble/model.py:228)
+ * plus EpochSpecificModel.f_info (jabble/model.py:857-901) and Model.__call__
+ * (jabble/model.py:138-160).  Everything below those calls -- Shifting/Stretching warp,
+ * CardinalSplineMixture evaluation, Additive/Composite combination, ChiSquare, the reverse pass,
+ * the per-epoch Fisher sums -- runs inside this library.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * jb_status; jb_last_error() gives the message for the calling thread.  No exceptions cross the
+ * boundary and there is NO CPU fallback: without a CUDA device every compute entry point fails
+ * with JB_ERR_CUDA.  Host buffers are owned by the caller and never retained after the call,
+ * except that jb_plan_create copies the data block into HBM once (the reference bakes the data
+ * into the jitted program per optimize() call, loss.py:47).
+ *
+ * Threading: calls on one plan are serial (scipy is serial); different plans may be driven from
+ * different host threads.  Each plan owns one CUDA stream.
+ */
+#ifndef JABBLE_B200_H
+#define JABBLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_ABI_VERSION 1
+
+typedef enum {
+    JB_OK = 0,
+    JB_ERR_BAD_ARG = -1,      /* null pointer, negative size, inconsistent descriptor            */
+    JB_ERR_UNSUPPORTED = -2,  /* model shape outside the compiled grammar (see jb_component_desc) */
+    JB_ERR_CUDA = -3,         /* CUDA runtime error, or no device                                 */
+    JB_ERR_OUT_OF_RANGE = -4, /* an unmasked warped pixel falls outside the knot grid (the         */
+                              /* reference clamps the gather silently, model.py:985)              */
+    JB_ERR_WINDOW = -5,       /* knot window of a pixel tile exceeds the on-chip capacity          */
+    JB_ERR_NONFINITE = -6     /* loss is NaN/Inf                                                   */
+} jb_status;
+
+typedef enum {
+    JB_COMP_SPLINE = 0,       /* CardinalSplineMixture: one control-point vector (model.py:991)     */
+    JB_COMP_NORM_SPLINE = 1   /* NormalizationModel over a CardinalSplineMixture: one control-point */
+                              /* vector PER KEY (model.py:1110-1143)                                */
+} jb_comp_kind;
+
+/*
+ * One additive component  a[k_a(r)] * Spline(x - d[k_d(r)]; ctrl)   (CompositeModel.call,
+ * model.py:670-675, of [ShiftingModel?, CardinalSplineMixture|NormalizationModel, StretchingModel?]).
+ * All *_offset fields index the plan's flat parameter vector ("params_all": every parameter of
+ * every leaf model, fit or fixed, in DFS order of the tree); -1 = that leaf is absent.
+ * Key arrays are (n_rows,) int32: the metablock column named by the leaf's which_key
+ * (dataset.py:214-235); NULL = row index.
+ */
+typedef struct {
+    int32_t kind;               /* jb_comp_kind                                                  */
+    int32_t p_val;              /* spline degree, 1..3                                           */
+    double xp0;                 /* xs[0] of the knot grid (model.py:979)                          */
+    double dx;                  /* xs[1] - xs[0]          (model.py:974)                          */
+    int64_t n_knots;            /* M (SPLINE) or K = knots per key (NORM_SPLINE)                  */
+    int64_t ctrl_offset;        /* control points: M values, or n_ctrl_keys * K values            */
+    int64_t n_ctrl_keys;        /* NORM_SPLINE: NormalizationModel.size; SPLINE: 0                */
+    const int32_t *ctrl_key;    /* NORM_SPLINE: row -> key                                        */
+    int64_t shift_offset;       /* ShiftingModel.p (model.py:927: x - p[key]) or -1               */
+    int64_t n_shift;
+    const int32_t *shift_key;
+    int64_t stretch_offset;     /* StretchingModel.p (model.py:946: p[key] * x) or -1             */
+    int64_t n_stretch;
+    const int32_t *stretch_key;
+} jb_component_desc;
+
+/* The data block of Data.blockify (dataset.py:192-237) plus the compiled model. */
+typedef struct {
+    int32_t abi_version;        /* JB_ABI_VERSION                                                */
+    int32_t device;             /* CUDA device ordinal                                           */
+    int64_t n_rows;             /* E                                                             */
+    int64_t n_pix;              /* P (padded row length of the block)                            */
+    const double *xs;           /* (E,P) row-major log-wavelength                                */
+    const double *ys;           /* (E,P) log-flux; may be NULL for forward-only plans            */
+    const double *yivar;        /* (E,P) inverse variance; may be NULL for forward-only plans    */
+    const uint8_t *mask;        /* (E,P) 1 = ignore pixel; may be NULL (nothing masked)          */
+    int32_t n_components;
+    const jb_component_desc *components;
+    int64_t n_params;           /* length of params_all                                          */
+    double coefficient;         /* LossFunc.coefficient (loss.py:31)                             */
+    int32_t rows_per_group;     /* 0 = choose; rows accumulated on chip before a partial is written */
+    int32_t reserved;
+} jb_plan_desc;
+
+typedef struct jb_plan jb_plan;
+
+/* Numbers a caller needs for benchmarking and diagnostics. */
+typedef struct {
+    int64_t n_rows, n_pix, n_pix_padded;
+    int64_t n_params, n_fit;
+    int64_t n_tasks;              /* (row group x pixel tile) work items of the fused kernel       */
+    int32_t rows_per_group;
+    int32_t tile_pixels;
+    int64_t device_bytes;         /* HBM held by the plan                                          */
+    int64_t scratch_bytes;        /* of which per-evaluation scratch (partials)                     */
+    int64_t algorithmic_bytes;    /* E*P*25 + 4*M*8 + E*7*8 for the compiled model     */
+    int64_t kernel_launches;      /* kernels launched by this plan since creation                   */
+    int64_t evaluations;
+    int64_t serial_rows;          /* rows that needed the serial (conflict) path in the last eval   */
+} jb_plan_info_t;
+
+const char *jb_last_error(void);
+int jb_abi_version(void);
+int jb_device_count(void);   /* 0 when no CUDA device/driver is present */
+
+int jb_plan_create(const jb_plan_desc *desc, jb_plan **out);
+void jb_plan_destroy(jb_plan *plan);
+int jb_plan_info(const jb_plan *plan, jb_plan_info_t *info);
+
+/* Upload the current value of EVERY parameter (fixed ones are read from here; Model.p). */
+int jb_plan_set_params(jb_plan *plan, const double *params_all, int64_t n_params);
+/* Which entries of params_all are in fit mode, in get_parameters() order (model.py:478-495). */
+int jb_plan_set_fit(jb_plan *plan, const int64_t *fit_index, int64_t n_fit);
+
+/*
+ * One fused evaluation at the fit vector p_fit: loss (loss.py:47-75), gradient w.r.t. p_fit
+ * (model.py:228) if grad != NULL, both written to host memory after a stream sync.
+ */
+int jb_plan_eval(jb_plan *plan, const double *p_fit, int64_t n_fit, double *loss, double *grad);
+
+/*
+ * Same, device resident: d_p_fit (n_fit doubles, may be NULL to keep the current parameters) and
+ * d_out (1 + n_fit doubles: loss, gradient) are DEVICE pointers on the plan's device; work is
+ * enqueued on `stream` (a cudaStream_t; NULL = the plan's own stream) and NOT synchronised.
+ * Status problems found by the kernels are reported by the next jb_plan_check().
+ */
+int jb_plan_eval_device(jb_plan *plan, const double *d_p_fit, double *d_out, void *stream);
+int jb_plan_check(jb_plan *plan);
+
+/* model(p, xs[r], meta[r]) for every row -> (E,P) host array (Model.__call__, model.py:138-160).
+ * Pixels outside the knot grid give NaN. */
+int jb_plan_forward(jb_plan *plan, const double *p_fit, int64_t n_fit, double *model_out);
+
+/*
+ * Diagonal Fisher information of the ShiftingModel of component `component`
+ * (EpochSpecificModel.f_info, model.py:857-901) at the current parameters:
+ * F[k] = sum_{rows with key k} sum_pix where(~mask, (d model / d shift_k)^2 * yivar, 0).
+ */
+int jb_plan_fisher(jb_plan *plan, int32_t component, double *f_out, int64_t n_shift);
+
+/* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests). */
+int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JABBLE_B200_H */

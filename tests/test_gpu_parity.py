@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the reference's own
+source and against the oracle.  Needs a GPU: run with ``-m gpu`` on the B200 box.
+
+Tolerance (BASELINE.json north_star): relative 1e-10 in float64 on loss, gradient (norm-relative
+per parameter block) and Fisher information."""
+
+import json
+
+import numpy as np
+import pytest
+
+import wobble_jax_b200 as jabble
+from wobble_jax_b200 import engine, synth
+from oracle import jabble_oracle as O
+from helpers import (dataset_from_golden, load_golden, rel_err, set_fit, stellar_from_golden,
+                     wobble_from_golden)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _blocks(data):
+    db, mb = data.blockify()
+    return db, mb, {k: db[k] for k in ("xs", "ys", "yivar", "mask")}, {k: mb[k] for k in mb.keys()}
+
+
+def _grad_blocks(model, grad):
+    """Split a fit-vector gradient into per-leaf blocks (norm-relative comparison per block)."""
+    spec = engine.TreeSpec(model)
+    out, o = [], 0
+    for lf in spec.leaves:
+        if lf.node._fit:
+            out.append(grad[o:o + lf.size]); o += lf.size
+    assert o == len(grad)
+    return out
+
+
+def _check_grad(model, g_gpu, g_ref, tol=TOL):
+    for a, b in zip(_grad_blocks(model, g_gpu), _grad_blocks(model, g_ref)):
+        assert rel_err(a, b) < tol
+
+
+@pytest.mark.parametrize("name", ["wobble_p3.npz", "wobble_p2.npz", "wobble_p1.npz", "wobble_p3_keyed.npz"])
+def test_golden_wobble(name):
+    g = load_golden(name)
+    data = dataset_from_golden(g)
+    model, meta = wobble_from_golden(g)
+    db, mb, dbd, mbd = _blocks(data)
+    loss = jabble.loss.ChiSquare()
+    for ci, fits in enumerate(json.loads(str(g["cases"]))):
+        set_fit(model, fits)
+        p = g[f"wb_case{ci}_p"]
+        obj = engine.Objective(loss, model, db, mb)
+        val, grad = obj.value(p), obj.gradient(p)
+        assert abs(val - float(g[f"wb_case{ci}_loss"])) <= TOL * abs(val), (name, ci)
+        _check_grad(model, grad, g[f"wb_case{ci}_grad"])
+        # same through the reference-facing callables
+        assert loss.loss_all(p, db, mb, model, None, 3) == val
+        assert np.array_equal(loss.grad_all(p, db, mb, model, None, 3), grad)
+    # forward model of every row, stored parameters
+    model.fix()
+    plan = engine.build_plan(model, db, mb)
+    fwd = plan.forward()
+    keep = ~db["mask"]
+    assert rel_err(fwd[keep], g["forward"][keep]) < TOL
+    row = model([], data[2].xs, mb.ele(2))
+    assert rel_err(row, g["forward"][2, :len(row)]) < TOL
+    # RV Fisher information through the reference-facing API
+    F = model[0][0].f_info(model, data)
+    assert rel_err(F, g["f_info"]) < TOL
+    assert rel_err(jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0, 0]), g["rv_err"]) < TOL
+    assert rel_err(model[1][0].f_info(model, data), g["f_info_tell"]) < TOL
+    # coefficient (LossFunc.__mul__)
+    set_fit(model, [(0, 0), (1, 1)])
+    loss2 = jabble.loss.ChiSquare() * 0.37
+    obj = engine.Objective(loss2, model, db, mb)
+    p = np.asarray(model.get_parameters())
+    assert abs(obj.value(p) - float(g["coef_loss"])) <= TOL * abs(float(g["coef_loss"]))
+    _check_grad(model, obj.gradient(p), g["coef_grad"])
+
+
+def test_golden_stellar():
+    g = load_golden("stellar.npz")
+    data = dataset_from_golden(g)
+    model, meta = stellar_from_golden(g)
+    db, mb, dbd, mbd = _blocks(data)
+    loss = jabble.loss.ChiSquare()
+    for ci, fits in enumerate([[(1,)], [(0,)], [(0,), (1,)]]):
+        set_fit(model, fits)
+        p = g[f"st_case{ci}_p"]
+        obj = engine.Objective(loss, model, db, mb)
+        assert abs(obj.value(p) - float(g[f"st_case{ci}_loss"])) <= TOL * abs(obj.value(p))
+        _check_grad(model, obj.gradient(p), g[f"st_case{ci}_grad"])
+    model.fix()
+    assert rel_err(model[0].f_info(model, data), g["f_info"]) < TOL
+    assert rel_err(jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0]), g["rv_err"]) < TOL
+
+
+@pytest.mark.parametrize("p_val,E,P,kw", [
+    (3, 40, 1500, {}),
+    (2, 33, 700, {"ragged": True}),
+    (1, 17, 300, {"descending": True}),
+    (3, 70, 4096, {"ragged": True, "descending": True}),
+])
+def test_synthetic_vs_oracle(p_val, E, P, kw):
+    ch = synth.make_chunk(chunk=3, n_epochs=E, n_pix=P, p_val=p_val, n_lines=20, **kw)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    obj = engine.Objective(jabble.loss.ChiSquare(), model, db, mb)
+    val, grad = obj.value(p), obj.gradient(p)
+    oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    # bit-reproducible: same plan twice, and a fresh plan
+    obj._p = None
+    val2, grad2 = obj.value(p), obj.gradient(p)
+    assert val2 == val and np.array_equal(grad, grad2)
+    obj3 = engine.Objective(jabble.loss.ChiSquare(), model, db, mb)
+    assert obj3.value(p) == val and np.array_equal(obj3.gradient(p), grad)
+    # Fisher vs the analytic sum (the dense-Jacobian oracle is O(E*P*N): small case only)
+    if E * P <= 30000:
+        model.fix(); model[0][0].fit()
+        F = O.f_info(model[0][0].p, dbd, mbd, model)
+        assert rel_err(model[0][0].f_info(model, ch.data), F) < TOL
+
+
+def test_rows_per_group_invariance_and_serial_path():
+    """Dense pixels (many per knot interval) break the lane-disjointness assumption: the kernel
+    must fall back to its serial path and still match the oracle."""
+    ch = synth.make_chunk(chunk=1, n_epochs=12, n_pix=640, p_val=3, n_lines=10, pixel_step=0.05 * 4.3478e-6)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+    for G in (1, 5, 12):
+        plan = engine.build_plan(model, db, mb, rows_per_group=G)
+        val, grad = plan.eval(p)
+        assert abs(val - oval) <= TOL * abs(oval)
+        _check_grad(model, grad, ograd)
+        assert plan.info()["serial_rows"] > 0
+        plan.close()
+
+
+def test_out_of_range_is_an_error():
+    ch = synth.make_chunk(chunk=0, n_epochs=4, n_pix=256, p_val=3, n_lines=5)
+    model = synth.fit_all(ch.model)
+    model[0][0].p = model[0][0].p + 1.0        # shift the stellar grid far outside the knots
+    db, mb = ch.data.blockify()
+    with pytest.raises(ValueError, match="outside the knot grid"):
+        engine.Objective(jabble.loss.ChiSquare(), model, db, mb).value(np.asarray(model.get_parameters()))
+
+
+def test_optimize_reduces_loss_and_unpacks():
+    ch = synth.make_chunk(chunk=2, n_epochs=24, n_pix=768, p_val=3, n_lines=12)
+    model = ch.model
+    loss = jabble.loss.ChiSquare()
+    model.fix(); model.fit(0, 1); model.fit(1, 1)
+    db, mb = ch.data.blockify()
+    f0 = loss.loss_all(model.get_parameters(), db, mb, model, None, None)
+    x, f, d = model.optimize(loss, ch.data, None, None, 1000, options={"maxiter": 30})
+    assert f < f0 and d["funcalls"] >= 1
+    assert len(model.results) == 1 and model.results["funcalls"][0] == d["funcalls"]
+    assert np.array_equal(np.asarray(model.get_parameters()), x)     # _unpack wrote the solution back

@@ -1,0 +1,105 @@
+"""ctypes binding of libjabble_b200.so (the C ABI of include/jabble_b200.h).
+
+Loading fails loudly: there is no CPU path behind this package.
+"""
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjabble_b200.so")
+
+JB_ABI_VERSION = 1
+JB_OK = 0
+JB_ERR_BAD_ARG, JB_ERR_UNSUPPORTED, JB_ERR_CUDA = -1, -2, -3
+JB_ERR_OUT_OF_RANGE, JB_ERR_WINDOW, JB_ERR_NONFINITE = -4, -5, -6
+JB_COMP_SPLINE, JB_COMP_NORM_SPLINE = 0, 1
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+c_i64p = C.POINTER(C.c_int64)
+
+
+class ComponentDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("p_val", C.c_int32),
+        ("xp0", C.c_double), ("dx", C.c_double),
+        ("n_knots", C.c_int64), ("ctrl_offset", C.c_int64), ("n_ctrl_keys", C.c_int64),
+        ("ctrl_key", c_i32p),
+        ("shift_offset", C.c_int64), ("n_shift", C.c_int64), ("shift_key", c_i32p),
+        ("stretch_offset", C.c_int64), ("n_stretch", C.c_int64), ("stretch_key", c_i32p),
+    ]
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("n_rows", C.c_int64), ("n_pix", C.c_int64),
+        ("xs", c_f64p), ("ys", c_f64p), ("yivar", c_f64p), ("mask", c_u8p),
+        ("n_components", C.c_int32), ("components", C.POINTER(ComponentDesc)),
+        ("n_params", C.c_int64), ("coefficient", C.c_double),
+        ("rows_per_group", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_rows", "n_pix", "n_pix_padded", "n_params", "n_fit", "n_tasks")] + \
+               [("rows_per_group", C.c_int32), ("tile_pixels", C.c_int32)] + \
+               [(n, C.c_int64) for n in ("device_bytes", "scratch_bytes", "algorithmic_bytes",
+                                         "kernel_launches", "evaluations", "serial_rows")]
+
+
+#: every symbol include/jabble_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("jb_last_error", C.c_char_p, []),
+    ("jb_abi_version", C.c_int, []),
+    ("jb_device_count", C.c_int, []),
+    ("jb_plan_create", C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
+    ("jb_plan_destroy", None, [C.c_void_p]),
+    ("jb_plan_info", C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
+    ("jb_plan_set_params", C.c_int, [C.c_void_p, c_f64p, C.c_int64]),
+    ("jb_plan_set_fit", C.c_int, [C.c_void_p, c_i64p, C.c_int64]),
+    ("jb_plan_eval", C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p, c_f64p]),
+    ("jb_plan_eval_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("jb_plan_check", C.c_int, [C.c_void_p]),
+    ("jb_plan_forward", C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p]),
+    ("jb_plan_fisher", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64]),
+    ("jb_plan_grad_all", C.c_int, [C.c_void_p, c_f64p, C.c_int64]),
+]
+
+_lib = None
+
+
+class JabbleB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libjabble_b200 error {code}: {message}")
+        self.code = code
+
+
+def load():
+    """Load the library (once).  Raises if it has not been built: see __graft_entry__.build()."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python wobble_jax_b200/csrc/build.py` "
+            "(nvcc, sm_100a). This package has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.jb_abi_version() != JB_ABI_VERSION:
+        raise ImportError("libjabble_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != JB_OK:
+        msg = load().jb_last_error().decode("utf-8", "replace")
+        if rc in (JB_ERR_BAD_ARG, JB_ERR_UNSUPPORTED, JB_ERR_OUT_OF_RANGE, JB_ERR_WINDOW):
+            raise ValueError(f"libjabble_b200 error {rc}: {msg}")
+        raise JabbleB200Error(rc, msg)

@@ -1,0 +1,618 @@
+// libjabble_b200: host side of the C ABI declared in include/jabble_b200.h.
+//
+// A plan owns: the data block in HBM (canonicalised: every row ascending in x, padded to a
+// multiple of the 128-pixel warp tile), the flat parameter vector, the fit map, the scratch for
+// per-task partials, one CUDA stream.  An evaluation is five launches on that stream:
+//   k_scatter_params -> k_fused -> k_reduce_stage1 -> k_reduce_stage2 -> k_finish
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/jabble_b200.h"
+#include "jb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define JB_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(JB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct jb_plan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t E = 0, P = 0, ppad = 0;
+    int n_tiles = 0;
+    bool has_data = false;   // ys / yivar present
+    double coef = 1.0;
+
+    int n_comp = 0;
+    jb_component_desc desc[jb::kMaxComp];
+    jb::CompDev comp[jb::kMaxComp];
+
+    std::vector<DevBuf> bufs;   // everything cudaMalloc'ed, freed in destroy
+    int64_t device_bytes = 0, scratch_bytes = 0;
+
+    double *d_x = nullptr, *d_y = nullptr, *d_iv = nullptr;
+    uint8_t *d_mask = nullptr, *d_row_rev = nullptr;
+    double *d_txmin = nullptr, *d_txmax = nullptr;
+    int* d_row_perm = nullptr;
+    std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
+    std::vector<uint8_t> h_row_rev;
+
+    int64_t n_params = 0, n_fit = 0;
+    double *d_params = nullptr, *d_grad_all = nullptr, *d_fisher_all = nullptr;
+    std::vector<double> h_params;
+    bool params_set = false, sort_dirty = true;
+    int64_t* d_fit_map = nullptr;
+    double *d_pfit = nullptr, *d_out = nullptr;
+    double *h_pfit = nullptr, *h_out = nullptr;   // pinned
+    int *d_status = nullptr, *h_status = nullptr; // h pinned
+
+    int G = 0, n_groups = 0;
+    int64_t n_tasks = 0;
+    double *d_part = nullptr, *d_rowpart = nullptr, *d_tmp = nullptr, *d_rowsum = nullptr;
+    int* d_part_base = nullptr;
+    int64_t max_knots = 0;
+    int* d_key_ptr[jb::kMaxComp][2] = {};   // [comp][0 shift,1 stretch] CSR rowptr
+    int* d_key_rows[jb::kMaxComp][2] = {};
+    int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
+
+    int64_t launches = 0, evaluations = 0, serial_rows = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(jb_plan* pl, T** out, size_t count, bool scratch = false) {
+    DevBuf b;
+    b.bytes = std::max<size_t>(count * sizeof(T), 16);
+    JB_CUDA(cudaMalloc(&b.p, b.bytes));
+    pl->bufs.push_back(b);
+    pl->device_bytes += (int64_t)b.bytes;
+    if (scratch) pl->scratch_bytes += (int64_t)b.bytes;
+    *out = static_cast<T*>(b.p);
+    return JB_OK;
+}
+
+template <typename T>
+int dev_upload(jb_plan* pl, T** out, const std::vector<T>& h) {
+    int rc = dev_alloc(pl, out, h.size());
+    if (rc) return rc;
+    if (!h.empty()) JB_CUDA(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return JB_OK;
+}
+
+int choose_rows_per_group(int64_t E, int n_tiles, int requested) {
+    if (requested > 0) return (int)std::min<int64_t>(requested, std::max<int64_t>(E, 1));
+    // enough tasks to fill 148 SMs x 12 resident warps several times over, but as many rows per
+    // group as that allows: each task writes one gradient window however many rows it streamed
+    const int64_t want_tasks = 148LL * 12 * 4;
+    int64_t g = (E * n_tiles) / want_tasks;
+    g = std::max<int64_t>(1, std::min<int64_t>(g, 32));
+    return (int)std::min<int64_t>(g, std::max<int64_t>(E, 1));
+}
+
+int alloc_scratch(jb_plan* pl) {
+    // (re)allocate the buffers whose size depends on rows_per_group
+    pl->n_groups = (int)((pl->E + pl->G - 1) / pl->G);
+    pl->n_tasks = (int64_t)pl->n_groups * pl->n_tiles;
+    int rc;
+    if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_comp * pl->n_tasks * jb::kWinCap, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_comp * pl->n_tasks, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_comp * pl->n_groups * pl->max_knots, true))) return rc;
+    return JB_OK;
+}
+
+// Sort rows by (smallest unmasked x) - (shift of the first component that has one), so that the
+// rows of a group land on nearly the same knots and the on-chip window stays small.
+int resort_rows(jb_plan* pl) {
+    std::vector<double> key(pl->E);
+    const jb_component_desc* sc = nullptr;
+    for (int c = 0; c < pl->n_comp; ++c)
+        if (pl->desc[c].shift_offset >= 0) { sc = &pl->desc[c]; break; }
+    std::vector<int> skey;
+    if (sc && pl->params_set && pl->d_keys[sc - pl->desc][0]) {
+        skey.resize(pl->E);
+        JB_CUDA(cudaMemcpy(skey.data(), pl->d_keys[sc - pl->desc][0], pl->E * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    for (int64_t r = 0; r < pl->E; ++r) {
+        double k = pl->h_xfirst[r];
+        if (!skey.empty()) k -= pl->h_params[sc->shift_offset + skey[r]];
+        key[r] = k;
+    }
+    std::vector<int> perm(pl->E);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    JB_CUDA(cudaMemcpyAsync(pl->d_row_perm, perm.data(), pl->E * sizeof(int), cudaMemcpyHostToDevice, pl->stream));
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    pl->sort_dirty = false;
+    return JB_OK;
+}
+
+template <int NC, int PV>
+int launch_fused_t(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
+    const size_t smem = (size_t)jb::kWarpsPerBlock * NC * jb::kClasses * jb::kWinCap * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int64_t blocks = (pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock;
+    jb::k_fused<NC, PV><<<(unsigned)blocks, jb::kWarpsPerBlock * 32, smem, st>>>(fp);
+    JB_CUDA(cudaGetLastError());
+    pl->launches++;
+    return JB_OK;
+}
+
+int launch_fused(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
+    const int pv = pl->desc[0].p_val;
+    switch (pl->n_comp * 10 + pv) {
+        case 11: return launch_fused_t<1, 1>(pl, fp, st);
+        case 12: return launch_fused_t<1, 2>(pl, fp, st);
+        case 13: return launch_fused_t<1, 3>(pl, fp, st);
+        case 21: return launch_fused_t<2, 1>(pl, fp, st);
+        case 22: return launch_fused_t<2, 2>(pl, fp, st);
+        case 23: return launch_fused_t<2, 3>(pl, fp, st);
+    }
+    return fail(JB_ERR_UNSUPPORTED, "no fused kernel for %d components of degree %d", pl->n_comp, pv);
+}
+
+int check_supported_for_eval(const jb_plan* pl) {
+    if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
+    for (int c = 0; c < pl->n_comp; ++c) {
+        if (pl->desc[c].kind != JB_COMP_SPLINE)
+            return fail(JB_ERR_UNSUPPORTED, "component %d: per-key (normalisation) splines are not in the fused kernel yet", c);
+        if (pl->desc[c].p_val != pl->desc[0].p_val)
+            return fail(JB_ERR_UNSUPPORTED, "components with different spline degrees (%d vs %d)", pl->desc[c].p_val, pl->desc[0].p_val);
+    }
+    if (pl->n_comp > 2) return fail(JB_ERR_UNSUPPORTED, "more than two spline components");
+    return JB_OK;
+}
+
+void fill_reduce_params(jb_plan* pl, jb::ReduceParams& rp, double* d_out) {
+    memset(&rp, 0, sizeof rp);
+    rp.n_comp = pl->n_comp;
+    for (int c = 0; c < pl->n_comp; ++c) {
+        rp.comp[c] = pl->comp[c];
+        rp.ctrl_off[c] = pl->desc[c].ctrl_offset;
+        rp.shift_off[c] = pl->desc[c].shift_offset;
+        rp.stretch_off[c] = pl->desc[c].stretch_offset;
+        rp.n_shift[c] = pl->desc[c].shift_offset >= 0 ? (int)pl->desc[c].n_shift : 0;
+        rp.n_stretch[c] = pl->desc[c].stretch_offset >= 0 ? (int)pl->desc[c].n_stretch : 0;
+        rp.shift_rowptr[c] = pl->d_key_ptr[c][0];   rp.shift_rows[c] = pl->d_key_rows[c][0];
+        rp.stretch_rowptr[c] = pl->d_key_ptr[c][1]; rp.stretch_rows[c] = pl->d_key_rows[c][1];
+    }
+    rp.n_rows = pl->E; rp.n_tasks = pl->n_tasks; rp.n_tiles = pl->n_tiles; rp.n_groups = pl->n_groups;
+    rp.part = pl->d_part; rp.part_base = pl->d_part_base; rp.rowpart = pl->d_rowpart;
+    rp.tmp = pl->d_tmp; rp.rowsum = pl->d_rowsum; rp.max_knots = pl->max_knots;
+    rp.coef = pl->coef;
+    rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
+    rp.fit_map = pl->d_fit_map; rp.n_fit = pl->n_fit;
+    rp.out = d_out; rp.status = pl->d_status;
+}
+
+// Enqueue one evaluation on `st`.  d_p_fit may be null (keep current parameters).
+int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t st) {
+    int rc = check_supported_for_eval(pl);
+    if (rc) return rc;
+    if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "jb_plan_set_params has not been called");
+    if (pl->sort_dirty && (rc = resort_rows(pl))) return rc;
+
+    if (d_p_fit && pl->n_fit > 0) {
+        jb::ScatterParams sp{d_p_fit, pl->d_fit_map, pl->d_params, pl->n_fit};
+        jb::k_scatter_params<<<(unsigned)((pl->n_fit + 255) / 256), 256, 0, st>>>(sp);
+        pl->launches++;
+    }
+    jb::FusedParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.x = pl->d_x; fp.y = pl->d_y; fp.ivar = pl->d_iv; fp.mask = pl->d_mask;
+    fp.txmin = pl->d_txmin; fp.txmax = pl->d_txmax; fp.row_perm = pl->d_row_perm;
+    fp.n_rows = pl->E; fp.ppad = pl->ppad; fp.n_tiles = pl->n_tiles;
+    fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks;
+    fp.n_comp = pl->n_comp;
+    for (int c = 0; c < pl->n_comp; ++c) fp.comp[c] = pl->comp[c];
+    fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
+    fp.status = pl->d_status;
+    if ((rc = launch_fused(pl, fp, st))) return rc;
+
+    jb::ReduceParams rp;
+    fill_reduce_params(pl, rp, d_out);
+    const int NQ = 1 + jb::kRowQ * pl->n_comp;
+    const int tpb = 128;
+    const int nb_knot = (int)((pl->max_knots + tpb - 1) / tpb);
+    const int nb_ctrl = nb_knot * pl->n_groups * pl->n_comp;
+    const int nb_rows = (int)((pl->E * NQ + tpb - 1) / tpb);
+    jb::k_reduce_stage1<<<nb_ctrl + nb_rows, tpb, 0, st>>>(rp, nb_knot, nb_ctrl);
+    int64_t n2 = 0;
+    for (int c = 0; c < pl->n_comp; ++c) n2 += pl->comp[c].n_knots + rp.n_shift[c] + rp.n_stretch[c];
+    jb::k_reduce_stage2<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(rp);
+    jb::k_finish<<<(unsigned)(1 + (pl->n_fit + 1023) / 1024), 1024, 0, st>>>(rp);
+    JB_CUDA(cudaGetLastError());
+    pl->launches += 3;
+    pl->evaluations++;
+    return JB_OK;
+}
+
+int read_status(jb_plan* pl, cudaStream_t st, bool* window) {
+    JB_CUDA(cudaMemcpyAsync(pl->h_status, pl->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    const int bits = pl->h_status[0];
+    pl->serial_rows = pl->h_status[1];
+    if (window) *window = false;
+    if (bits || pl->h_status[1]) JB_CUDA(cudaMemsetAsync(pl->d_status, 0, 2 * sizeof(int), st));
+    if (bits & jb::kStatOutOfRange)
+        return fail(JB_ERR_OUT_OF_RANGE, "an unmasked warped pixel lies outside the knot grid of a spline component");
+    if (bits & jb::kStatWindow) {
+        if (window) *window = true;
+        return fail(JB_ERR_WINDOW, "knot window of a pixel tile exceeds %d knots (grid much finer than the pixels, or rows of one group far apart)", jb::kWinCap);
+    }
+    return JB_OK;
+}
+
+// Evaluate on the plan's stream and wait; d_p_fit null = at the current parameters.  Leaves
+// [loss, grad_fit] in pl->h_out.  Retries after a window overflow: first re-sort the rows with
+// the current parameters (the shifts may have drifted), then shrink the row groups.
+int eval_sync(jb_plan* pl, const double* d_p_fit) {
+    cudaStream_t st = pl->stream;
+    for (int attempt = 0;; ++attempt) {
+        int rc = enqueue_eval(pl, d_p_fit, pl->d_out, st);
+        if (rc) return rc;
+        JB_CUDA(cudaMemcpyAsync(pl->h_out, pl->d_out, (pl->n_fit + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        bool window = false;
+        rc = read_status(pl, st, &window);
+        if (rc == JB_OK) return JB_OK;
+        if (!window || attempt >= 6) return rc;
+        JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
+        if (attempt > 0) {
+            if (pl->G == 1) return rc;
+            pl->G = std::max(1, pl->G / 4);
+            int rc2 = alloc_scratch(pl);
+            if (rc2) return rc2;
+        }
+        int rc2 = resort_rows(pl);
+        if (rc2) return rc2;
+    }
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* jb_last_error(void) { return g_err.c_str(); }
+int jb_abi_version(void) { return JB_ABI_VERSION; }
+
+int jb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void jb_plan_destroy(jb_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    if (pl->stream) cudaStreamSynchronize(pl->stream);
+    for (auto& b : pl->bufs) cudaFree(b.p);
+    if (pl->h_pfit) cudaFreeHost(pl->h_pfit);
+    if (pl->h_out) cudaFreeHost(pl->h_out);
+    if (pl->h_status) cudaFreeHost(pl->h_status);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
+    if (!d || !out) return fail(JB_ERR_BAD_ARG, "null descriptor");
+    *out = nullptr;
+    if (d->abi_version != JB_ABI_VERSION) return fail(JB_ERR_BAD_ARG, "ABI version %d, library is %d", d->abi_version, JB_ABI_VERSION);
+    if (d->n_rows <= 0 || d->n_pix <= 0 || !d->xs) return fail(JB_ERR_BAD_ARG, "empty data block");
+    if (d->n_components < 1 || d->n_components > jb::kMaxComp || !d->components)
+        return fail(JB_ERR_UNSUPPORTED, "%d additive components (1..%d supported)", d->n_components, jb::kMaxComp);
+    if ((d->ys == nullptr) != (d->yivar == nullptr)) return fail(JB_ERR_BAD_ARG, "ys and yivar must both be given or both be NULL");
+    if (d->n_rows > INT_MAX / 2) return fail(JB_ERR_BAD_ARG, "too many rows");
+    for (int c = 0; c < d->n_components; ++c) {
+        const jb_component_desc& cd = d->components[c];
+        if (cd.p_val < 1 || cd.p_val > 3) return fail(JB_ERR_UNSUPPORTED, "component %d: spline degree %d (1..3 supported)", c, cd.p_val);
+        if (cd.kind != JB_COMP_SPLINE && cd.kind != JB_COMP_NORM_SPLINE) return fail(JB_ERR_BAD_ARG, "component %d: kind %d", c, cd.kind);
+        if (cd.n_knots < cd.p_val + 1 || !(cd.dx > 0) || !std::isfinite(cd.xp0)) return fail(JB_ERR_BAD_ARG, "component %d: bad knot grid", c);
+        const int64_t nctrl = cd.kind == JB_COMP_SPLINE ? cd.n_knots : cd.n_knots * cd.n_ctrl_keys;
+        if (cd.ctrl_offset < 0 || cd.ctrl_offset + nctrl > d->n_params) return fail(JB_ERR_BAD_ARG, "component %d: control points outside params_all", c);
+        if (cd.kind == JB_COMP_NORM_SPLINE && cd.n_ctrl_keys <= 0) return fail(JB_ERR_BAD_ARG, "component %d: n_ctrl_keys", c);
+        if (cd.shift_offset >= 0 && (cd.n_shift <= 0 || cd.shift_offset + cd.n_shift > d->n_params)) return fail(JB_ERR_BAD_ARG, "component %d: shift slot", c);
+        if (cd.stretch_offset >= 0 && (cd.n_stretch <= 0 || cd.stretch_offset + cd.n_stretch > d->n_params)) return fail(JB_ERR_BAD_ARG, "component %d: stretch slot", c);
+        if (cd.n_knots > INT_MAX / 2) return fail(JB_ERR_BAD_ARG, "component %d: too many knots", c);
+    }
+    int ndev = jb_device_count();
+    if (ndev <= 0) return fail(JB_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    if (d->device < 0 || d->device >= ndev) return fail(JB_ERR_BAD_ARG, "device %d of %d", d->device, ndev);
+    JB_CUDA(cudaSetDevice(d->device));
+
+    jb_plan* pl = new jb_plan;
+    struct Guard { jb_plan* p; ~Guard() { if (p) jb_plan_destroy(p); } } guard{pl};
+    pl->device = d->device;
+    JB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    const int64_t E = d->n_rows, P = d->n_pix;
+    pl->E = E; pl->P = P;
+    pl->ppad = (P + jb::kTile - 1) / jb::kTile * jb::kTile;
+    pl->n_tiles = (int)(pl->ppad / jb::kTile);
+    pl->has_data = d->ys != nullptr;
+    pl->coef = d->coefficient;
+    pl->n_comp = d->n_components;
+    pl->n_params = d->n_params;
+    const int64_t ppad = pl->ppad;
+
+    // ---- canonical copy of the block: ascending x per row, padded, padding masked -------------
+    std::vector<double> hx((size_t)E * ppad, 0.0), hy, hiv;
+    std::vector<uint8_t> hm((size_t)E * ppad, 1);
+    if (pl->has_data) { hy.assign((size_t)E * ppad, 0.0); hiv.assign((size_t)E * ppad, 0.0); }
+    pl->h_row_rev.assign(E, 0);
+    pl->h_xfirst.assign(E, INFINITY);
+    std::vector<double> txmin((size_t)E * pl->n_tiles, INFINITY), txmax((size_t)E * pl->n_tiles, -INFINITY);
+    for (int64_t r = 0; r < E; ++r) {
+        const double* xr = d->xs + r * P;
+        const uint8_t* mr = d->mask ? d->mask + r * P : nullptr;
+        int64_t first = -1, last = -1;
+        for (int64_t p = 0; p < P; ++p)
+            if (!mr || !mr[p]) { if (first < 0) first = p; last = p; }
+        const bool rev = first >= 0 && xr[last] < xr[first];
+        pl->h_row_rev[r] = rev;
+        for (int64_t p = 0; p < P; ++p) {
+            const int64_t src = rev ? P - 1 - p : p;
+            const size_t dst = (size_t)r * ppad + p;
+            const bool masked = mr && mr[src];
+            hx[dst] = xr[src];
+            hm[dst] = masked ? 1 : 0;
+            if (pl->has_data) { hy[dst] = d->ys[r * P + src]; hiv[dst] = d->yivar[r * P + src]; }
+            if (!masked) {
+                if (!std::isfinite(xr[src])) return fail(JB_ERR_BAD_ARG, "row %lld pixel %lld: unmasked x is not finite", (long long)r, (long long)src);
+                const size_t t = (size_t)r * pl->n_tiles + p / jb::kTile;
+                txmin[t] = std::min(txmin[t], xr[src]);
+                txmax[t] = std::max(txmax[t], xr[src]);
+                pl->h_xfirst[r] = std::min(pl->h_xfirst[r], xr[src]);
+            }
+        }
+    }
+    int rc;
+    if ((rc = dev_upload(pl, &pl->d_x, hx))) return rc;
+    if ((rc = dev_upload(pl, &pl->d_mask, hm))) return rc;
+    if (pl->has_data) {
+        if ((rc = dev_upload(pl, &pl->d_y, hy))) return rc;
+        if ((rc = dev_upload(pl, &pl->d_iv, hiv))) return rc;
+    }
+    if ((rc = dev_upload(pl, &pl->d_row_rev, pl->h_row_rev))) return rc;
+    if ((rc = dev_upload(pl, &pl->d_txmin, txmin))) return rc;
+    if ((rc = dev_upload(pl, &pl->d_txmax, txmax))) return rc;
+    std::vector<int> perm(E);
+    std::iota(perm.begin(), perm.end(), 0);
+    if ((rc = dev_upload(pl, &pl->d_row_perm, perm))) return rc;
+
+    // ---- components ---------------------------------------------------------------------------
+    if ((rc = dev_alloc(pl, &pl->d_params, (size_t)d->n_params))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_grad_all, (size_t)d->n_params))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_fisher_all, (size_t)d->n_params))) return rc;
+    JB_CUDA(cudaMemset(pl->d_params, 0, d->n_params * sizeof(double)));
+    JB_CUDA(cudaMemset(pl->d_grad_all, 0, d->n_params * sizeof(double)));
+    JB_CUDA(cudaMemset(pl->d_fisher_all, 0, d->n_params * sizeof(double)));
+    pl->h_params.assign(d->n_params, 0.0);
+    std::vector<int> ident(E);
+    std::iota(ident.begin(), ident.end(), 0);
+    for (int c = 0; c < pl->n_comp; ++c) {
+        const jb_component_desc& cd = d->components[c];
+        pl->desc[c] = cd;
+        pl->desc[c].ctrl_key = pl->desc[c].shift_key = pl->desc[c].stretch_key = nullptr;  // host pointers are not retained
+        jb::CompDev& cv = pl->comp[c];
+        memset(&cv, 0, sizeof cv);
+        cv.kind = cd.kind; cv.p_val = cd.p_val; cv.n_knots = (int)cd.n_knots;
+        cv.xp0 = cd.xp0; cv.inv_dx = 1.0 / cd.dx;
+        cv.ctrl = pl->d_params + cd.ctrl_offset;
+        pl->max_knots = std::max<int64_t>(pl->max_knots, cd.n_knots);
+        const int32_t* keys[3] = {cd.shift_key, cd.stretch_key, cd.ctrl_key};
+        const int64_t nkeys[3] = {cd.shift_offset >= 0 ? cd.n_shift : 0, cd.stretch_offset >= 0 ? cd.n_stretch : 0,
+                                  cd.kind == JB_COMP_NORM_SPLINE ? cd.n_ctrl_keys : 0};
+        for (int s = 0; s < 3; ++s) {
+            if (nkeys[s] == 0) continue;
+            std::vector<int> k(E);
+            for (int64_t r = 0; r < E; ++r) {
+                k[r] = keys[s] ? keys[s][r] : (int)r;
+                if (k[r] < 0 || k[r] >= nkeys[s]) return fail(JB_ERR_BAD_ARG, "component %d: key %d of row %lld outside [0,%lld)", c, k[r], (long long)r, (long long)nkeys[s]);
+            }
+            if ((rc = dev_upload(pl, &pl->d_keys[c][s], k))) return rc;
+            if (s < 2) {   // CSR key -> rows, rows ascending: the fixed order of the per-key sums
+                std::vector<int> ptr(nkeys[s] + 1, 0), rows(E);
+                for (int64_t r = 0; r < E; ++r) ptr[k[r] + 1]++;
+                for (int64_t i = 0; i < nkeys[s]; ++i) ptr[i + 1] += ptr[i];
+                std::vector<int> fillp(ptr.begin(), ptr.end() - 1);
+                for (int64_t r = 0; r < E; ++r) rows[fillp[k[r]]++] = (int)r;
+                if ((rc = dev_upload(pl, &pl->d_key_ptr[c][s], ptr))) return rc;
+                if ((rc = dev_upload(pl, &pl->d_key_rows[c][s], rows))) return rc;
+            }
+        }
+        if (cd.shift_offset >= 0) { cv.shift = pl->d_params + cd.shift_offset; cv.shift_key = pl->d_keys[c][0]; }
+        if (cd.stretch_offset >= 0) { cv.stretch = pl->d_params + cd.stretch_offset; cv.stretch_key = pl->d_keys[c][1]; }
+        if (cd.kind == JB_COMP_NORM_SPLINE) cv.ctrl_key = pl->d_keys[c][2];
+    }
+
+    // ---- scratch ------------------------------------------------------------------------------
+    const int NQ = 1 + jb::kRowQ * pl->n_comp;
+    pl->G = choose_rows_per_group(E, pl->n_tiles, d->rows_per_group);
+    if ((rc = dev_alloc(pl, &pl->d_rowpart, (size_t)E * pl->n_tiles * NQ, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_rowsum, (size_t)E * NQ, true))) return rc;
+    if ((rc = alloc_scratch(pl))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_status, 2))) return rc;
+    JB_CUDA(cudaMemset(pl->d_status, 0, 2 * sizeof(int)));
+    JB_CUDA(cudaMallocHost(&pl->h_status, 2 * sizeof(int)));
+    // a fit map of length zero until jb_plan_set_fit is called
+    if ((rc = dev_alloc(pl, &pl->d_fit_map, 1))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_pfit, 1))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_out, 1))) return rc;
+    JB_CUDA(cudaMallocHost(&pl->h_pfit, sizeof(double)));
+    JB_CUDA(cudaMallocHost(&pl->h_out, sizeof(double)));
+
+    guard.p = nullptr;
+    *out = pl;
+    return JB_OK;
+}
+
+int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
+    if (!pl || !info) return fail(JB_ERR_BAD_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    info->n_rows = pl->E; info->n_pix = pl->P; info->n_pix_padded = pl->ppad;
+    info->n_params = pl->n_params; info->n_fit = pl->n_fit;
+    info->n_tasks = pl->n_tasks; info->rows_per_group = pl->G; info->tile_pixels = jb::kTile;
+    info->device_bytes = pl->device_bytes; info->scratch_bytes = pl->scratch_bytes;
+    // x, y, ivar (8 B each) + 1-byte mask per pixel; read S,T and write their
+    // gradients; per row read shift/stretch and write their gradients, Fisher and row loss
+    int64_t knots = 0;
+    for (int c = 0; c < pl->n_comp; ++c)
+        knots += pl->desc[c].kind == JB_COMP_SPLINE ? pl->desc[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys;
+    info->algorithmic_bytes = pl->E * pl->P * 25 + 2 * knots * 8 + pl->E * 7 * 8;
+    info->kernel_launches = pl->launches; info->evaluations = pl->evaluations;
+    info->serial_rows = pl->serial_rows;
+    return JB_OK;
+}
+
+int jb_plan_set_params(jb_plan* pl, const double* params_all, int64_t n) {
+    if (!pl || !params_all) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (n != pl->n_params) return fail(JB_ERR_BAD_ARG, "n_params %lld, plan has %lld", (long long)n, (long long)pl->n_params);
+    JB_CUDA(cudaSetDevice(pl->device));
+    pl->h_params.assign(params_all, params_all + n);
+    JB_CUDA(cudaMemcpyAsync(pl->d_params, pl->h_params.data(), n * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    pl->params_set = true;
+    pl->sort_dirty = true;
+    return JB_OK;
+}
+
+int jb_plan_set_fit(jb_plan* pl, const int64_t* fit_index, int64_t n_fit) {
+    if (!pl || n_fit < 0 || (n_fit > 0 && !fit_index)) return fail(JB_ERR_BAD_ARG, "bad fit map");
+    for (int64_t i = 0; i < n_fit; ++i)
+        if (fit_index[i] < 0 || fit_index[i] >= pl->n_params) return fail(JB_ERR_BAD_ARG, "fit index %lld outside params_all", (long long)fit_index[i]);
+    JB_CUDA(cudaSetDevice(pl->device));
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    int rc;
+    if ((rc = dev_alloc(pl, &pl->d_fit_map, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_pfit, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_out, (size_t)n_fit + 1))) return rc;
+    if (n_fit) JB_CUDA(cudaMemcpy(pl->d_fit_map, fit_index, n_fit * sizeof(int64_t), cudaMemcpyHostToDevice));
+    cudaFreeHost(pl->h_pfit); cudaFreeHost(pl->h_out);
+    pl->h_pfit = pl->h_out = nullptr;
+    JB_CUDA(cudaMallocHost(&pl->h_pfit, std::max<int64_t>(n_fit, 1) * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&pl->h_out, (n_fit + 1) * sizeof(double)));
+    pl->n_fit = n_fit;
+    return JB_OK;
+}
+
+int jb_plan_eval_device(jb_plan* pl, const double* d_p_fit, double* d_out, void* stream) {
+    if (!pl || !d_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(pl->device));
+    return enqueue_eval(pl, d_p_fit, d_out, stream ? (cudaStream_t)stream : pl->stream);
+}
+
+int jb_plan_check(jb_plan* pl) {
+    if (!pl) return fail(JB_ERR_BAD_ARG, "null plan");
+    JB_CUDA(cudaSetDevice(pl->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    return read_status(pl, pl->stream, nullptr);
+}
+
+int jb_plan_eval(jb_plan* pl, const double* p_fit, int64_t n_fit, double* loss, double* grad) {
+    if (!pl || !loss) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (n_fit != pl->n_fit) return fail(JB_ERR_BAD_ARG, "n_fit %lld, plan expects %lld", (long long)n_fit, (long long)pl->n_fit);
+    if (n_fit > 0 && !p_fit) return fail(JB_ERR_BAD_ARG, "null p_fit");
+    JB_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    if (n_fit) {
+        memcpy(pl->h_pfit, p_fit, n_fit * sizeof(double));
+        JB_CUDA(cudaMemcpyAsync(pl->d_pfit, pl->h_pfit, n_fit * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    int rc = eval_sync(pl, n_fit ? pl->d_pfit : nullptr);
+    if (rc) return rc;
+    *loss = pl->h_out[0];
+    if (grad && n_fit) memcpy(grad, pl->h_out + 1, n_fit * sizeof(double));
+    if (!std::isfinite(*loss)) return fail(JB_ERR_NONFINITE, "loss is not finite");
+    return JB_OK;
+}
+
+int jb_plan_forward(jb_plan* pl, const double* p_fit, int64_t n_fit, double* model_out) {
+    if (!pl || !model_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (n_fit != 0 && n_fit != pl->n_fit) return fail(JB_ERR_BAD_ARG, "n_fit %lld, plan expects %lld", (long long)n_fit, (long long)pl->n_fit);
+    if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "jb_plan_set_params has not been called");
+    JB_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    if (n_fit) {
+        if (!p_fit) return fail(JB_ERR_BAD_ARG, "null p_fit");
+        memcpy(pl->h_pfit, p_fit, n_fit * sizeof(double));
+        JB_CUDA(cudaMemcpyAsync(pl->d_pfit, pl->h_pfit, n_fit * sizeof(double), cudaMemcpyHostToDevice, st));
+        jb::ScatterParams sp{pl->d_pfit, pl->d_fit_map, pl->d_params, n_fit};
+        jb::k_scatter_params<<<(unsigned)((n_fit + 255) / 256), 256, 0, st>>>(sp);
+        pl->launches++;
+    }
+    double* d_model = nullptr;
+    const size_t n = (size_t)pl->E * pl->P;
+    JB_CUDA(cudaMallocAsync(&d_model, n * sizeof(double), st));
+    jb::ForwardParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.x = pl->d_x; fp.row_rev = pl->d_row_rev; fp.out = d_model;
+    fp.n_rows = pl->E; fp.n_pix = pl->P; fp.ppad = pl->ppad; fp.n_comp = pl->n_comp;
+    for (int c = 0; c < pl->n_comp; ++c) fp.comp[c] = pl->comp[c];
+    const int64_t blocks = std::min<int64_t>((int64_t)((n + 255) / 256), 148LL * 16);
+    jb::k_forward<<<(unsigned)blocks, 256, 0, st>>>(fp);
+    pl->launches++;
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaMemcpyAsync(model_out, d_model, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaFreeAsync(d_model, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    return JB_OK;
+}
+
+int jb_plan_fisher(jb_plan* pl, int32_t component, double* f_out, int64_t n_shift) {
+    if (!pl || !f_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (component < 0 || component >= pl->n_comp) return fail(JB_ERR_BAD_ARG, "component %d", component);
+    const jb_component_desc& cd = pl->desc[component];
+    if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
+    if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
+    JB_CUDA(cudaSetDevice(pl->device));
+    int rc = eval_sync(pl, nullptr);
+    if (rc) return rc;
+    JB_CUDA(cudaMemcpy(f_out, pl->d_fisher_all + cd.shift_offset, n_shift * sizeof(double), cudaMemcpyDeviceToHost));
+    return JB_OK;
+}
+
+int jb_plan_grad_all(jb_plan* pl, double* grad_all, int64_t n) {
+    if (!pl || !grad_all) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (n != pl->n_params) return fail(JB_ERR_BAD_ARG, "n_params mismatch");
+    JB_CUDA(cudaSetDevice(pl->device));
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    JB_CUDA(cudaMemcpy(grad_all, pl->d_grad_all, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return JB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+"""Model tree -> flat plan -> C ABI calls.
+
+This is the host half of the drop-in boundary: it recognises the tree
+shapes the reference's recipes build (jabble/quickplay.py:131-236)
+
+    top      := component | AdditiveModel[component, ...]
+    component:= spline | CompositeModel[ShiftingModel?, spline, StretchingModel?]
+    spline   := CardinalSplineMixture | NormalizationModel(CardinalSplineMixture)
+
+lays every leaf's parameters out in one vector in DFS order (the order of
+``ContainerModel.get_parameters``, jabble/model.py:478-495, when everything is in fit mode) and
+hands data + descriptors to ``jb_plan_create``.  Anything outside the grammar raises
+``ValueError``: there is no CPU fallback.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import model as M
+
+
+class Leaf:
+    __slots__ = ("node", "offset", "size")
+
+    def __init__(self, node, offset, size):
+        self.node, self.offset, self.size = node, offset, size
+
+
+class TreeSpec:
+    """Flat description of a model tree."""
+
+    def __init__(self, root):
+        self.root = root
+        self.leaves = []        # DFS order
+        self.n_params = 0
+        self.components = []    # dicts: shift/spline/stretch leaves
+        self._walk(root)
+        tops = root.models if isinstance(root, M.AdditiveModel) else [root]
+        for top in tops:
+            self.components.append(self._component(top))
+        if len(self.components) > 3:
+            raise ValueError(f"{len(self.components)} additive components; the CUDA plan supports up to 3")
+
+    def _walk(self, node):
+        if isinstance(node, M.ContainerModel):
+            for m in node.models:
+                self._walk(m)
+            return
+        if isinstance(node, (M.EpochSpecificModel, M.CardinalSplineMixture, M.NormalizationModel)):
+            size = int(np.asarray(node.p).size)
+            self.leaves.append(Leaf(node, self.n_params, size))
+            self.n_params += size
+            return
+        raise ValueError(f"unsupported model node {type(node).__name__}")
+
+    def leaf_of(self, node):
+        for lf in self.leaves:
+            if lf.node is node:
+                return lf
+        raise KeyError(node)
+
+    def _component(self, top):
+        def flatten(n):
+            if isinstance(n, M.CompositeModel):
+                out = []
+                for m in n.models:
+                    out += flatten(m)
+                return out
+            if isinstance(n, M.AdditiveModel):
+                raise ValueError("an AdditiveModel nested below the top level is outside the supported grammar")
+            return [n]
+
+        chain = flatten(top)
+        comp = {"shift": None, "spline": None, "stretch": None}
+        for n in chain:
+            if isinstance(n, M.ShiftingModel):
+                if comp["spline"] is not None or comp["shift"] is not None:
+                    raise ValueError("component grammar is [ShiftingModel?, spline, StretchingModel?]")
+                comp["shift"] = n
+            elif isinstance(n, (M.CardinalSplineMixture, M.NormalizationModel)):
+                if comp["spline"] is not None:
+                    raise ValueError("two spline models in series are outside the supported grammar")
+                comp["spline"] = n
+            elif isinstance(n, M.StretchingModel):
+                if comp["spline"] is None or comp["stretch"] is not None:
+                    raise ValueError("component grammar is [ShiftingModel?, spline, StretchingModel?]")
+                comp["stretch"] = n
+            else:
+                raise ValueError(f"unsupported model node {type(n).__name__}")
+        if comp["spline"] is None:
+            raise ValueError("every additive component needs a CardinalSplineMixture or NormalizationModel")
+        sp = comp["spline"]
+        if isinstance(sp, M.NormalizationModel) and not isinstance(sp.model, M.CardinalSplineMixture):
+            raise ValueError("NormalizationModel over anything but a CardinalSplineMixture is unsupported")
+        return comp
+
+    # ----------------------------------------------------------------------------------------
+    def params_all(self):
+        out = np.empty(self.n_params, dtype=np.float64)
+        for lf in self.leaves:
+            out[lf.offset:lf.offset + lf.size] = np.asarray(lf.node.p, dtype=np.float64).reshape(-1)
+        return out
+
+    def fit_index(self):
+        idx = [np.arange(lf.offset, lf.offset + lf.size, dtype=np.int64) for lf in self.leaves if lf.node._fit]
+        return np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+
+    def signature(self):
+        sig = []
+        for comp in self.components:
+            sp = comp["spline"]
+            inner = sp.model if isinstance(sp, M.NormalizationModel) else sp
+            sig.append((type(sp).__name__, inner.p_val, id(inner.xs), inner.xs.shape,
+                        None if comp["shift"] is None else (comp["shift"].which_key, comp["shift"].p.size),
+                        None if comp["stretch"] is None else (comp["stretch"].which_key, comp["stretch"].p.size),
+                        getattr(sp, "which_key", None), getattr(sp, "size", None)))
+        return tuple(sig)
+
+
+def _key_array(metablock, key, n_rows, n_keys, what):
+    try:
+        col = metablock[key]
+    except KeyError:
+        raise ValueError(f"metablock has no column {key!r} needed by {what}")
+    arr = np.ascontiguousarray(np.asarray(col).reshape(-1), dtype=np.int32)
+    if arr.size != n_rows:
+        raise ValueError(f"metablock[{key!r}] has {arr.size} entries for {n_rows} rows")
+    if arr.size and (arr.min() < 0 or arr.max() >= n_keys):
+        raise ValueError(f"metablock[{key!r}] indexes outside the {n_keys} parameters of {what}")
+    return arr
+
+
+class Plan:
+    """Owner of one ``jb_plan`` (data block resident in HBM + compiled model)."""
+
+    def __init__(self, spec, xs, ys, yivar, mask, metablock, coefficient=1.0, device=0, rows_per_group=0):
+        lib = _lib.load()
+        self.lib = lib
+        self.spec = spec
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if xs.ndim != 2:
+            raise ValueError("xs must be (rows, pixels)")
+        E, P = xs.shape
+        self.shape = (E, P)
+        keep = [xs]
+        f64p = lambda a: a.ctypes.data_as(_lib.c_f64p)
+        desc = _lib.PlanDesc()
+        desc.abi_version = _lib.JB_ABI_VERSION
+        desc.device = int(device)
+        desc.n_rows, desc.n_pix = E, P
+        desc.xs = f64p(xs)
+        if ys is not None:
+            ys = np.ascontiguousarray(ys, dtype=np.float64)
+            yivar = np.ascontiguousarray(yivar, dtype=np.float64)
+            if ys.shape != xs.shape or yivar.shape != xs.shape:
+                raise ValueError("ys / yivar must have the shape of xs")
+            keep += [ys, yivar]
+            desc.ys, desc.yivar = f64p(ys), f64p(yivar)
+        if mask is not None:
+            mask = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+            if mask.shape != xs.shape:
+                raise ValueError("mask must have the shape of xs")
+            keep.append(mask)
+            desc.mask = mask.ctypes.data_as(_lib.c_u8p)
+        comps = (_lib.ComponentDesc * len(spec.components))()
+        i32p = lambda a: a.ctypes.data_as(_lib.c_i32p)
+        for cd, comp in zip(comps, spec.components):
+            sp = comp["spline"]
+            is_norm = isinstance(sp, M.NormalizationModel)
+            inner = sp.model if is_norm else sp
+            grid = np.asarray(inner.xs, dtype=np.float64).reshape(-1)
+            if grid.size < 2:
+                raise ValueError("a spline needs at least two knots")
+            lf = spec.leaf_of(sp)
+            cd.kind = _lib.JB_COMP_NORM_SPLINE if is_norm else _lib.JB_COMP_SPLINE
+            cd.p_val = int(inner.p_val)
+            cd.xp0 = float(grid[0])
+            cd.dx = float(grid[1] - grid[0])            # model.py:974
+            cd.n_knots = grid.size
+            cd.ctrl_offset = lf.offset
+            if is_norm:
+                if lf.size != sp.size * grid.size:
+                    raise ValueError("NormalizationModel.p must hold size * len(model.p) values")
+                cd.n_ctrl_keys = sp.size
+                k = _key_array(metablock, sp.which_key, E, sp.size, "NormalizationModel")
+                keep.append(k)
+                cd.ctrl_key = i32p(k)
+            elif lf.size != grid.size:
+                raise ValueError("CardinalSplineMixture.p must have the shape of its knot grid")
+            cd.shift_offset = cd.stretch_offset = -1
+            for name in ("shift", "stretch"):
+                node = comp[name]
+                if node is None:
+                    continue
+                nlf = spec.leaf_of(node)
+                k = _key_array(metablock, node.which_key, E, nlf.size, type(node).__name__)
+                keep.append(k)
+                setattr(cd, name + "_offset", nlf.offset)
+                setattr(cd, "n_" + name, nlf.size)
+                setattr(cd, name + "_key", i32p(k))
+        desc.n_components = len(spec.components)
+        desc.components = comps
+        desc.n_params = spec.n_params
+        desc.coefficient = float(coefficient)
+        desc.rows_per_group = int(rows_per_group)
+        handle = C.c_void_p()
+        _lib.check(lib.jb_plan_create(C.byref(desc), C.byref(handle)))
+        self.handle = handle
+        self.n_fit = 0
+        del keep
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.jb_plan_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    # ----------------------------------------------------------------------------------------
+    def set_params(self, params_all):
+        p = np.ascontiguousarray(params_all, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_set_params(self.handle, p.ctypes.data_as(_lib.c_f64p), p.size))
+
+    def set_fit(self, fit_index):
+        idx = np.ascontiguousarray(fit_index, dtype=np.int64)
+        _lib.check(self.lib.jb_plan_set_fit(self.handle, idx.ctypes.data_as(_lib.c_i64p), idx.size))
+        self.n_fit = idx.size
+
+    def sync_from_model(self):
+        """Upload the tree's current parameter values and fit flags."""
+        self.set_params(self.spec.params_all())
+        self.set_fit(self.spec.fit_index())
+
+    def eval(self, p_fit, want_grad=True):
+        p = np.ascontiguousarray(p_fit, dtype=np.float64).reshape(-1)
+        loss = C.c_double()
+        grad = np.empty(p.size, dtype=np.float64) if want_grad else None
+        _lib.check(self.lib.jb_plan_eval(
+            self.handle, p.ctypes.data_as(_lib.c_f64p), p.size, C.byref(loss),
+            grad.ctypes.data_as(_lib.c_f64p) if want_grad else None))
+        return loss.value, grad
+
+    def forward(self, p_fit=()):
+        p = np.ascontiguousarray(p_fit, dtype=np.float64).reshape(-1)
+        out = np.empty(self.shape, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_forward(self.handle, p.ctypes.data_as(_lib.c_f64p), p.size,
+                                            out.ctypes.data_as(_lib.c_f64p)))
+        return out
+
+    def fisher(self, component):
+        n = self.spec.leaf_of(self.spec.components[component]["shift"]).size
+        out = np.empty(n, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_fisher(self.handle, component, out.ctypes.data_as(_lib.c_f64p), n))
+        return out
+
+    def grad_all(self):
+        out = np.empty(self.spec.n_params, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_grad_all(self.handle, out.ctypes.data_as(_lib.c_f64p), out.size))
+        return out
+
+    def info(self):
+        info = _lib.PlanInfo()
+        _lib.check(self.lib.jb_plan_info(self.handle, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in _lib.PlanInfo._fields_}
+
+    def eval_device(self, d_p_fit_ptr, d_out_ptr, stream_ptr=0):
+        """Enqueue one evaluation with device-resident in/out (see jb_plan_eval_device)."""
+        _lib.check(self.lib.jb_plan_eval_device(self.handle, C.c_void_p(d_p_fit_ptr), C.c_void_p(d_out_ptr),
+                                                C.c_void_p(stream_ptr)))
+
+    def check(self):
+        _lib.check(self.lib.jb_plan_check(self.handle))
+
+
+def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_group=0):
+    spec = TreeSpec(model)
+    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
+                coefficient=coefficient, device=device, rows_per_group=rows_per_group)
+    plan.sync_from_model()
+    return plan
+
+
+class Objective:
+    """The (func, fprime) pair scipy receives in Model.optimize (jabble/model.py:226-232), backed by
+    one fused evaluation per distinct parameter vector."""
+
+    _cache = {}
+
+    def __init__(self, loss, model, datablock, metablock, device=0):
+        from . import loss as L
+        if not isinstance(loss, L.ChiSquare):
+            raise NotImplementedError(
+                f"{type(loss).__name__}: only ChiSquare runs on the CUDA path so far (SURVEY.md section 8f-1)")
+        self.plan = build_plan(model, datablock, metablock, coefficient=loss.coefficient, device=device)
+        self.n_evals = 0
+        self._p = None
+        self._f = None
+        self._g = None
+
+    @classmethod
+    def cached(cls, loss, model, datablock, metablock):
+        """Reuse the resident data block between loss_all / grad_all calls on the same objects;
+        parameters and fit flags are re-read from the model tree every time."""
+        key = (id(datablock), id(metablock), id(model), type(loss).__name__, float(loss.coefficient))
+        obj = cls._cache.get(key)
+        sig = TreeSpec(model).signature()
+        if obj is None or obj._sig != sig or obj._db is not datablock:
+            cls._cache.clear()          # one resident block at a time
+            obj = cls(loss, model, datablock, metablock)
+            obj._sig, obj._db = sig, datablock
+            cls._cache[key] = obj
+        else:
+            obj.plan.spec = TreeSpec(model)
+            obj.plan.sync_from_model()
+            obj._p = None
+        return obj
+
+    def _eval(self, p):
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        if self._p is None or p.shape != self._p.shape or not np.array_equal(p, self._p):
+            self._f, self._g = self.plan.eval(p)
+            self._p = p.copy()
+            self.n_evals += 1
+        return self._f, self._g
+
+    def value(self, p):
+        return self._eval(p)[0]
+
+    def gradient(self, p):
+        return self._eval(p)[1].copy()
+
+
+def _meta_value(meta, key):
+    try:
+        v = meta[key]
+    except (KeyError, TypeError):
+        raise ValueError(f"meta has no entry {key!r}")
+    return int(np.asarray(v).reshape(-1)[0])
+
+
+def evaluate_row(model, p, x, meta):
+    """``model(p, x, meta)`` for one row (jabble/model.py:138-160, 456-462, 730-736)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    if isinstance(model, M.EpochSpecificModel):
+        # a bare warp has no spline to evaluate: one subtraction / multiplication per pixel on the
+        # host (jabble/model.py:927, 946); not a hot-path operation
+        val = (p if len(p) else model.p)[_meta_value(meta, model.which_key)]
+        return x - val if isinstance(model, M.ShiftingModel) else val * x
+    spec = TreeSpec(model)
+    keys = {}
+    for lf in spec.leaves:
+        k = getattr(lf.node, "which_key", None)
+        if k is not None:
+            keys[k] = np.array([_meta_value(meta, k)], dtype=np.int32)
+    plan = Plan(spec, x[None, :], None, None, None, keys)
+    try:
+        plan.sync_from_model()
+        if len(p) not in (0, plan.n_fit):
+            raise ValueError(f"p has {len(p)} entries, the model has {plan.n_fit} parameters in fit mode")
+        return plan.forward(p)[0]
+    finally:
+        plan.close()
+
+
+def fisher_information(model, rv_model, datablock, metablock, device=0):
+    """EpochSpecificModel.f_info (jabble/model.py:857-901) for a ShiftingModel of the tree."""
+    spec = TreeSpec(model)
+    comp = None
+    for i, c in enumerate(spec.components):
+        if c["shift"] is rv_model:
+            comp = i
+    if comp is None:
+        raise ValueError("f_info: the model is not the ShiftingModel of any additive component of the tree")
+    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock, device=device)
+    try:
+        plan.sync_from_model()
+        return plan.fisher(comp)
+    finally:
+        plan.close()
