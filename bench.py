@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the fused loss+gradient+Fisher hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[3]): synthetic HARPS-like chunks of
+2,000 epochs x 4,096 pixels, WobbleModel tree (stellar + telluric cubic splines), shifts, both
+templates and airmass in fit mode; 64 chunks resident per GPU (13.1 GB of float64 inputs, far larger
+than the 126 MB L2, so every evaluation streams from HBM).  One "step" = one fused
+loss+gradient+Fisher evaluation of every chunk.  Chunks are independent fits: ranks share nothing
+and there is no data-path collective (weak scaling: 64 chunks per GPU at every N).
+
+Printed JSON (one line, rank 0): see the bench contract in the task statement; `value` is G
+epoch-pixels/s with parameters and outputs device-resident, `e2e` the same metric through the
+host-buffer C-ABI call (jb_plan_eval: p_fit H2D, loss+gradient D2H, every chunk, every step).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "loss+grad evals/s (G epoch-pixels/s) and % HBM peak at 1/2/4/8 B200"
+UNIT = "G epoch-pixels/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=64, help="chunks per GPU")
+    ap.add_argument("--epochs", type=int, default=2000)
+    ap.add_argument("--pixels", type=int, default=4096)
+    ap.add_argument("--p-val", type=int, default=3)
+    ap.add_argument("--rows-per-group", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_baseline(args, budget_s, nthreads=0):
+    """The oracle port (oracle/jb_oracle.c: plain-C restatement of the reference's arithmetic,
+    OpenMP over rows) on a bounded sample of the same workload: whole rows of chunk 0."""
+    from oracle import c_oracle
+    from wobble_jax_b200 import synth
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    cores = c_oracle.lib().jbo_max_threads() if nthreads <= 0 else nthreads
+    rows = min(args.epochs, max(8 * cores, 64))
+    ch = synth.make_chunk(0, n_epochs=rows, n_pix=args.pixels, p_val=args.p_val, as_block=True)
+    model = synth.fit_all(ch.model)
+    p = np.asarray(model.get_parameters())
+    t0 = time.perf_counter()
+    c_oracle.evaluate(p, ch.datablock, ch.metablock, model, nthreads=cores)
+    t1 = time.perf_counter() - t0
+    # grow the sample towards the time budget (bounded by one full chunk)
+    want = int(min(args.epochs, max(rows, rows * (budget_s / 4.0) / max(t1, 1e-6))))
+    if want > rows * 1.5:
+        rows = want
+        ch = synth.make_chunk(0, n_epochs=rows, n_pix=args.pixels, p_val=args.p_val, as_block=True)
+        model = synth.fit_all(ch.model)
+        p = np.asarray(model.get_parameters())
+        c_oracle.evaluate(p, ch.datablock, ch.metablock, model, nthreads=cores)   # warm-up
+    return ch, model, p, rows, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    ch, model, p, rows, cores = cpu_baseline(args, args.cpu_seconds)
+    for _ in range(max(args.warmup, 0)):
+        c_oracle.evaluate(p, ch.datablock, ch.metablock, model, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.evaluate(p, ch.datablock, ch.metablock, model, nthreads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    px = rows * args.pixels
+    value = px / dt / 1e9
+    sample = (f"{rows} epochs x {args.pixels} px of chunk 0 per step (1/{args.epochs * args.chunks / rows:.0f} of the "
+              f"{args.chunks}-chunk workload), fused loss+grad+Fisher, oracle/jb_oracle.c, OpenMP {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"synthetic {args.epochs} epochs x {args.pixels} px x {args.chunks} chunks per GPU "
+                        f"(BASELINE.json configs[3]), WobbleModel p_val={args.p_val}, shifts+templates+airmass in fit mode",
+            "epochs": args.epochs, "pixels": args.pixels, "chunks_per_gpu": args.chunks,
+            "parallelism": "chunk-sharded, no collective",
+            "cache": "inputs 13.1 GB per GPU >> 126 MB L2; parameters perturbed every step"}
+
+
+# ------------------------------------------------------------------------------------ own arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import wobble_jax_b200  # noqa: F401
+    from wobble_jax_b200 import engine, synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- build: generate chunks on host threads, upload each into its plan ------------------
+    t_setup = time.perf_counter()
+
+    def make(c):
+        ch = synth.make_chunk(rank * args.chunks + c, n_epochs=args.epochs, n_pix=args.pixels,
+                              p_val=args.p_val, as_block=True)
+        model = synth.fit_all(ch.model)
+        return ch, model
+
+    plans, p_host = [], []
+    nworkers = min(8, len(os.sched_getaffinity(0)), args.chunks)
+    with ThreadPoolExecutor(nworkers) as pool:
+        for ch, model in pool.map(make, range(args.chunks)):
+            spec = engine.TreeSpec(model)
+            plan = engine.Plan(spec, ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
+                               ch.datablock["mask"], ch.metablock, device=local_rank,
+                               rows_per_group=args.rows_per_group)
+            plan.sync_from_model()
+            plans.append(plan)
+            p_host.append(np.asarray(model.get_parameters()).copy())
+            del ch
+    info = plans[0].info()
+    n_fit = info["n_fit"]
+    setup_s = time.perf_counter() - t_setup
+
+    # device-resident parameters and outputs
+    d_p = [torch.from_numpy(p).cuda() for p in p_host]
+    d_out = [torch.empty(n_fit + 1, dtype=torch.float64, device="cuda") for _ in plans]
+    streams = [torch.cuda.ExternalStream(pl.stream()) for pl in plans]
+    main = torch.cuda.current_stream()
+
+    def step_device():
+        # fork: every plan's stream waits for the main stream; join: main waits for every plan
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for pl, s, dp, do in zip(plans, streams, d_p, d_out):
+            s.wait_event(ev)
+            with torch.cuda.stream(s):
+                dp.add_(1e-13)                       # new parameter vector every step
+            pl.eval_device(dp.data_ptr(), do.data_ptr())
+            done = torch.cuda.Event()
+            done.record(s)
+            main.wait_event(done)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    for pl in plans:
+        pl.check()
+    launches0 = sum(pl.info()["kernel_launches"] for pl in plans)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(main)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(main)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = sum(pl.info()["kernel_launches"] for pl in plans) - launches0
+    for pl in plans:
+        pl.check()
+    losses = [float(o[0]) for o in d_out]
+    assert all(np.isfinite(losses)), "non-finite loss"
+
+    # ---- roofline pass: the fused kernel alone, one chunk at a time, events around it -------
+    for pl in plans:
+        pl.profile(True)
+    torch.cuda.synchronize()
+    for _ in range(max(1, min(args.steps, 5))):
+        for pl, dp, do in zip(plans, d_p, d_out):
+            pl.eval_device(dp.data_ptr(), do.data_ptr())
+            torch.cuda.synchronize()
+    fused_ms, fused_n = 0.0, 0
+    for pl in plans:
+        ms, n = pl.profile_read()
+        fused_ms += ms; fused_n += n
+        pl.profile(False)
+    fused_avg_ms = fused_ms / max(fused_n, 1)
+
+    # ---- end to end through the host-buffer C-ABI call ---------------------------------------
+    grads = [np.empty(n_fit) for _ in plans]
+
+    def eval_host(i):
+        p_host[i] += 1e-13
+        f, g = plans[i].eval(p_host[i])
+        grads[i] = g
+        return f
+
+    with ThreadPoolExecutor(min(16, args.chunks)) as pool:
+        for _ in range(min(args.warmup, 2)):
+            list(pool.map(eval_host, range(len(plans))))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_losses = list(pool.map(eval_host, range(len(plans))))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    assert all(np.isfinite(host_losses))
+
+    # ---- reduce over ranks (max time) ---------------------------------------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    px_step = args.epochs * args.pixels * args.chunks * world
+    value = px_step * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_value = px_step * args.steps / (e2e_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    achieved = info["algorithmic_bytes"] / (fused_avg_ms * 1e-3) / 1e9
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "evals_per_s": args.chunks * world * args.steps / (dev_ms * 1e-3),
+        "hbm_frac_whole_step": (info["algorithmic_bytes"] * args.chunks * args.steps / (dev_ms * 1e-3) / 1e9) / peak,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_fit * args.chunks * world),
+                "d2h_bytes_per_step": int(8 * (n_fit + 1) * args.chunks * world),
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "jb_plan_eval (host p_fit in, host loss+gradient out), 16 host threads over the chunks"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": f"k_fused<2,{args.p_val}>", "kernel_ms": fused_avg_ms,
+                     "algorithmic_bytes_per_launch": int(info["algorithmic_bytes"]), "peak_source": peak_src,
+                     "timed": "CUDA events around the kernel on its stream, one chunk at a time (no overlap)"},
+        "plan": {k: info[k] for k in ("n_tasks", "rows_per_group", "tile_pixels", "device_bytes", "scratch_bytes", "n_fit")},
+        "setup_s": setup_s,
+        "loss_chunk0": losses[0],
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        ch, model, p, rows, cores = cpu_baseline(args, args.cpu_seconds)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            c_oracle.evaluate(p, ch.datablock, ch.metablock, model, nthreads=cores)
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {
+            "value": rows * args.pixels / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{rows} epochs x {args.pixels} px of chunk 0 ({reps} evals, {dt:.2f} s each), fused "
+                      f"loss+grad+Fisher in oracle/jb_oracle.c (plain-C restatement of the reference, OpenMP)"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != max(args.gpus, 1) and world != 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,18 @@ int jb_plan_fisher(jb_plan *plan, int32_t component, double *f_out, int64_t n_sh
 /* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests). */
 int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);
 
+/* The plan's own cudaStream_t (so that a caller can order its work, or time it with events). */
+int jb_plan_stream(jb_plan *plan, void **stream_out);
+
+/*
+ * Per-kernel timing for roofline reporting: while enabled, every evaluation records a CUDA event
+ * pair around the fused loss+gradient kernel on the launching stream.  jb_plan_profile_read waits
+ * for the stream, returns the summed duration (ms) and number of timed launches since the last
+ * read, and resets both.
+ */
+int jb_plan_profile(jb_plan *plan, int enable);
+int jb_plan_profile_read(jb_plan *plan, double *fused_ms_total, int64_t *n_launches);
+
 #ifdef __cplusplus
 }
 #endif

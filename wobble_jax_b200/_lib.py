@@ -66,6 +66,9 @@ SYMBOLS = [
     ("jb_plan_forward", C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p]),
     ("jb_plan_fisher", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64]),
     ("jb_plan_grad_all", C.c_int, [C.c_void_p, c_f64p, C.c_int64]),
+    ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("jb_plan_profile", C.c_int, [C.c_void_p, C.c_int]),
+    ("jb_plan_profile_read", C.c_int, [C.c_void_p, c_f64p, c_i64p]),
 ]
 
 _lib = None

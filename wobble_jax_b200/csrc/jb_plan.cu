@@ -87,6 +87,11 @@ struct jb_plan {
     int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
 
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
+
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // pool, reused
+    size_t prof_used = 0;
+    cudaStream_t prof_stream = nullptr;
 };
 
 namespace {
@@ -242,7 +247,21 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     for (int c = 0; c < pl->n_comp; ++c) fp.comp[c] = pl->comp[c];
     fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
     fp.status = pl->d_status;
+    if (pl->profiling) {
+        if (pl->prof_used == pl->prof_events.size()) {
+            cudaEvent_t a, b;
+            JB_CUDA(cudaEventCreate(&a));
+            JB_CUDA(cudaEventCreate(&b));
+            pl->prof_events.emplace_back(a, b);
+        }
+        JB_CUDA(cudaEventRecord(pl->prof_events[pl->prof_used].first, st));
+    }
     if ((rc = launch_fused(pl, fp, st))) return rc;
+    if (pl->profiling) {
+        JB_CUDA(cudaEventRecord(pl->prof_events[pl->prof_used].second, st));
+        pl->prof_used++;
+        pl->prof_stream = st;
+    }
 
     jb::ReduceParams rp;
     fill_reduce_params(pl, rp, d_out);
@@ -322,6 +341,7 @@ void jb_plan_destroy(jb_plan* pl) {
     cudaSetDevice(pl->device);
     if (pl->stream) cudaStreamSynchronize(pl->stream);
     for (auto& b : pl->bufs) cudaFree(b.p);
+    for (auto& e : pl->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (pl->h_pfit) cudaFreeHost(pl->h_pfit);
     if (pl->h_out) cudaFreeHost(pl->h_out);
     if (pl->h_status) cudaFreeHost(pl->h_status);
@@ -603,6 +623,34 @@ int jb_plan_fisher(jb_plan* pl, int32_t component, double* f_out, int64_t n_shif
     int rc = eval_sync(pl, nullptr);
     if (rc) return rc;
     JB_CUDA(cudaMemcpy(f_out, pl->d_fisher_all + cd.shift_offset, n_shift * sizeof(double), cudaMemcpyDeviceToHost));
+    return JB_OK;
+}
+
+int jb_plan_stream(jb_plan* pl, void** stream_out) {
+    if (!pl || !stream_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    *stream_out = (void*)pl->stream;
+    return JB_OK;
+}
+
+int jb_plan_profile(jb_plan* pl, int enable) {
+    if (!pl) return fail(JB_ERR_BAD_ARG, "null plan");
+    pl->profiling = enable != 0;
+    return JB_OK;
+}
+
+int jb_plan_profile_read(jb_plan* pl, double* fused_ms_total, int64_t* n_launches) {
+    if (!pl || !fused_ms_total || !n_launches) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(pl->device));
+    if (pl->prof_stream) JB_CUDA(cudaStreamSynchronize(pl->prof_stream));
+    double total = 0.0;
+    for (size_t i = 0; i < pl->prof_used; ++i) {
+        float ms = 0.f;
+        JB_CUDA(cudaEventElapsedTime(&ms, pl->prof_events[i].first, pl->prof_events[i].second));
+        total += ms;
+    }
+    *fused_ms_total = total;
+    *n_launches = (int64_t)pl->prof_used;
+    pl->prof_used = 0;
     return JB_OK;
 }
 

@@ -273,6 +273,21 @@ class Plan:
     def check(self):
         _lib.check(self.lib.jb_plan_check(self.handle))
 
+    def stream(self):
+        """The plan's cudaStream_t as an integer (for torch.cuda.ExternalStream / event ordering)."""
+        out = C.c_void_p()
+        _lib.check(self.lib.jb_plan_stream(self.handle, C.byref(out)))
+        return out.value or 0
+
+    def profile(self, enable=True):
+        _lib.check(self.lib.jb_plan_profile(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """(summed fused-kernel milliseconds, launches) since the last read."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self.lib.jb_plan_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
 
 def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_group=0):
     spec = TreeSpec(model)

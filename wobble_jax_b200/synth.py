@@ -35,6 +35,14 @@ def _lines_at(x, centers, depths, sigma):
     return out
 
 
+def _interp_uniform(xq, x0, h, table):
+    """Linear interpolation in a table sampled at x0 + h*i (np.interp without the binary search)."""
+    t = (xq - x0) * (1.0 / h)
+    i = np.clip(t.astype(np.int64), 0, len(table) - 2)
+    f = t - i
+    return table[i] * (1.0 - f) + table[i + 1] * f
+
+
 class Chunk:
     """One spectral chunk: the data, the model tree at the evaluation point, and the truth."""
 
@@ -44,7 +52,7 @@ class Chunk:
 
 def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=100, mask_frac=0.01,
                resolution=RESOLUTION, pixel_step=PIXEL_STEP, seed=20260101, descending=False,
-               ragged=False, dtype=np.float64):
+               ragged=False, as_block=False):
     """SURVEY.md section 8d "Synthetic inputs -- config 4", chunk ``chunk``.
 
     Returns a Chunk with ``data`` (Data), ``model`` (get_wobble_model tree at the evaluation point:
@@ -63,10 +71,14 @@ def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=1
     vel = 30e3 * np.sin(2 * np.pi * np.arange(E) / E) + rng.uniform(-200, 200, E)
     shift_true = physics.shifts(vel)
     airmass = rng.uniform(1.0, 2.0, E)
-    y = np.empty_like(x)
-    for e in range(E):
-        y[e] = _lines_at(x[e] - shift_true[e], s_cent, s_depth, sigma) + \
-            airmass[e] * _lines_at(x[e], t_cent, t_depth, sigma)
+    # both templates are tabulated once on a uniform grid of 1/32 knot and read back by linear
+    # interpolation: the interpolant IS the synthetic truth (smooth to ~1e-5, far below the noise)
+    fine = np.linspace(grid[0], grid[-1], 32 * (len(grid) - 1) + 1)
+    s_fine = _lines_at(fine, s_cent, s_depth, sigma)
+    t_fine = _lines_at(fine, t_cent, t_depth, sigma)
+    h = fine[1] - fine[0]
+    y = _interp_uniform(x - shift_true[:, None], fine[0], h, s_fine)
+    y += airmass[:, None] * _interp_uniform(x, fine[0], h, t_fine)
     y += rng.normal(0.0, 1.0 / snr, y.shape)
     yivar = np.full_like(x, snr ** 2)
     mask = rng.uniform(size=x.shape) < mask_frac
@@ -80,6 +92,18 @@ def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=1
     T0 = T_true + rng.normal(0, 0.01 / fact, grid.shape)
     shift0 = shift_true + rng.normal(0, float(physics.shifts(100.0)), E)
 
+    model = quickplay.get_wobble_model(np.zeros(E), airmass, grid, p_val)
+    model[0][0].p = shift0.copy()
+    model[0][1].p = S0
+    model[1][1].p = T0
+    truth = dict(vel=vel, shift=shift_true, airmass=airmass, S=S_true, T=T_true)
+    if as_block:
+        # what Data.blockify would return for equal-length ascending rows, without 4*E row copies
+        from .dataset import DataBlock
+        return Chunk(datablock=DataBlock(xs=x, ys=y, yivar=yivar, mask=mask),
+                     metablock=DataBlock(index=np.arange(E, dtype=int)), model=model, grid=grid,
+                     chunk=chunk, truth=truth)
+
     xs, ys, ivs, ms = [], [], [], []
     for e in range(E):
         sl = slice(0, int(lengths[e]))
@@ -88,12 +112,7 @@ def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=1
             row = [a[::-1].copy() for a in row]
         xs.append(row[0]); ys.append(row[1]); ivs.append(row[2]); ms.append(row[3])
     data = Data.from_lists(xs, ys, ivs, ms)
-    model = quickplay.get_wobble_model(np.zeros(E), airmass, grid, p_val)
-    model[0][0].p = shift0.copy()
-    model[0][1].p = S0
-    model[1][1].p = T0
-    return Chunk(data=data, model=model, grid=grid, chunk=chunk,
-                 truth=dict(vel=vel, shift=shift_true, airmass=airmass, S=S_true, T=T_true))
+    return Chunk(data=data, model=model, grid=grid, chunk=chunk, truth=truth)
 
 
 def fit_all(model):
