@@ -17,6 +17,9 @@ constexpr int kWinCap = 128;      // knots in a warp's on-chip gradient window
 constexpr int kClasses = 4;       // lane residue classes with private accumulator copies
 constexpr int kWarpsPerBlock = 4;
 constexpr int kRowQ = 3;          // per-component per-row sums: d/dshift, d/dstretch, Fisher
+constexpr int kStages = 4;        // rows in flight per warp (TMA bulk-copy ring)
+constexpr int kStageBytes = kTile * 8 * 3 + kTile;   // x, y, ivar (f64) + mask (u8) of one row tile
+constexpr int kMaxGroup = 32;     // rows per group: lane i keeps the parameters of row i
 
 // status bits written by kernels into plan->d_status[0]
 constexpr int kStatOutOfRange = 1;
@@ -88,11 +91,11 @@ template <> struct Basis<3> {
     __device__ __forceinline__ static void eval(double g, double (&w)[4], double (&dw)[3]) {
         const double a = 0.5 + g, b = 0.5 - g;
         const double ab = a * b;
-        const double q = 1.0 + ab;
+        const double q3 = __fma_rn(3.0, ab, 3.0);
         const double a2 = a * a, b2 = b * b;
         w[0] = b2 * b;
-        w[1] = __fma_rn(3.0 * b, q, 1.0);
-        w[2] = __fma_rn(3.0 * a, q, 1.0);
+        w[1] = __fma_rn(b, q3, 1.0);
+        w[2] = __fma_rn(a, q3, 1.0);
         w[3] = a2 * a;
         dw[0] = b2;
         dw[1] = __fma_rn(2.0, ab, 1.0);
@@ -112,6 +115,57 @@ __device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine), shared::cta addresses as 32-bit ------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "JB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra JB_DONE;\n"
+        "bra JB_WAIT;\n"
+        "JB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Sum NV (4 or 8) per-lane values over the warp with NV+1 shuffles instead of 5*NV: each step
+// halves the number of values a lane carries.  Afterwards lane L holds the total of value
+// q(L) = bits 4..(5-log2 NV) of L (replicated on the other lanes); fixed order -> deterministic.
+template <int NV>
+__device__ __forceinline__ double warp_sum_multi(double (&v)[NV], int lane) {
+    static_assert(NV == 4 || NV == 8, "NV");
+    int bit = 16;
+#pragma unroll
+    for (int n = NV / 2; n >= 1; n >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const double send = up ? v[i] : v[i + n];
+            const double keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+        bit >>= 1;
+    }
+    for (; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+    return v[0];
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -81,18 +81,26 @@ __global__ void k_forward(ForwardParams a) {
 // ------------------------------------------------------------------------------------------
 // Fused loss + gradient + Fisher.
 //
-// Work item ("task") = one warp, one tile of kTile pixel columns, one group of rows.  Lane l owns
-// pixel columns [4l, 4l+4) of the tile for every row of the group, so its pixels walk through the
-// knot intervals monotonically and the control-point adjoint of the current interval lives in
-// registers (a sliding window of p_val+1 accumulators).  A knot leaves the window when the lane
-// moves on; its sum is then added, with a plain shared-memory read-modify-write, to the warp's
-// on-chip gradient window.  Lanes whose knot ranges could overlap never share an accumulator:
-// there are kClasses copies of the window and lane l uses copy l % kClasses; the ranges of lanes
-// l and l+4 are checked to be disjoint per row (13 pixels apart), else the row takes the serial
-// path.  Every sum therefore has one fixed order: no float atomics, bit-reproducible.
+// Work item ("task") = one warp, one tile of kTile pixel columns, one group of <= 32 rows.
+//
+// Data movement: lane 0 issues, per row, four 1-D bulk async copies (TMA engine; x, y, ivar: 1 KB
+// each, mask: 128 B) into a kStages-deep ring in shared memory, completion counted on an mbarrier,
+// so kStages-1 rows are in flight per warp independent of occupancy.  The control points the task
+// can touch (a window of <= kWinCap knots per component) are copied to shared memory once.
+//
+// Arithmetic: lane l owns pixel columns [4l, 4l+4) of the tile for every row, so its pixels walk
+// through the knot intervals monotonically and the control-point adjoint of the current interval
+// lives in registers (a sliding window of p_val+1 accumulators).  A knot leaves the window when
+// the lane moves on; its sum is then added, with a plain shared-memory read-modify-write, to the
+// warp's gradient window.  Lanes whose knot ranges could overlap never share an accumulator:
+// there are kClasses copies of the window and lane l uses copy l % kClasses; lanes l and l+4 are
+// 13 pixels apart, and the plan marks (row, tile) pairs where that is not enough knots ("dense")
+// -- those rows run lane by lane.  Every sum has one fixed order: no float atomics,
+// bit-reproducible.
 struct FusedParams {
     const double* x; const double* y; const double* ivar; const uint8_t* mask;   // [E][ppad]
     const double* txmin; const double* txmax;   // [E][n_tiles] extent of the unmasked pixels of a tile
+    const uint8_t* dense;                       // [E][n_tiles] 1 = lanes of one class may share knots
     const int* row_perm;                        // rows sorted so that a group spans few knots
     int64_t n_rows, ppad;
     int n_tiles, rows_per_group, n_groups;
@@ -101,9 +109,16 @@ struct FusedParams {
     CompDev comp[kMaxComp];
     double* part;        // [n_comp][n_tasks][kWinCap] per-task gradient windows
     int* part_base;      // [n_comp][n_tasks] first knot of the window (INT_MAX: empty)
-    double* rowpart;     // [E][n_tiles][1 + kRowQ*n_comp]
+    double* rowpart;     // [E][n_tiles][NQP]   NQP = 4 (1 component) or 8 (2 components)
     int* status;         // [0] error bits  [1] rows that took the serial path
 };
+
+template <int NC> struct RowQ { static constexpr int NQP = (NC == 1) ? 4 : 8; };
+
+template <int NC>
+__host__ __device__ constexpr size_t fused_warp_smem() {
+    return (size_t)NC * kClasses * kWinCap * 8 + (size_t)NC * kWinCap * 8 + (size_t)kStages * kStageBytes + kStages * 8;
+}
 
 template <int PV>
 struct Run {
@@ -122,27 +137,27 @@ __device__ __forceinline__ void run_flush(Run<PV>& R, double* accw, int base) {
     R.valid = false;
 }
 
+// ctrlw: this component's control-point window in shared memory (index = knot - base)
 template <int PV>
-__device__ __forceinline__ void run_advance(Run<PV>& R, int klo_new, const double* __restrict__ ctrl,
-                                            double* accw, int base) {
+__device__ __forceinline__ void run_advance(Run<PV>& R, int klo_new, const double* ctrlw, double* accw, int base) {
     if (R.valid && klo_new == R.klo + 1) {
         accw[R.klo - base] += R.acc[0];
 #pragma unroll
         for (int j = 0; j < PV; ++j) { R.c[j] = R.c[j + 1]; R.acc[j] = R.acc[j + 1]; }
-        R.c[PV] = __ldg(ctrl + klo_new + PV);
+        R.c[PV] = ctrlw[klo_new + PV - base];
         R.acc[PV] = 0.0;
     } else {
         run_flush<PV>(R, accw, base);
 #pragma unroll
-        for (int j = 0; j <= PV; ++j) { R.c[j] = __ldg(ctrl + klo_new + j); R.acc[j] = 0.0; }
+        for (int j = 0; j <= PV; ++j) { R.c[j] = ctrlw[klo_new + j - base]; R.acc[j] = 0.0; }
         R.valid = true;
     }
     R.klo = klo_new;
 }
 
 template <int NC, int PV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_constant__ FusedParams a) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_constant__ FusedParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     if (task >= a.n_tasks) return;
@@ -150,35 +165,45 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_c
     const int group = (int)(task / a.n_tiles);
     const int row0 = group * a.rows_per_group;
     const int nrow = min(a.rows_per_group, (int)a.n_rows - row0);
-    constexpr int NQ = 1 + kRowQ * NC;
+    constexpr int NQP = RowQ<NC>::NQP;
 
-    // this warp's accumulator copies: [NC][kClasses][kWinCap]
-    double* acc_warp = smem + (size_t)warp * NC * kClasses * kWinCap;
+    unsigned char* wbase = smem_raw + (size_t)warp * fused_warp_smem<NC>();
+    double* acc_warp = reinterpret_cast<double*>(wbase);                     // [NC][kClasses][kWinCap]
+    double* ctrl_warp = acc_warp + NC * kClasses * kWinCap;                  // [NC][kWinCap]
+    unsigned char* ring = reinterpret_cast<unsigned char*>(ctrl_warp + NC * kWinCap);   // [kStages][kStageBytes]
+    const uint32_t bar0 = smem_u32(ring + (size_t)kStages * kStageBytes);    // [kStages] mbarriers
 
-    // ---- 1. knot window of the task: min/max interval over the group's rows -------------------
+    // ---- 0. per-lane row record: lane i keeps row i of the group ------------------------------
+    int my_row = 0;
+    double my_sh[NC], my_st[NC];
+    uint32_t my_dense = 0;
     int lo[NC], hi[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; }
-    for (int i = lane; i < nrow; i += 32) {
-        const int r = a.row_perm[row0 + i];
+    for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; my_sh[c] = 0.0; my_st[c] = 1.0; }
+    if (lane < nrow) {
+        const int r = a.row_perm[row0 + lane];
+        my_row = r;
+        my_dense = a.dense[(int64_t)r * a.n_tiles + tile];
         const double xmin = a.txmin[(int64_t)r * a.n_tiles + tile];
         const double xmax = a.txmax[(int64_t)r * a.n_tiles + tile];
-        if (xmin <= xmax) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const CompDev& cd = a.comp[c];
-                const double sh = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
+        for (int c = 0; c < NC; ++c) {
+            const CompDev& cd = a.comp[c];
+            if (cd.shift) my_sh[c] = cd.shift[cd.shift_key[r]];
+            if (cd.stretch) my_st[c] = cd.stretch[cd.stretch_key[r]];
+            if (xmin <= xmax) {
                 double g; int I0, I1;
-                knot_coord<PV>(xmin, sh, cd.xp0, cd.inv_dx, g, I0);
-                knot_coord<PV>(xmax, sh, cd.xp0, cd.inv_dx, g, I1);
+                knot_coord<PV>(xmin, my_sh[c], cd.xp0, cd.inv_dx, g, I0);
+                knot_coord<PV>(xmax, my_sh[c], cd.xp0, cd.inv_dx, g, I1);
                 // guard the magic-number trick: coordinates must be far inside +-2^31
-                const double t0 = ((xmin - sh) - cd.xp0) * cd.inv_dx, t1 = ((xmax - sh) - cd.xp0) * cd.inv_dx;
+                const double t0 = ((xmin - my_sh[c]) - cd.xp0) * cd.inv_dx, t1 = ((xmax - my_sh[c]) - cd.xp0) * cd.inv_dx;
                 if (!(t0 > -1.0e9 && t1 < 1.0e9)) { I0 = -(1 << 30); I1 = (1 << 30); }
-                lo[c] = min(lo[c], knot_lo<PV>(I0));
-                hi[c] = max(hi[c], knot_lo<PV>(I1) + PV);
+                lo[c] = knot_lo<PV>(I0);
+                hi[c] = knot_lo<PV>(I1) + PV;
             }
         }
     }
+    // ---- 1. knot window of the task ---------------------------------------------------------
     bool bad_range = false, bad_window = false, empty = false;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -201,96 +226,82 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_c
         for (int c = 0; c < NC; ++c) a.part_base[(int64_t)c * a.n_tasks + task] = skip ? INT_MAX : lo[c];
     }
     if (skip) {   // nothing unmasked here (or an error): the row sums of this tile are zero
-        for (int i = lane; i < nrow * NQ; i += 32) {
-            const int r = a.row_perm[row0 + i / NQ];
-            a.rowpart[((int64_t)r * a.n_tiles + tile) * NQ + i % NQ] = 0.0;
+        for (int i = lane; i < nrow * NQP; i += 32) {
+            const int r = a.row_perm[row0 + i / NQP];
+            a.rowpart[((int64_t)r * a.n_tiles + tile) * NQP + i % NQP] = 0.0;
         }
         return;
     }
 
-    // ---- 2. zero the accumulator copies -------------------------------------------------------
+    // ---- 2. barriers, first copies, accumulators, control-point window ------------------------
+    const int64_t col = (int64_t)tile * kTile;
+    auto issue_row = [&](int i, int r) {      // lane 0 only
+        const int s = i % kStages;
+        const uint32_t bar = bar0 + 8 * s;
+        const uint32_t dst = smem_u32(ring + (size_t)s * kStageBytes);
+        const int64_t off = (int64_t)r * a.ppad + col;
+        mbar_expect_tx(bar, kStageBytes);
+        tma_load_1d(dst, a.x + off, kTile * 8, bar);
+        tma_load_1d(dst + kTile * 8, a.y + off, kTile * 8, bar);
+        tma_load_1d(dst + kTile * 16, a.ivar + off, kTile * 8, bar);
+        tma_load_1d(dst + kTile * 24, a.mask + off, kTile, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+        const int r = __shfl_sync(0xffffffffu, my_row, i);
+        if (lane == 0 && i < nrow) issue_row(i, r);
+    }
     for (int i = lane; i < NC * kClasses * kWinCap; i += 32) acc_warp[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int n = hi[c] - lo[c] + 1;
+        for (int k = lane; k < n; k += 32) ctrl_warp[c * kWinCap + k] = __ldg(a.comp[c].ctrl + lo[c] + k);
+    }
     __syncwarp();
 
     const int cls = lane & (kClasses - 1);
     Run<PV> run[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) run[c].valid = false;
+    int serial_rows = 0;
 
     // ---- 3. stream the rows of the group ------------------------------------------------------
-    const int64_t col = (int64_t)tile * kTile + lane * kPixPerLane;
-    double xv[4], yv[4], iv[4];
-    uint32_t mk;
-    {
-        const int64_t off = (int64_t)a.row_perm[row0] * a.ppad + col;
-        ldg256(a.x + off, xv); ldg256(a.y + off, yv); ldg256(a.ivar + off, iv);
-        mk = ldg32_stream(a.mask + off);
-    }
-    int serial_rows = 0;
     for (int i = 0; i < nrow; ++i) {
-        const int r = a.row_perm[row0 + i];
-        // software prefetch of the next row of the group
-        double xn[4], yn[4], in_[4];
-        uint32_t mn = 0;
-        if (i + 1 < nrow) {
-            const int64_t off = (int64_t)a.row_perm[row0 + i + 1] * a.ppad + col;
-            ldg256(a.x + off, xn); ldg256(a.y + off, yn); ldg256(a.ivar + off, in_);
-            mn = ldg32_stream(a.mask + off);
-        }
-
-        // per-row parameters
+        const int s = i % kStages;
+        const int r = __shfl_sync(0xffffffffu, my_row, i);
+        const bool dense = __shfl_sync(0xffffffffu, my_dense, i) != 0;
         double sh[NC], st[NC];
-        const double* ctrl[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const CompDev& cd = a.comp[c];
-            sh[c] = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
-            st[c] = cd.stretch ? cd.stretch[cd.stretch_key[r]] : 1.0;
-            ctrl[c] = cd.ctrl;
+            sh[c] = __shfl_sync(0xffffffffu, my_sh[c], i);
+            st[c] = __shfl_sync(0xffffffffu, my_st[c], i);
         }
+        mbar_wait(bar0 + 8 * s, (uint32_t)((i / kStages) & 1));
 
-        // knot coordinates of this lane's pixels and its knot range in this row
-        double g[NC][4];
-        int kl[NC][4];
-        int rlo[NC], rhi[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            rlo[c] = INT_MAX; rhi[c] = INT_MIN;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int I;
-                knot_coord<PV>(xv[j], sh[c], a.comp[c].xp0, a.comp[c].inv_dx, g[c][j], I);
-                kl[c][j] = knot_lo<PV>(I);
-                if (!((mk >> (8 * j)) & 0xffu)) { rlo[c] = min(rlo[c], kl[c][j]); rhi[c] = max(rhi[c], kl[c][j] + PV); }
-            }
-        }
-        // lanes l-4, l-8, ... share this lane's accumulator copy: their knot ranges must lie
-        // strictly below this lane's range
-        bool ok = true;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            int v = rhi[c];
-#pragma unroll
-            for (int o = kClasses; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v = max(v, t);
-            }
-            int prev = __shfl_up_sync(0xffffffffu, v, kClasses);
-            if (lane < kClasses) prev = INT_MIN;
-            if (rlo[c] <= rhi[c] && rlo[c] <= prev) ok = false;
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        if (!ok) ++serial_rows;
+        const unsigned char* stg = ring + (size_t)s * kStageBytes;
+        const double2* px = reinterpret_cast<const double2*>(stg) + lane * 2;
+        const double2* py = reinterpret_cast<const double2*>(stg + kTile * 8) + lane * 2;
+        const double2* pi = reinterpret_cast<const double2*>(stg + kTile * 16) + lane * 2;
+        const double2 x01 = px[0], x23 = px[1], y01 = py[0], y23 = py[1], i01 = pi[0], i23 = pi[1];
+        const uint32_t mk = reinterpret_cast<const uint32_t*>(stg + kTile * 24)[lane];
+        const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+        const double iv[4] = {i01.x, i01.y, i23.x, i23.y};
 
-        double s_loss = 0.0, s_q[NC][kRowQ];
+        double sums[NQP];
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-            for (int q = 0; q < kRowQ; ++q) s_q[c][q] = 0.0;
+        for (int q = 0; q < NQP; ++q) sums[q] = 0.0;
+        if (dense) ++serial_rows;
 
-        const int nturn = ok ? 1 : 32 / kClasses;
+        const int nturn = dense ? 32 / kClasses : 1;
         for (int turn = 0; turn < nturn; ++turn) {
-            if (ok || (lane / kClasses) == turn) {
+            if (!dense || (lane / kClasses) == turn) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if ((mk >> (8 * j)) & 0xffu) continue;       // masked pixel: a hole
@@ -298,31 +309,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_c
                     double m = 0.0;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
+                        double g; int I;
+                        knot_coord<PV>(xv[j], sh[c], a.comp[c].xp0, a.comp[c].inv_dx, g, I);
+                        const int kl = knot_lo<PV>(I);
                         double* accw = acc_warp + ((size_t)c * kClasses + cls) * kWinCap;
-                        if (!run[c].valid || kl[c][j] != run[c].klo)
-                            run_advance<PV>(run[c], kl[c][j], ctrl[c], accw, lo[c]);
+                        if (!run[c].valid || kl != run[c].klo)
+                            run_advance<PV>(run[c], kl, ctrl_warp + c * kWinCap, accw, lo[c]);
                         double dw[PV];
-                        Basis<PV>::eval(g[c][j], w[c], dw);
-                        double s = run[c].c[0] * w[c][0];
+                        Basis<PV>::eval(g, w[c], dw);
+                        double sv = run[c].c[0] * w[c][0];
                         double d = (run[c].c[1] - run[c].c[0]) * dw[0];
 #pragma unroll
-                        for (int k = 1; k <= PV; ++k) s = __fma_rn(run[c].c[k], w[c][k], s);
+                        for (int k = 1; k <= PV; ++k) sv = __fma_rn(run[c].c[k], w[c][k], sv);
 #pragma unroll
                         for (int k = 1; k < PV; ++k) d = __fma_rn(run[c].c[k + 1] - run[c].c[k], dw[k], d);
-                        S[c] = s; dS[c] = d;
-                        m = __fma_rn(st[c], s, m);                // StretchingModel / AdditiveModel
+                        S[c] = sv; dS[c] = d;
+                        m = __fma_rn(st[c], sv, m);               // StretchingModel / AdditiveModel
                     }
                     const double res = yv[j] - m;                 // ChiSquare, loss.py:169-171
                     const double wr = iv[j] * res;
-                    s_loss = __fma_rn(wr, res, s_loss);
+                    sums[0] = __fma_rn(wr, res, sums[0]);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const double q = wr * st[c];
 #pragma unroll
                         for (int k = 0; k <= PV; ++k) run[c].acc[k] = __fma_rn(q, w[c][k], run[c].acc[k]);
-                        s_q[c][0] = __fma_rn(q, dS[c], s_q[c][0]);              // -> d/d shift
-                        s_q[c][1] = __fma_rn(wr, S[c], s_q[c][1]);              // -> d/d stretch
-                        s_q[c][2] = __fma_rn(iv[j] * dS[c], dS[c], s_q[c][2]);  // -> Fisher
+                        sums[1 + c * kRowQ + 0] = __fma_rn(q, dS[c], sums[1 + c * kRowQ + 0]);              // d/d shift
+                        sums[1 + c * kRowQ + 1] = __fma_rn(wr, S[c], sums[1 + c * kRowQ + 1]);              // d/d stretch
+                        sums[1 + c * kRowQ + 2] = __fma_rn(iv[j] * dS[c], dS[c], sums[1 + c * kRowQ + 2]);  // Fisher
                     }
                 }
 #pragma unroll
@@ -332,26 +346,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_c
             __syncwarp();
         }
 
-        // per-row sums of this tile (fixed butterfly order)
-        s_loss = warp_sum(s_loss);
+        // per-row sums of this tile (fixed order); lane L ends up with value q = L >> (NQP == 8 ? 2 : 3)
+        const double tot = warp_sum_multi<NQP>(sums, lane);
+        constexpr int kShift = (NQP == 8) ? 2 : 3;
+        if ((lane & ((1 << kShift) - 1)) == 0) {
+            const int q = lane >> kShift;
+            double s2 = 1.0;                       // Fisher sums carry the squared stretch of the row
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-            for (int q = 0; q < kRowQ; ++q) s_q[c][q] = warp_sum(s_q[c][q]);
-        if (lane == 0) {
-            double* rp = a.rowpart + ((int64_t)r * a.n_tiles + tile) * NQ;
-            rp[0] = s_loss;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                rp[1 + c * kRowQ + 0] = s_q[c][0];
-                rp[1 + c * kRowQ + 1] = s_q[c][1];
-                rp[1 + c * kRowQ + 2] = s_q[c][2] * st[c] * st[c];
-            }
+            for (int c = 0; c < NC; ++c)
+                if (q == 1 + c * kRowQ + 2) s2 = st[c] * st[c];
+            const double v = tot * s2;
+            a.rowpart[((int64_t)r * a.n_tiles + tile) * NQP + q] = v;
         }
-
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { xv[j] = xn[j]; yv[j] = yn[j]; iv[j] = in_[j]; }
-        mk = mn;
+        // every lane has consumed stage s (the sums above depend on all of its data): refill it
+        __syncwarp();
+        if (i + kStages < nrow) {
+            const int rn = __shfl_sync(0xffffffffu, my_row, i + kStages);
+            if (lane == 0) issue_row(i + kStages, rn);
+        }
     }
 
     // ---- 4. fold the accumulator copies in a fixed order and publish the window ----------------
@@ -361,10 +373,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_fused(const __grid_c
         const double* ac = acc_warp + (size_t)c * kClasses * kWinCap;
         double* dst = a.part + ((int64_t)c * a.n_tasks + task) * kWinCap;
         for (int k = lane; k < kWinCap; k += 32) {
-            double s = ac[k];
+            double sacc = ac[k];
 #pragma unroll
-            for (int q = 1; q < kClasses; ++q) s += ac[q * kWinCap + k];
-            dst[k] = s;
+            for (int q = 1; q < kClasses; ++q) sacc += ac[q * kWinCap + k];
+            dst[k] = sacc;
         }
     }
     if (lane == 0 && serial_rows) atomicAdd(a.status + 1, serial_rows);
@@ -395,7 +407,7 @@ struct ReduceParams {
 // blocks [0, nb_ctrl): tmp[c][g][k] = sum over tiles of the group, in tile order, of the windows
 // covering knot k.  blocks [nb_ctrl, ...): rowsum[r][q] = sum over tiles of rowpart.
 __global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
-    const int NQ = 1 + kRowQ * a.n_comp;
+    const int NQ = a.n_comp == 1 ? 4 : 8;
     if ((int)blockIdx.x < nb_ctrl) {
         const int kb = blockIdx.x % nb_knot;
         const int g = (blockIdx.x / nb_knot) % a.n_groups;
@@ -428,7 +440,7 @@ __global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
 //   d loss / d stretch[k] = -coef * sum wr*S
 //   F[key]                = (PV/dx)^2 * sum ivar*(a*S')^2        (model.py:893-897; no coefficient)
 __global__ void k_reduce_stage2(ReduceParams a) {
-    const int NQ = 1 + kRowQ * a.n_comp;
+    const int NQ = a.n_comp == 1 ? 4 : 8;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int c = 0; c < a.n_comp; ++c) {
         const int M = a.comp[c].n_knots;
@@ -465,7 +477,7 @@ __global__ void k_reduce_stage2(ReduceParams a) {
 
 // Block 0: loss = 0.5 * coef * sum_rows rowsum[r][0], fixed-shape tree.  Other blocks: gather.
 __global__ void k_finish(ReduceParams a) {
-    const int NQ = 1 + kRowQ * a.n_comp;
+    const int NQ = a.n_comp == 1 ? 4 : 8;
     if (blockIdx.x == 0) {
         __shared__ double sh[1024];
         double s = 0.0;

@@ -62,7 +62,7 @@ struct jb_plan {
     int64_t device_bytes = 0, scratch_bytes = 0;
 
     double *d_x = nullptr, *d_y = nullptr, *d_iv = nullptr;
-    uint8_t *d_mask = nullptr, *d_row_rev = nullptr;
+    uint8_t *d_mask = nullptr, *d_row_rev = nullptr, *d_dense = nullptr;
     double *d_txmin = nullptr, *d_txmax = nullptr;
     int* d_row_perm = nullptr;
     std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
@@ -117,12 +117,12 @@ int dev_upload(jb_plan* pl, T** out, const std::vector<T>& h) {
 }
 
 int choose_rows_per_group(int64_t E, int n_tiles, int requested) {
-    if (requested > 0) return (int)std::min<int64_t>(requested, std::max<int64_t>(E, 1));
+    if (requested > 0) return (int)std::min<int64_t>(std::min(requested, jb::kMaxGroup), std::max<int64_t>(E, 1));
     // enough tasks to fill 148 SMs x 12 resident warps several times over, but as many rows per
     // group as that allows: each task writes one gradient window however many rows it streamed
     const int64_t want_tasks = 148LL * 12 * 4;
     int64_t g = (E * n_tiles) / want_tasks;
-    g = std::max<int64_t>(1, std::min<int64_t>(g, 32));
+    g = std::max<int64_t>(1, std::min<int64_t>(g, jb::kMaxGroup));
     return (int)std::min<int64_t>(g, std::max<int64_t>(E, 1));
 }
 
@@ -165,12 +165,8 @@ int resort_rows(jb_plan* pl) {
 
 template <int NC, int PV>
 int launch_fused_t(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
-    const size_t smem = (size_t)jb::kWarpsPerBlock * NC * jb::kClasses * jb::kWinCap * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>();
+    JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock;
     jb::k_fused<NC, PV><<<(unsigned)blocks, jb::kWarpsPerBlock * 32, smem, st>>>(fp);
     JB_CUDA(cudaGetLastError());
@@ -240,7 +236,7 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     jb::FusedParams fp;
     memset(&fp, 0, sizeof fp);
     fp.x = pl->d_x; fp.y = pl->d_y; fp.ivar = pl->d_iv; fp.mask = pl->d_mask;
-    fp.txmin = pl->d_txmin; fp.txmax = pl->d_txmax; fp.row_perm = pl->d_row_perm;
+    fp.txmin = pl->d_txmin; fp.txmax = pl->d_txmax; fp.dense = pl->d_dense; fp.row_perm = pl->d_row_perm;
     fp.n_rows = pl->E; fp.ppad = pl->ppad; fp.n_tiles = pl->n_tiles;
     fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks;
     fp.n_comp = pl->n_comp;
@@ -265,7 +261,7 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
 
     jb::ReduceParams rp;
     fill_reduce_params(pl, rp, d_out);
-    const int NQ = 1 + jb::kRowQ * pl->n_comp;
+    const int NQ = pl->n_comp == 1 ? 4 : 8;
     const int tpb = 128;
     const int nb_knot = (int)((pl->max_knots + tpb - 1) / tpb);
     const int nb_ctrl = nb_knot * pl->n_groups * pl->n_comp;
@@ -420,7 +416,34 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             }
         }
     }
+    // "dense" (row, tile) pairs: lanes l and l+4 (13 pixels apart) share an accumulator copy, which is
+    // safe when every unmasked pixel of lane l lies at least p_val+1 knots above every unmasked
+    // pixel of lanes l-4, l-8, ...  The knot distance of two pixels does not depend on the shift, so
+    // this is decided once, here, from x alone (with 1 % margin for rounding).
+    double need = 0.0;
+    for (int c = 0; c < d->n_components; ++c)
+        need = std::max(need, (d->components[c].p_val + 1.01) * d->components[c].dx);
+    std::vector<uint8_t> dense((size_t)E * pl->n_tiles, 0);
+    for (int64_t r = 0; r < E; ++r)
+        for (int t = 0; t < pl->n_tiles; ++t) {
+            double cmax[jb::kClasses];
+            for (int q = 0; q < jb::kClasses; ++q) cmax[q] = -INFINITY;
+            bool bad = false;
+            for (int l = 0; l < 32 && !bad; ++l) {
+                double lmin = INFINITY, lmax = -INFINITY;
+                for (int j = 0; j < jb::kPixPerLane; ++j) {
+                    const size_t i = (size_t)r * ppad + (size_t)t * jb::kTile + l * jb::kPixPerLane + j;
+                    if (!hm[i]) { lmin = std::min(lmin, hx[i]); lmax = std::max(lmax, hx[i]); }
+                }
+                if (lmin > lmax) continue;
+                double& cm = cmax[l % jb::kClasses];
+                if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
+                cm = std::max(cm, lmax);
+            }
+            dense[(size_t)r * pl->n_tiles + t] = bad;
+        }
     int rc;
+    if ((rc = dev_upload(pl, &pl->d_dense, dense))) return rc;
     if ((rc = dev_upload(pl, &pl->d_x, hx))) return rc;
     if ((rc = dev_upload(pl, &pl->d_mask, hm))) return rc;
     if (pl->has_data) {
@@ -481,7 +504,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     }
 
     // ---- scratch ------------------------------------------------------------------------------
-    const int NQ = 1 + jb::kRowQ * pl->n_comp;
+    const int NQ = pl->n_comp == 1 ? 4 : 8;
     pl->G = choose_rows_per_group(E, pl->n_tiles, d->rows_per_group);
     if ((rc = dev_alloc(pl, &pl->d_rowpart, (size_t)E * pl->n_tiles * NQ, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_rowsum, (size_t)E * NQ, true))) return rc;
