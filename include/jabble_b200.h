@@ -109,6 +109,12 @@ typedef struct {
     int64_t kernel_launches;      /* kernels launched by this plan since creation                   */
     int64_t evaluations;
     int64_t serial_rows;          /* rows that needed the serial (conflict) path in the last eval   */
+    int64_t tiles_smooth;         /* (row, tile) pairs on the branch-free path                       */
+    int64_t tiles_general;        /* ... on the general per-pixel path (pixels >= 1 knot apart)      */
+    int64_t tiles_serial;         /* ... walked lane by lane (lanes of a class may share knots)      */
+    int64_t tiles_empty;          /* ... without any weighted pixel                                  */
+    int32_t window_knots;         /* on-chip gradient window per warp and component                  */
+    int32_t reserved;
 } jb_plan_info_t;
 
 const char *jb_last_error(void);

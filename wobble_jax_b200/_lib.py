@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjabble_b200.so")
+# JABBLE_B200_LIB: load another build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get("JABBLE_B200_LIB") or os.path.join(_HERE, "libjabble_b200.so")
 
 JB_ABI_VERSION = 1
 JB_OK = 0
@@ -47,7 +48,9 @@ class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_rows", "n_pix", "n_pix_padded", "n_params", "n_fit", "n_tasks")] + \
                [("rows_per_group", C.c_int32), ("tile_pixels", C.c_int32)] + \
                [(n, C.c_int64) for n in ("device_bytes", "scratch_bytes", "algorithmic_bytes",
-                                         "kernel_launches", "evaluations", "serial_rows")]
+                                         "kernel_launches", "evaluations", "serial_rows", "tiles_smooth",
+                                         "tiles_general", "tiles_serial", "tiles_empty")] + \
+               [("window_knots", C.c_int32), ("reserved", C.c_int32)]
 
 
 #: every symbol include/jabble_b200.h declares: (name, restype, argtypes)

@@ -13,9 +13,15 @@ namespace jb {
 constexpr int kMaxComp = 3;       // additive components per plan
 constexpr int kTile = 128;        // pixels per warp tile
 constexpr int kPixPerLane = 4;    // consecutive pixels owned by one lane (one 256-bit load per array)
-constexpr int kWinCap = 128;      // knots in a warp's on-chip gradient window
+constexpr int kWinCapMax = 256;   // knots in a warp's on-chip gradient window: chosen per plan (multiple of 32)
 constexpr int kClasses = 4;       // lane residue classes with private accumulator copies
-constexpr int kWarpsPerBlock = 4;
+#ifndef JB_WARPS
+#define JB_WARPS 4
+#endif
+#ifndef JB_MAXREG
+#define JB_MAXREG 255
+#endif
+constexpr int kWarpsPerBlock = JB_WARPS;   // tasks per block
 constexpr int kRowQ = 3;          // per-component per-row sums: d/dshift, d/dstretch, Fisher
 constexpr int kStages = 4;        // rows in flight per warp (TMA bulk-copy ring)
 constexpr int kStageBytes = kTile * 8 * 3 + kTile;   // x, y, ivar (f64) + mask (u8) of one row tile

@@ -26,8 +26,18 @@ __global__ void k_scatter_params(ScatterParams a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Data layout in HBM ("tile-interleaved"): for every (row r, tile t) one contiguous record of
+//   x[kTile] | y[kTile] | ivar[kTile]      (3 * kTile doubles = 3072 B)
+// at offset (r * n_tiles + t) * kTileDoubles.  The mask is folded into the data at upload: a masked
+// or padded pixel gets ivar = 0, y = 0 and the x of the nearest weighted pixel before it in the row
+// (so it is evaluated on knots the lane already holds and contributes exactly 0 to every sum),
+// which is what where(~mask, ., 0) of ChiSquare does to value and cotangent.  The forward kernel
+// reads the original x from a separate row-major copy.
+constexpr int kTileDoubles = 3 * kTile;
+constexpr int kTileBytes = kTileDoubles * 8;
+
 struct ForwardParams {
-    const double* x;       // [E][ppad], canonical orientation
+    const double* x;       // [E][ppad] canonical orientation, original x of every pixel
     const uint8_t* row_rev;
     double* out;           // [E][n_pix], caller orientation
     int64_t n_rows, n_pix, ppad;
@@ -83,80 +93,222 @@ __global__ void k_forward(ForwardParams a) {
 //
 // Work item ("task") = one warp, one tile of kTile pixel columns, one group of <= 32 rows.
 //
-// Data movement: lane 0 issues, per row, four 1-D bulk async copies (TMA engine; x, y, ivar: 1 KB
-// each, mask: 128 B) into a kStages-deep ring in shared memory, completion counted on an mbarrier,
-// so kStages-1 rows are in flight per warp independent of occupancy.  The control points the task
-// can touch (a window of <= kWinCap knots per component) are copied to shared memory once.
+// Data movement: lane 0 issues ONE 3 KB bulk async copy (TMA engine) per row into a kStages-deep
+// ring in shared memory, completion counted on an mbarrier, so kStages-1 rows are in flight per
+// warp independent of occupancy.  The control points the task can touch (a window of <= wincap
+// knots per component) are copied to shared memory once per task and read from there per pixel.
 //
 // Arithmetic: lane l owns pixel columns [4l, 4l+4) of the tile for every row, so its pixels walk
 // through the knot intervals monotonically and the control-point adjoint of the current interval
-// lives in registers (a sliding window of p_val+1 accumulators).  A knot leaves the window when
-// the lane moves on; its sum is then added, with a plain shared-memory read-modify-write, to the
-// warp's gradient window.  Lanes whose knot ranges could overlap never share an accumulator:
-// there are kClasses copies of the window and lane l uses copy l % kClasses; lanes l and l+4 are
-// 13 pixels apart, and the plan marks (row, tile) pairs where that is not enough knots ("dense")
-// -- those rows run lane by lane.  Every sum has one fixed order: no float atomics,
-// bit-reproducible.
+// lives in registers: p_val+1 accumulators that slide (with selects, no branches) when the lane
+// moves to the next interval; the knot that leaves the window is added, with a plain
+// shared-memory read-modify-write, to the warp's gradient window.  Rows are walked in alternating
+// direction (pixels 0..3, then 3..0) so the accumulators carry over from row to row and nothing is
+// flushed at a row end.  Lanes whose knot ranges could overlap never share an accumulator copy:
+// there are kClasses copies and lane l uses copy l % kClasses; lanes l and l+4 are 13 pixels apart,
+// and (row, tile) pairs where that is not enough knots ("dense", decided at upload from x alone:
+// knot distances inside a row do not depend on the shift) are walked lane by lane.
+// Every sum has one fixed order: no float atomics, bit-reproducible.
 struct FusedParams {
-    const double* x; const double* y; const double* ivar; const uint8_t* mask;   // [E][ppad]
-    const double* txmin; const double* txmax;   // [E][n_tiles] extent of the unmasked pixels of a tile
-    const uint8_t* dense;                       // [E][n_tiles] 1 = lanes of one class may share knots
+    const double* data;                         // tile-interleaved x | y | ivar
+    const double* txmin; const double* txmax;   // [E][n_tiles] extent of the weighted pixels of a tile
+    const uint8_t* dense;                       // [E][n_tiles]
     const int* row_perm;                        // rows sorted so that a group spans few knots
-    int64_t n_rows, ppad;
+    int64_t n_rows;
     int n_tiles, rows_per_group, n_groups;
+    int wincap;          // knots per on-chip window (multiple of 32, <= kWinCapMax)
     int64_t n_tasks;
     int n_comp;
     CompDev comp[kMaxComp];
-    double* part;        // [n_comp][n_tasks][kWinCap] per-task gradient windows
+    double* part;        // [n_comp][n_tasks][wincap] per-task gradient windows
     int* part_base;      // [n_comp][n_tasks] first knot of the window (INT_MAX: empty)
-    double* rowpart;     // [E][n_tiles][NQP]   NQP = 4 (1 component) or 8 (2 components)
+    double* rowpart;     // [E][n_tiles][NQP]   per-row sums: (d/dshift, d/dstretch, Fisher) per component
+    double* losspart;    // [n_tasks] sum of ivar*res^2 of the task
     int* status;         // [0] error bits  [1] rows that took the serial path
 };
 
 template <int NC> struct RowQ { static constexpr int NQP = (NC == 1) ? 4 : 8; };
 
+template <int NC> struct alignas(16) RowRec { double sh[NC]; double st[NC]; int row; int dense; int pad_[2]; };
+
 template <int NC>
-__host__ __device__ constexpr size_t fused_warp_smem() {
-    return (size_t)NC * kClasses * kWinCap * 8 + (size_t)NC * kWinCap * 8 + (size_t)kStages * kStageBytes + kStages * 8;
+__host__ __device__ constexpr size_t fused_warp_smem(int wincap) {
+    return ((size_t)NC * kClasses * wincap * 8 + (size_t)NC * wincap * 8 + (size_t)kStages * kTileBytes +
+            (size_t)kMaxGroup * sizeof(RowRec<NC>) + kStages * 8 + 127) / 128 * 128;
 }
 
 template <int PV>
-struct Run {
-    double c[PV + 1];     // control points klo .. klo+PV
-    double acc[PV + 1];   // adjoint sums of those knots accumulated by this lane
+struct Acc {
+    double a[PV + 1];   // adjoint sums of knots klo .. klo+PV accumulated by this lane
     int klo;
-    bool valid;
 };
 
 template <int PV>
-__device__ __forceinline__ void run_flush(Run<PV>& R, double* accw, int base) {
-    if (R.valid) {
+__device__ __forceinline__ void acc_flush(Acc<PV>& A, double* accw, int base) {
 #pragma unroll
-        for (int j = 0; j <= PV; ++j) accw[R.klo + j - base] += R.acc[j];
-    }
-    R.valid = false;
+    for (int j = 0; j <= PV; ++j) { accw[A.klo + j - base] += A.a[j]; A.a[j] = 0.0; }
 }
 
-// ctrlw: this component's control-point window in shared memory (index = knot - base)
-template <int PV>
-__device__ __forceinline__ void run_advance(Run<PV>& R, int klo_new, const double* ctrlw, double* accw, int base) {
-    if (R.valid && klo_new == R.klo + 1) {
-        accw[R.klo - base] += R.acc[0];
-#pragma unroll
-        for (int j = 0; j < PV; ++j) { R.c[j] = R.c[j + 1]; R.acc[j] = R.acc[j + 1]; }
-        R.c[PV] = ctrlw[klo_new + PV - base];
-        R.acc[PV] = 0.0;
-    } else {
-        run_flush<PV>(R, accw, base);
-#pragma unroll
-        for (int j = 0; j <= PV; ++j) { R.c[j] = ctrlw[klo_new + j - base]; R.acc[j] = 0.0; }
-        R.valid = true;
+// Move the lane's window to the knots of its next pixel.  DIR = +1: the lane walks its pixels
+// upwards in x, -1: downwards.  The common case (same interval, or one interval further in the
+// walking direction) is branch-free: the knot that leaves the window is retired to shared memory
+// and the accumulators slide by one.
+template <int PV, int DIR>
+__device__ __forceinline__ void acc_move(Acc<PV>& A, int kl, double* accw, int base) {
+    const int d = kl - A.klo;
+    const bool step = d == DIR;
+    if (d != 0 && !step) {            // turn-around mismatch or a jump over several knots: rare
+        acc_flush<PV>(A, accw, base);
+        A.klo = kl;
     }
-    R.klo = klo_new;
+    if (step) {
+        if (DIR > 0) accw[A.klo - base] += A.a[0];
+        else accw[A.klo + PV - base] += A.a[PV];
+    }
+    if (DIR > 0) {
+#pragma unroll
+        for (int j = 0; j < PV; ++j) A.a[j] = step ? A.a[j + 1] : A.a[j];
+        A.a[PV] = step ? 0.0 : A.a[PV];
+    } else {
+#pragma unroll
+        for (int j = PV; j > 0; --j) A.a[j] = step ? A.a[j - 1] : A.a[j];
+        A.a[0] = step ? 0.0 : A.a[0];
+    }
+    A.klo += step ? DIR : 0;
+}
+
+template <int NC, int PV, int DIR>
+__device__ __forceinline__ void fused_pixel(double x, double y, double iv, const double (&sh)[NC], const double (&st)[NC],
+                                            const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
+                                            double* acc_cls, const int W, const int (&lo)[NC], double& loss,
+                                            double (&sums)[RowQ<NC>::NQP]) {
+    double w[NC][PV + 1], S[NC], dS[NC];
+    double m = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        double g; int I;
+        knot_coord<PV>(x, sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
+        acc_move<PV, DIR>(acc[c], knot_lo<PV>(I), acc_cls + c * kClasses * W, lo[c]);
+        const double* cw = ctrl_warp + c * W + (acc[c].klo - lo[c]);
+        double cv[PV + 1];
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) cv[k] = cw[k];
+        double dw[PV];
+        Basis<PV>::eval(g, w[c], dw);
+        double sv = cv[0] * w[c][0];
+        double d = (cv[1] - cv[0]) * dw[0];
+#pragma unroll
+        for (int k = 1; k <= PV; ++k) sv = __fma_rn(cv[k], w[c][k], sv);
+#pragma unroll
+        for (int k = 1; k < PV; ++k) d = __fma_rn(cv[k + 1] - cv[k], dw[k], d);
+        S[c] = sv; dS[c] = d;
+        m = __fma_rn(st[c], sv, m);                // StretchingModel / AdditiveModel
+    }
+    const double res = y - m;                      // ChiSquare, loss.py:169-171
+    const double wr = iv * res;
+    loss = __fma_rn(wr, res, loss);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const double q = wr * st[c];
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) acc[c].a[k] = __fma_rn(q, w[c][k], acc[c].a[k]);
+        sums[c * kRowQ + 0] = __fma_rn(q, dS[c], sums[c * kRowQ + 0]);              // d/d shift
+        sums[c * kRowQ + 1] = __fma_rn(wr, S[c], sums[c * kRowQ + 1]);              // d/d stretch
+        sums[c * kRowQ + 2] = __fma_rn(iv * dS[c], dS[c], sums[c * kRowQ + 2]);     // Fisher
+    }
+}
+
+// ---- fast path: rows whose consecutive pixels are less than one knot apart ("smooth" rows) ------
+// Inside such a row a lane's window either stays or moves by exactly one knot in the walking
+// direction, so the per-pixel code needs no branch: the slide is folded into the accumulation
+// (the addend of the FMA is the neighbour's accumulator when the window moved).
+template <int PV, int DIR>
+__device__ __forceinline__ void acc_reposition(Acc<PV>& A, int kl, double* accw, int base) {
+    // row start: bring the window to the first pixel of the row (usually already there)
+    if (kl != A.klo) {
+        acc_flush<PV>(A, accw, base);
+        A.klo = kl;
+    }
+}
+
+template <int NC, int PV, int DIR>
+__device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, const double (&sh)[NC], const double (&st)[NC],
+                                                 const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
+                                                 double* acc_cls, const int W, const int (&lo)[NC], double& loss,
+                                                 double (&sums)[RowQ<NC>::NQP]) {
+    double w[NC][PV + 1], S[NC], dS[NC];
+    bool step[NC];
+    double m = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        double g; int I;
+        knot_coord<PV>(x, sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
+        const int kl = knot_lo<PV>(I);
+        step[c] = kl != acc[c].klo;
+        double* accw = acc_cls + c * kClasses * W;
+        if (step[c]) {                              // retire the knot that leaves the window
+            if (DIR > 0) accw[acc[c].klo - lo[c]] += acc[c].a[0];
+            else accw[acc[c].klo + PV - lo[c]] += acc[c].a[PV];
+        }
+        acc[c].klo = kl;
+        const double* cw = ctrl_warp + c * W + (kl - lo[c]);
+        double cv[PV + 1];
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) cv[k] = cw[k];
+        double dw[PV];
+        Basis<PV>::eval(g, w[c], dw);
+        double sv = cv[0] * w[c][0];
+        double d = (cv[1] - cv[0]) * dw[0];
+#pragma unroll
+        for (int k = 1; k <= PV; ++k) sv = __fma_rn(cv[k], w[c][k], sv);
+#pragma unroll
+        for (int k = 1; k < PV; ++k) d = __fma_rn(cv[k + 1] - cv[k], dw[k], d);
+        S[c] = sv; dS[c] = d;
+        m = __fma_rn(st[c], sv, m);
+    }
+    const double res = y - m;
+    const double wr = iv * res;
+    loss = __fma_rn(wr, res, loss);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const double q = wr * st[c];
+        if (DIR > 0) {
+#pragma unroll
+            for (int k = 0; k < PV; ++k) acc[c].a[k] = __fma_rn(q, w[c][k], step[c] ? acc[c].a[k + 1] : acc[c].a[k]);
+            acc[c].a[PV] = __fma_rn(q, w[c][PV], step[c] ? 0.0 : acc[c].a[PV]);
+        } else {
+#pragma unroll
+            for (int k = PV; k > 0; --k) acc[c].a[k] = __fma_rn(q, w[c][k], step[c] ? acc[c].a[k - 1] : acc[c].a[k]);
+            acc[c].a[0] = __fma_rn(q, w[c][0], step[c] ? 0.0 : acc[c].a[0]);
+        }
+        sums[c * kRowQ + 0] = __fma_rn(q, dS[c], sums[c * kRowQ + 0]);
+        sums[c * kRowQ + 1] = __fma_rn(wr, S[c], sums[c * kRowQ + 1]);
+        sums[c * kRowQ + 2] = __fma_rn(iv * dS[c], dS[c], sums[c * kRowQ + 2]);
+    }
+}
+
+// the four pixels of a lane in walking order
+template <int NC, int PV, int DIR>
+__device__ __forceinline__ void fused_run_fast(const double (&xv)[4], const double (&yv)[4], const double (&iv)[4],
+                                               const double (&sh)[NC], const double (&st)[NC], const CompDev* comp,
+                                               Acc<PV> (&acc)[NC], const double* ctrl_warp, double* acc_cls, const int W,
+                                               const int (&lo)[NC], double& loss, double (&sums)[RowQ<NC>::NQP]) {
+    constexpr int j0 = DIR > 0 ? 0 : 3;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        double g; int I;
+        knot_coord<PV>(xv[j0], sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
+        acc_reposition<PV, DIR>(acc[c], knot_lo<PV>(I), acc_cls + c * kClasses * W, lo[c]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = DIR > 0 ? jj : 3 - jj;
+        fused_pixel_fast<NC, PV, DIR>(xv[j], yv[j], iv[j], sh, st, comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+    }
 }
 
 template <int NC, int PV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_constant__ FusedParams a) {
+__global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedParams a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
@@ -166,42 +318,44 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
     const int row0 = group * a.rows_per_group;
     const int nrow = min(a.rows_per_group, (int)a.n_rows - row0);
     constexpr int NQP = RowQ<NC>::NQP;
+    const int W = a.wincap;
 
-    unsigned char* wbase = smem_raw + (size_t)warp * fused_warp_smem<NC>();
-    double* acc_warp = reinterpret_cast<double*>(wbase);                     // [NC][kClasses][kWinCap]
-    double* ctrl_warp = acc_warp + NC * kClasses * kWinCap;                  // [NC][kWinCap]
-    unsigned char* ring = reinterpret_cast<unsigned char*>(ctrl_warp + NC * kWinCap);   // [kStages][kStageBytes]
-    const uint32_t bar0 = smem_u32(ring + (size_t)kStages * kStageBytes);    // [kStages] mbarriers
+    unsigned char* wbase = smem_raw + (size_t)warp * fused_warp_smem<NC>(W);
+    double* acc_warp = reinterpret_cast<double*>(wbase);                     // [NC][kClasses][W]
+    double* ctrl_warp = acc_warp + NC * kClasses * W;                        // [NC][W]
+    unsigned char* ring = reinterpret_cast<unsigned char*>(ctrl_warp + NC * W);   // [kStages][kTileBytes]
+    RowRec<NC>* recs = reinterpret_cast<RowRec<NC>*>(ring + (size_t)kStages * kTileBytes);
+    const uint32_t bar0 = smem_u32(recs + kMaxGroup);                        // [kStages] mbarriers
 
-    // ---- 0. per-lane row record: lane i keeps row i of the group ------------------------------
-    int my_row = 0;
-    double my_sh[NC], my_st[NC];
-    uint32_t my_dense = 0;
+    // ---- 0. lane i prepares the record of row i of the group ---------------------------------
     int lo[NC], hi[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; my_sh[c] = 0.0; my_st[c] = 1.0; }
+    for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; }
     if (lane < nrow) {
         const int r = a.row_perm[row0 + lane];
-        my_row = r;
-        my_dense = a.dense[(int64_t)r * a.n_tiles + tile];
+        RowRec<NC> rec;
+        rec.row = r;
+        rec.dense = a.dense[(int64_t)r * a.n_tiles + tile];
+        rec.pad_[0] = rec.pad_[1] = 0;
         const double xmin = a.txmin[(int64_t)r * a.n_tiles + tile];
         const double xmax = a.txmax[(int64_t)r * a.n_tiles + tile];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const CompDev& cd = a.comp[c];
-            if (cd.shift) my_sh[c] = cd.shift[cd.shift_key[r]];
-            if (cd.stretch) my_st[c] = cd.stretch[cd.stretch_key[r]];
+            rec.sh[c] = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
+            rec.st[c] = cd.stretch ? cd.stretch[cd.stretch_key[r]] : 1.0;
             if (xmin <= xmax) {
                 double g; int I0, I1;
-                knot_coord<PV>(xmin, my_sh[c], cd.xp0, cd.inv_dx, g, I0);
-                knot_coord<PV>(xmax, my_sh[c], cd.xp0, cd.inv_dx, g, I1);
+                knot_coord<PV>(xmin, rec.sh[c], cd.xp0, cd.inv_dx, g, I0);
+                knot_coord<PV>(xmax, rec.sh[c], cd.xp0, cd.inv_dx, g, I1);
                 // guard the magic-number trick: coordinates must be far inside +-2^31
-                const double t0 = ((xmin - my_sh[c]) - cd.xp0) * cd.inv_dx, t1 = ((xmax - my_sh[c]) - cd.xp0) * cd.inv_dx;
+                const double t0 = ((xmin - rec.sh[c]) - cd.xp0) * cd.inv_dx, t1 = ((xmax - rec.sh[c]) - cd.xp0) * cd.inv_dx;
                 if (!(t0 > -1.0e9 && t1 < 1.0e9)) { I0 = -(1 << 30); I1 = (1 << 30); }
                 lo[c] = knot_lo<PV>(I0);
                 hi[c] = knot_lo<PV>(I1) + PV;
             }
         }
+        recs[lane] = rec;
     }
     // ---- 1. knot window of the task ---------------------------------------------------------
     bool bad_range = false, bad_window = false, empty = false;
@@ -215,7 +369,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
         if (lo[c] > hi[c]) empty = true;
         else {
             if (lo[c] < 0 || hi[c] > a.comp[c].n_knots - 1) bad_range = true;
-            if (hi[c] - lo[c] + 1 > kWinCap) bad_window = true;
+            if (hi[c] - lo[c] + 1 > W) bad_window = true;
         }
     }
     const bool skip = empty || bad_range || bad_window;
@@ -224,8 +378,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
         else if (!empty && bad_window) atomicOr(a.status, kStatWindow);
 #pragma unroll
         for (int c = 0; c < NC; ++c) a.part_base[(int64_t)c * a.n_tasks + task] = skip ? INT_MAX : lo[c];
+        if (skip) a.losspart[task] = 0.0;
     }
-    if (skip) {   // nothing unmasked here (or an error): the row sums of this tile are zero
+    if (skip) {   // nothing weighted here (or an error): the row sums of this tile are zero
         for (int i = lane; i < nrow * NQP; i += 32) {
             const int r = a.row_perm[row0 + i / NQP];
             a.rowpart[((int64_t)r * a.n_tiles + tile) * NQP + i % NQP] = 0.0;
@@ -234,17 +389,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
     }
 
     // ---- 2. barriers, first copies, accumulators, control-point window ------------------------
-    const int64_t col = (int64_t)tile * kTile;
     auto issue_row = [&](int i, int r) {      // lane 0 only
         const int s = i % kStages;
         const uint32_t bar = bar0 + 8 * s;
-        const uint32_t dst = smem_u32(ring + (size_t)s * kStageBytes);
-        const int64_t off = (int64_t)r * a.ppad + col;
-        mbar_expect_tx(bar, kStageBytes);
-        tma_load_1d(dst, a.x + off, kTile * 8, bar);
-        tma_load_1d(dst + kTile * 8, a.y + off, kTile * 8, bar);
-        tma_load_1d(dst + kTile * 16, a.ivar + off, kTile * 8, bar);
-        tma_load_1d(dst + kTile * 24, a.mask + off, kTile, bar);
+        mbar_expect_tx(bar, kTileBytes);
+        tma_load_1d(smem_u32(ring + (size_t)s * kTileBytes), a.data + ((int64_t)r * a.n_tiles + tile) * kTileDoubles,
+                    kTileBytes, bar);
     };
     if (lane == 0) {
 #pragma unroll
@@ -252,98 +402,78 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
         mbar_fence_init();
     }
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < kStages; ++i) {
-        const int r = __shfl_sync(0xffffffffu, my_row, i);
-        if (lane == 0 && i < nrow) issue_row(i, r);
+    if (lane == 0) {
+        for (int i = 0; i < kStages && i < nrow; ++i) issue_row(i, recs[i].row);
     }
-    for (int i = lane; i < NC * kClasses * kWinCap; i += 32) acc_warp[i] = 0.0;
+    for (int i = lane; i < NC * kClasses * W; i += 32) acc_warp[i] = 0.0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int n = hi[c] - lo[c] + 1;
-        for (int k = lane; k < n; k += 32) ctrl_warp[c * kWinCap + k] = __ldg(a.comp[c].ctrl + lo[c] + k);
+        for (int k = lane; k < W; k += 32) ctrl_warp[c * W + k] = k < n ? __ldg(a.comp[c].ctrl + lo[c] + k) : 0.0;
     }
     __syncwarp();
 
-    const int cls = lane & (kClasses - 1);
-    Run<PV> run[NC];
+    double* acc_cls = acc_warp + (lane & (kClasses - 1)) * W;   // + c * kClasses * W per component
+    Acc<PV> acc[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) run[c].valid = false;
+    for (int c = 0; c < NC; ++c) {
+        acc[c].klo = lo[c];            // a valid (empty) window until the first pixel moves it
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) acc[c].a[k] = 0.0;
+    }
     int serial_rows = 0;
+    double loss = 0.0;
 
     // ---- 3. stream the rows of the group ------------------------------------------------------
     for (int i = 0; i < nrow; ++i) {
         const int s = i % kStages;
-        const int r = __shfl_sync(0xffffffffu, my_row, i);
-        const bool dense = __shfl_sync(0xffffffffu, my_dense, i) != 0;
-        double sh[NC], st[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            sh[c] = __shfl_sync(0xffffffffu, my_sh[c], i);
-            st[c] = __shfl_sync(0xffffffffu, my_st[c], i);
-        }
+        const RowRec<NC> rec = recs[i];
         mbar_wait(bar0 + 8 * s, (uint32_t)((i / kStages) & 1));
+        if (rec.dense == 2) {          // no weighted pixel in this row of the tile
+            if (lane < NQP) a.rowpart[((int64_t)rec.row * a.n_tiles + tile) * NQP + lane] = 0.0;
+            __syncwarp();
+            if (lane == 0 && i + kStages < nrow) issue_row(i + kStages, recs[i + kStages].row);
+            continue;
+        }
 
-        const unsigned char* stg = ring + (size_t)s * kStageBytes;
-        const double2* px = reinterpret_cast<const double2*>(stg) + lane * 2;
-        const double2* py = reinterpret_cast<const double2*>(stg + kTile * 8) + lane * 2;
-        const double2* pi = reinterpret_cast<const double2*>(stg + kTile * 16) + lane * 2;
-        const double2 x01 = px[0], x23 = px[1], y01 = py[0], y23 = py[1], i01 = pi[0], i23 = pi[1];
-        const uint32_t mk = reinterpret_cast<const uint32_t*>(stg + kTile * 24)[lane];
-        const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
-        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
-        const double iv[4] = {i01.x, i01.y, i23.x, i23.y};
+        const double2* px = reinterpret_cast<const double2*>(ring + (size_t)s * kTileBytes) + lane * 2;
+        const double2 x01 = px[0], x23 = px[1], y01 = px[kTile / 2], y23 = px[kTile / 2 + 1],
+                      i01 = px[kTile], i23 = px[kTile + 1];
 
         double sums[NQP];
 #pragma unroll
         for (int q = 0; q < NQP; ++q) sums[q] = 0.0;
-        if (dense) ++serial_rows;
+        const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+        const double wv[4] = {i01.x, i01.y, i23.x, i23.y};
 
-        const int nturn = dense ? 32 / kClasses : 1;
-        for (int turn = 0; turn < nturn; ++turn) {
-            if (!dense || (lane / kClasses) == turn) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if ((mk >> (8 * j)) & 0xffu) continue;       // masked pixel: a hole
-                    double w[NC][PV + 1], S[NC], dS[NC];
-                    double m = 0.0;
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        double g; int I;
-                        knot_coord<PV>(xv[j], sh[c], a.comp[c].xp0, a.comp[c].inv_dx, g, I);
-                        const int kl = knot_lo<PV>(I);
-                        double* accw = acc_warp + ((size_t)c * kClasses + cls) * kWinCap;
-                        if (!run[c].valid || kl != run[c].klo)
-                            run_advance<PV>(run[c], kl, ctrl_warp + c * kWinCap, accw, lo[c]);
-                        double dw[PV];
-                        Basis<PV>::eval(g, w[c], dw);
-                        double sv = run[c].c[0] * w[c][0];
-                        double d = (run[c].c[1] - run[c].c[0]) * dw[0];
-#pragma unroll
-                        for (int k = 1; k <= PV; ++k) sv = __fma_rn(run[c].c[k], w[c][k], sv);
-#pragma unroll
-                        for (int k = 1; k < PV; ++k) d = __fma_rn(run[c].c[k + 1] - run[c].c[k], dw[k], d);
-                        S[c] = sv; dS[c] = d;
-                        m = __fma_rn(st[c], sv, m);               // StretchingModel / AdditiveModel
+        if (rec.dense == 0) {
+            // smooth row: branch-free sliding
+            if ((i & 1) == 0) fused_run_fast<NC, PV, +1>(xv, yv, wv, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+            else fused_run_fast<NC, PV, -1>(xv, yv, wv, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+        } else {
+            // general row (pixels a knot or more apart, non-monotone x), lane by lane when the lanes
+            // of one class could touch the same knots (rec.dense & 1)
+            const bool serial = (rec.dense & 1) != 0;
+            if (serial) ++serial_rows;
+            const int nturn = serial ? 32 / kClasses : 1;
+            for (int turn = 0; turn < nturn; ++turn) {
+                if (!serial || (lane / kClasses) == turn) {
+#pragma unroll 1
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = (i & 1) ? 3 - jj : jj;
+                        const double xj = j == 0 ? xv[0] : j == 1 ? xv[1] : j == 2 ? xv[2] : xv[3];
+                        const double yj = j == 0 ? yv[0] : j == 1 ? yv[1] : j == 2 ? yv[2] : yv[3];
+                        const double wj = j == 0 ? wv[0] : j == 1 ? wv[1] : j == 2 ? wv[2] : wv[3];
+                        fused_pixel<NC, PV, +1>(xj, yj, wj, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
                     }
-                    const double res = yv[j] - m;                 // ChiSquare, loss.py:169-171
-                    const double wr = iv[j] * res;
-                    sums[0] = __fma_rn(wr, res, sums[0]);
+                    if (serial) {   // lanes take turns: nothing may stay in registers across turns
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const double q = wr * st[c];
-#pragma unroll
-                        for (int k = 0; k <= PV; ++k) run[c].acc[k] = __fma_rn(q, w[c][k], run[c].acc[k]);
-                        sums[1 + c * kRowQ + 0] = __fma_rn(q, dS[c], sums[1 + c * kRowQ + 0]);              // d/d shift
-                        sums[1 + c * kRowQ + 1] = __fma_rn(wr, S[c], sums[1 + c * kRowQ + 1]);              // d/d stretch
-                        sums[1 + c * kRowQ + 2] = __fma_rn(iv[j] * dS[c], dS[c], sums[1 + c * kRowQ + 2]);  // Fisher
+                        for (int c = 0; c < NC; ++c) acc_flush<PV>(acc[c], acc_cls + c * kClasses * W, lo[c]);
                     }
                 }
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    run_flush<PV>(run[c], acc_warp + ((size_t)c * kClasses + cls) * kWinCap, lo[c]);
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         // per-row sums of this tile (fixed order); lane L ends up with value q = L >> (NQP == 8 ? 2 : 3)
@@ -354,32 +484,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_fused(const __grid_c
             double s2 = 1.0;                       // Fisher sums carry the squared stretch of the row
 #pragma unroll
             for (int c = 0; c < NC; ++c)
-                if (q == 1 + c * kRowQ + 2) s2 = st[c] * st[c];
-            const double v = tot * s2;
-            a.rowpart[((int64_t)r * a.n_tiles + tile) * NQP + q] = v;
+                if (q == c * kRowQ + 2) s2 = rec.st[c] * rec.st[c];
+            a.rowpart[((int64_t)rec.row * a.n_tiles + tile) * NQP + q] = tot * s2;
         }
         // every lane has consumed stage s (the sums above depend on all of its data): refill it
         __syncwarp();
-        if (i + kStages < nrow) {
-            const int rn = __shfl_sync(0xffffffffu, my_row, i + kStages);
-            if (lane == 0) issue_row(i + kStages, rn);
-        }
+        if (lane == 0 && i + kStages < nrow) issue_row(i + kStages, recs[i + kStages].row);
     }
 
-    // ---- 4. fold the accumulator copies in a fixed order and publish the window ----------------
-    __syncwarp();
+    // ---- 4. flush, fold the accumulator copies in a fixed order, publish the window ------------
+    // lanes of one class flush one after the other (their last windows may still overlap a
+    // neighbour's after the final turn-around)
+    for (int turn = 0; turn < 32 / kClasses; ++turn) {
+        if ((lane / kClasses) == turn) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc_flush<PV>(acc[c], acc_cls + c * kClasses * W, lo[c]);
+        }
+        __syncwarp();
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        const double* ac = acc_warp + (size_t)c * kClasses * kWinCap;
-        double* dst = a.part + ((int64_t)c * a.n_tasks + task) * kWinCap;
-        for (int k = lane; k < kWinCap; k += 32) {
+        const double* ac = acc_warp + c * kClasses * W;
+        double* dst = a.part + ((int64_t)c * a.n_tasks + task) * W;
+        for (int k = lane; k < W; k += 32) {
             double sacc = ac[k];
 #pragma unroll
-            for (int q = 1; q < kClasses; ++q) sacc += ac[q * kWinCap + k];
+            for (int q = 1; q < kClasses; ++q) sacc += ac[q * W + k];
             dst[k] = sacc;
         }
     }
-    if (lane == 0 && serial_rows) atomicAdd(a.status + 1, serial_rows);
+    loss = warp_sum(loss);
+    if (lane == 0) {
+        a.losspart[task] = loss;
+        if (serial_rows) atomicAdd(a.status + 1, serial_rows);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -392,8 +530,8 @@ struct ReduceParams {
     const int* shift_rowptr[kMaxComp];   const int* shift_rows[kMaxComp];     // key -> rows (CSR)
     const int* stretch_rowptr[kMaxComp]; const int* stretch_rows[kMaxComp];
     int64_t n_rows, n_tasks;
-    int n_tiles, n_groups;
-    const double* part; const int* part_base; const double* rowpart;
+    int n_tiles, n_groups, wincap;
+    const double* part; const int* part_base; const double* rowpart; const double* losspart;
     double* tmp;        // [n_comp][n_groups][max_knots]
     double* rowsum;     // [E][NQ]
     int64_t max_knots;
@@ -419,8 +557,8 @@ __global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
             const int64_t task = (int64_t)g * a.n_tiles + t;
             const int base = a.part_base[(int64_t)c * a.n_tasks + task];
             const int w = k - base;
-            if (base != INT_MAX && w >= 0 && w < kWinCap)
-                s += a.part[((int64_t)c * a.n_tasks + task) * kWinCap + w];
+            if (base != INT_MAX && w >= 0 && w < a.wincap)
+                s += a.part[((int64_t)c * a.n_tasks + task) * a.wincap + w];
         }
         a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + k] = s;
     } else {
@@ -455,8 +593,8 @@ __global__ void k_reduce_stage2(ReduceParams a) {
             double gs = 0.0, fs = 0.0;
             for (int e = a.shift_rowptr[c][i]; e < a.shift_rowptr[c][i + 1]; ++e) {
                 const int64_t r = a.shift_rows[c][e];
-                gs += a.rowsum[r * NQ + 1 + c * kRowQ + 0];
-                fs += a.rowsum[r * NQ + 1 + c * kRowQ + 2];
+                gs += a.rowsum[r * NQ + c * kRowQ + 0];
+                fs += a.rowsum[r * NQ + c * kRowQ + 2];
             }
             const double sc = a.comp[c].p_val * a.comp[c].inv_dx;
             a.grad_all[a.shift_off[c] + i] = a.coef * sc * gs;
@@ -467,7 +605,7 @@ __global__ void k_reduce_stage2(ReduceParams a) {
         if (i < a.n_stretch[c]) {
             double gs = 0.0;
             for (int e = a.stretch_rowptr[c][i]; e < a.stretch_rowptr[c][i + 1]; ++e)
-                gs += a.rowsum[(int64_t)a.stretch_rows[c][e] * NQ + 1 + c * kRowQ + 1];
+                gs += a.rowsum[(int64_t)a.stretch_rows[c][e] * NQ + c * kRowQ + 1];
             a.grad_all[a.stretch_off[c] + i] = -a.coef * gs;
             return;
         }
@@ -475,13 +613,12 @@ __global__ void k_reduce_stage2(ReduceParams a) {
     }
 }
 
-// Block 0: loss = 0.5 * coef * sum_rows rowsum[r][0], fixed-shape tree.  Other blocks: gather.
+// Block 0: loss = 0.5 * coef * sum_tasks losspart, fixed-shape tree.  Other blocks: gather.
 __global__ void k_finish(ReduceParams a) {
-    const int NQ = a.n_comp == 1 ? 4 : 8;
     if (blockIdx.x == 0) {
         __shared__ double sh[1024];
         double s = 0.0;
-        for (int64_t r = threadIdx.x; r < a.n_rows; r += blockDim.x) s += a.rowsum[r * NQ];
+        for (int64_t r = threadIdx.x; r < a.n_tasks; r += blockDim.x) s += a.losspart[r];
         sh[threadIdx.x] = s;
         __syncthreads();
         for (int o = blockDim.x / 2; o > 0; o >>= 1) {

@@ -61,8 +61,9 @@ struct jb_plan {
     std::vector<DevBuf> bufs;   // everything cudaMalloc'ed, freed in destroy
     int64_t device_bytes = 0, scratch_bytes = 0;
 
-    double *d_x = nullptr, *d_y = nullptr, *d_iv = nullptr;
-    uint8_t *d_mask = nullptr, *d_row_rev = nullptr, *d_dense = nullptr;
+    double* d_data = nullptr;   // tile-interleaved x | y | ivar (jb_kernels.cuh)
+    double* d_x = nullptr;      // [E][ppad] original x, canonical orientation (forward kernel)
+    uint8_t *d_row_rev = nullptr, *d_dense = nullptr;
     double *d_txmin = nullptr, *d_txmax = nullptr;
     int* d_row_perm = nullptr;
     std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
@@ -77,9 +78,9 @@ struct jb_plan {
     double *h_pfit = nullptr, *h_out = nullptr;   // pinned
     int *d_status = nullptr, *h_status = nullptr; // h pinned
 
-    int G = 0, n_groups = 0;
+    int G = 0, n_groups = 0, wincap = 0;
     int64_t n_tasks = 0;
-    double *d_part = nullptr, *d_rowpart = nullptr, *d_tmp = nullptr, *d_rowsum = nullptr;
+    double *d_part = nullptr, *d_rowpart = nullptr, *d_tmp = nullptr, *d_rowsum = nullptr, *d_losspart = nullptr;
     int* d_part_base = nullptr;
     int64_t max_knots = 0;
     int* d_key_ptr[jb::kMaxComp][2] = {};   // [comp][0 shift,1 stretch] CSR rowptr
@@ -87,6 +88,7 @@ struct jb_plan {
     int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
 
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
+    int64_t tiles_kind[4] = {0, 0, 0, 0};   // smooth, general, serial, empty
 
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // pool, reused
@@ -131,8 +133,9 @@ int alloc_scratch(jb_plan* pl) {
     pl->n_groups = (int)((pl->E + pl->G - 1) / pl->G);
     pl->n_tasks = (int64_t)pl->n_groups * pl->n_tiles;
     int rc;
-    if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_comp * pl->n_tasks * jb::kWinCap, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_comp * pl->n_tasks * pl->wincap, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_comp * pl->n_tasks, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_losspart, (size_t)pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_comp * pl->n_groups * pl->max_knots, true))) return rc;
     return JB_OK;
 }
@@ -165,7 +168,7 @@ int resort_rows(jb_plan* pl) {
 
 template <int NC, int PV>
 int launch_fused_t(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
-    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>();
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>(pl->wincap);
     JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock;
     jb::k_fused<NC, PV><<<(unsigned)blocks, jb::kWarpsPerBlock * 32, smem, st>>>(fp);
@@ -212,8 +215,8 @@ void fill_reduce_params(jb_plan* pl, jb::ReduceParams& rp, double* d_out) {
         rp.shift_rowptr[c] = pl->d_key_ptr[c][0];   rp.shift_rows[c] = pl->d_key_rows[c][0];
         rp.stretch_rowptr[c] = pl->d_key_ptr[c][1]; rp.stretch_rows[c] = pl->d_key_rows[c][1];
     }
-    rp.n_rows = pl->E; rp.n_tasks = pl->n_tasks; rp.n_tiles = pl->n_tiles; rp.n_groups = pl->n_groups;
-    rp.part = pl->d_part; rp.part_base = pl->d_part_base; rp.rowpart = pl->d_rowpart;
+    rp.n_rows = pl->E; rp.n_tasks = pl->n_tasks; rp.n_tiles = pl->n_tiles; rp.n_groups = pl->n_groups; rp.wincap = pl->wincap;
+    rp.part = pl->d_part; rp.part_base = pl->d_part_base; rp.rowpart = pl->d_rowpart; rp.losspart = pl->d_losspart;
     rp.tmp = pl->d_tmp; rp.rowsum = pl->d_rowsum; rp.max_knots = pl->max_knots;
     rp.coef = pl->coef;
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
@@ -235,13 +238,14 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     }
     jb::FusedParams fp;
     memset(&fp, 0, sizeof fp);
-    fp.x = pl->d_x; fp.y = pl->d_y; fp.ivar = pl->d_iv; fp.mask = pl->d_mask;
+    fp.data = pl->d_data;
     fp.txmin = pl->d_txmin; fp.txmax = pl->d_txmax; fp.dense = pl->d_dense; fp.row_perm = pl->d_row_perm;
-    fp.n_rows = pl->E; fp.ppad = pl->ppad; fp.n_tiles = pl->n_tiles;
-    fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks;
+    fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
+    fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
     fp.n_comp = pl->n_comp;
     for (int c = 0; c < pl->n_comp; ++c) fp.comp[c] = pl->comp[c];
     fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
+    fp.losspart = pl->d_losspart;
     fp.status = pl->d_status;
     if (pl->profiling) {
         if (pl->prof_used == pl->prof_events.size()) {
@@ -288,7 +292,7 @@ int read_status(jb_plan* pl, cudaStream_t st, bool* window) {
         return fail(JB_ERR_OUT_OF_RANGE, "an unmasked warped pixel lies outside the knot grid of a spline component");
     if (bits & jb::kStatWindow) {
         if (window) *window = true;
-        return fail(JB_ERR_WINDOW, "knot window of a pixel tile exceeds %d knots (grid much finer than the pixels, or rows of one group far apart)", jb::kWinCap);
+        return fail(JB_ERR_WINDOW, "knot window of a pixel tile exceeds %d knots (grid much finer than the pixels, or rows of one group far apart)", pl->wincap);
     }
     return JB_OK;
 }
@@ -305,11 +309,12 @@ int eval_sync(jb_plan* pl, const double* d_p_fit) {
         bool window = false;
         rc = read_status(pl, st, &window);
         if (rc == JB_OK) return JB_OK;
-        if (!window || attempt >= 6) return rc;
+        if (!window || attempt >= 12) return rc;
         JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
         if (attempt > 0) {
-            if (pl->G == 1) return rc;
-            pl->G = std::max(1, pl->G / 4);
+            if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
+            else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
+            else return rc;
             int rc2 = alloc_scratch(pl);
             if (rc2) return rc2;
         }
@@ -385,71 +390,102 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->n_params = d->n_params;
     const int64_t ppad = pl->ppad;
 
-    // ---- canonical copy of the block: ascending x per row, padded, padding masked -------------
-    std::vector<double> hx((size_t)E * ppad, 0.0), hy, hiv;
-    std::vector<uint8_t> hm((size_t)E * ppad, 1);
-    if (pl->has_data) { hy.assign((size_t)E * ppad, 0.0); hiv.assign((size_t)E * ppad, 0.0); }
+    // ---- canonical copy of the block: every row ascending in x, tile-interleaved (x | y | ivar per
+    // (row, tile)), mask folded in: a pixel that carries no weight (masked, padded, or ivar == 0)
+    // gets ivar = 0, y = 0 and an x between its weighted neighbours (its own x when that is finite
+    // and monotone, else the x of the nearest weighted pixel before it; the first weighted x for
+    // leading ones), so it is evaluated on knots the data already touch and contributes exactly
+    // zero -- ChiSquare's where(~mask, ., 0), loss.py:168-173, for value and cotangent.
+    const int NT = pl->n_tiles;
+    std::vector<double> hdata((size_t)E * NT * jb::kTileDoubles, 0.0);
+    std::vector<double> hx((size_t)E * ppad, 0.0);    // original x, canonical orientation
+    std::vector<double> hxf((size_t)E * ppad, 0.0);   // filled x (what the fused kernel sees)
+    std::vector<uint8_t> hm((size_t)E * ppad, 1);     // 1 = carries no weight
     pl->h_row_rev.assign(E, 0);
     pl->h_xfirst.assign(E, INFINITY);
-    std::vector<double> txmin((size_t)E * pl->n_tiles, INFINITY), txmax((size_t)E * pl->n_tiles, -INFINITY);
+    std::vector<double> txmin((size_t)E * NT, INFINITY), txmax((size_t)E * NT, -INFINITY);
+    std::vector<uint8_t> dense((size_t)E * NT, 0);
+    double need = 0.0;   // knots two lanes of one class must be apart, in x units, 1 % margin
+    for (int c = 0; c < d->n_components; ++c)
+        need = std::max(need, (d->components[c].p_val + 1.01) * d->components[c].dx);
+    double smooth = INFINITY;   // two pixels closer than this are at most one knot interval apart
+    for (int c = 0; c < d->n_components; ++c) smooth = std::min(smooth, 0.99 * d->components[c].dx);
+    double any_x = 0.0;
+    for (int64_t i = 0; i < E * P && any_x == 0.0; ++i)
+        if ((!d->mask || !d->mask[i]) && std::isfinite(d->xs[i])) any_x = d->xs[i];
     for (int64_t r = 0; r < E; ++r) {
         const double* xr = d->xs + r * P;
         const uint8_t* mr = d->mask ? d->mask + r * P : nullptr;
+        auto weighted = [&](int64_t p) {
+            if (mr && mr[p]) return false;
+            return !pl->has_data || d->yivar[r * P + p] != 0.0;
+        };
         int64_t first = -1, last = -1;
         for (int64_t p = 0; p < P; ++p)
-            if (!mr || !mr[p]) { if (first < 0) first = p; last = p; }
+            if (weighted(p)) { if (first < 0) first = p; last = p; }
         const bool rev = first >= 0 && xr[last] < xr[first];
         pl->h_row_rev[r] = rev;
-        for (int64_t p = 0; p < P; ++p) {
+        double fill = first >= 0 ? xr[rev ? last : first] : any_x;
+        // next weighted x after each canonical position (+inf behind the last one)
+        std::vector<double> nextw(ppad + 1, INFINITY);
+        for (int64_t p = P - 1; p >= 0; --p) {
             const int64_t src = rev ? P - 1 - p : p;
-            const size_t dst = (size_t)r * ppad + p;
-            const bool masked = mr && mr[src];
-            hx[dst] = xr[src];
-            hm[dst] = masked ? 1 : 0;
-            if (pl->has_data) { hy[dst] = d->ys[r * P + src]; hiv[dst] = d->yivar[r * P + src]; }
-            if (!masked) {
-                if (!std::isfinite(xr[src])) return fail(JB_ERR_BAD_ARG, "row %lld pixel %lld: unmasked x is not finite", (long long)r, (long long)src);
-                const size_t t = (size_t)r * pl->n_tiles + p / jb::kTile;
-                txmin[t] = std::min(txmin[t], xr[src]);
-                txmax[t] = std::max(txmax[t], xr[src]);
-                pl->h_xfirst[r] = std::min(pl->h_xfirst[r], xr[src]);
-            }
+            nextw[p] = weighted(src) ? xr[src] : nextw[p + 1];
         }
-    }
-    // "dense" (row, tile) pairs: lanes l and l+4 (13 pixels apart) share an accumulator copy, which is
-    // safe when every unmasked pixel of lane l lies at least p_val+1 knots above every unmasked
-    // pixel of lanes l-4, l-8, ...  The knot distance of two pixels does not depend on the shift, so
-    // this is decided once, here, from x alone (with 1 % margin for rounding).
-    double need = 0.0;
-    for (int c = 0; c < d->n_components; ++c)
-        need = std::max(need, (d->components[c].p_val + 1.01) * d->components[c].dx);
-    std::vector<uint8_t> dense((size_t)E * pl->n_tiles, 0);
-    for (int64_t r = 0; r < E; ++r)
-        for (int t = 0; t < pl->n_tiles; ++t) {
+        for (int64_t p = 0; p < ppad; ++p) {
+            const int64_t src = rev ? P - 1 - p : p;
+            const int t = (int)(p / jb::kTile);
+            double* rec = hdata.data() + ((size_t)r * NT + t) * jb::kTileDoubles + p % jb::kTile;
+            const bool w = p < P && weighted(src);
+            if (p < P) hx[(size_t)r * ppad + p] = std::isfinite(xr[src]) ? xr[src] : 0.0;
+            if (w) {
+                if (!std::isfinite(xr[src])) return fail(JB_ERR_BAD_ARG, "row %lld pixel %lld: unmasked x is not finite", (long long)r, (long long)src);
+                fill = xr[src];
+                if (pl->has_data) { rec[jb::kTile] = d->ys[r * P + src]; rec[2 * jb::kTile] = d->yivar[r * P + src]; }
+                pl->h_xfirst[r] = std::min(pl->h_xfirst[r], fill);
+                hm[(size_t)r * ppad + p] = 0;
+            }
+            else if (p < P && std::isfinite(xr[src]) && xr[src] >= fill && xr[src] <= nextw[p] && std::isfinite(nextw[p]))
+                fill = xr[src];   // an interior masked pixel keeps its own x when it sits between its weighted neighbours
+            rec[0] = fill;
+            hxf[(size_t)r * ppad + p] = fill;
+        }
+        // tile extents, over every pixel the kernel will walk (filled ones included), and density:
+        // lanes l and l+4 (13 pixels apart) share an accumulator copy, which is safe when every pixel
+        // of lane l lies at least p_val+1 knots above every pixel of lanes l-4, l-8, ...  Knot
+        // distances inside a row do not depend on the shift, so this is decided here, from x alone.
+        for (int t = 0; t < NT; ++t) {
+            const size_t ti = (size_t)r * NT + t;
+            bool any_w = false;
             double cmax[jb::kClasses];
             for (int q = 0; q < jb::kClasses; ++q) cmax[q] = -INFINITY;
-            bool bad = false;
-            for (int l = 0; l < 32 && !bad; ++l) {
+            bool bad = false, jumpy = false;
+            for (int l = 0; l < 32; ++l) {
                 double lmin = INFINITY, lmax = -INFINITY;
                 for (int j = 0; j < jb::kPixPerLane; ++j) {
                     const size_t i = (size_t)r * ppad + (size_t)t * jb::kTile + l * jb::kPixPerLane + j;
-                    if (!hm[i]) { lmin = std::min(lmin, hx[i]); lmax = std::max(lmax, hx[i]); }
+                    lmin = std::min(lmin, hxf[i]); lmax = std::max(lmax, hxf[i]);
+                    any_w |= !hm[i];
+                    // inside a lane's run: a step of less than one knot of the finest grid, never backwards
+                    if (j > 0 && !(hxf[i] >= hxf[i - 1] && hxf[i] - hxf[i - 1] < smooth)) jumpy = true;
                 }
-                if (lmin > lmax) continue;
                 double& cm = cmax[l % jb::kClasses];
                 if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
                 cm = std::max(cm, lmax);
+                txmin[ti] = std::min(txmin[ti], lmin);
+                txmax[ti] = std::max(txmax[ti], lmax);
             }
-            dense[(size_t)r * pl->n_tiles + t] = bad;
+            // flags: 1 = lanes of a class may collide (walk lane by lane), 2 = nothing weighted (skip),
+            //        4 = consecutive pixels a knot or more apart somewhere (general per-pixel path)
+            dense[ti] = !any_w ? 2 : ((bad ? 1 : 0) | (jumpy ? 4 : 0));
+            if (!any_w) { txmin[ti] = INFINITY; txmax[ti] = -INFINITY; }
+            pl->tiles_kind[!any_w ? 3 : bad ? 2 : jumpy ? 1 : 0]++;
         }
+    }
     int rc;
     if ((rc = dev_upload(pl, &pl->d_dense, dense))) return rc;
+    if ((rc = dev_upload(pl, &pl->d_data, hdata))) return rc;
     if ((rc = dev_upload(pl, &pl->d_x, hx))) return rc;
-    if ((rc = dev_upload(pl, &pl->d_mask, hm))) return rc;
-    if (pl->has_data) {
-        if ((rc = dev_upload(pl, &pl->d_y, hy))) return rc;
-        if ((rc = dev_upload(pl, &pl->d_iv, hiv))) return rc;
-    }
     if ((rc = dev_upload(pl, &pl->d_row_rev, pl->h_row_rev))) return rc;
     if ((rc = dev_upload(pl, &pl->d_txmin, txmin))) return rc;
     if ((rc = dev_upload(pl, &pl->d_txmax, txmax))) return rc;
@@ -504,6 +540,14 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     }
 
     // ---- scratch ------------------------------------------------------------------------------
+    // on-chip window: the widest tile, in knots of the finest grid, plus the spline support and room
+    // for the rows of a group to sit a few knots apart; grown on demand (eval_sync)
+    double max_knots_tile = 0.0;
+    for (size_t i = 0; i < txmin.size(); ++i)
+        if (txmin[i] <= txmax[i])
+            for (int c = 0; c < pl->n_comp; ++c)
+                max_knots_tile = std::max(max_knots_tile, (txmax[i] - txmin[i]) / d->components[c].dx + d->components[c].p_val + 2);
+    pl->wincap = (int)std::min<double>(jb::kWinCapMax, std::max(64.0, std::ceil((max_knots_tile + 8) / 32.0) * 32.0));
     const int NQ = pl->n_comp == 1 ? 4 : 8;
     pl->G = choose_rows_per_group(E, pl->n_tiles, d->rows_per_group);
     if ((rc = dev_alloc(pl, &pl->d_rowpart, (size_t)E * pl->n_tiles * NQ, true))) return rc;
@@ -539,6 +583,9 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     info->algorithmic_bytes = pl->E * pl->P * 25 + 2 * knots * 8 + pl->E * 7 * 8;
     info->kernel_launches = pl->launches; info->evaluations = pl->evaluations;
     info->serial_rows = pl->serial_rows;
+    info->tiles_smooth = pl->tiles_kind[0]; info->tiles_general = pl->tiles_kind[1];
+    info->tiles_serial = pl->tiles_kind[2]; info->tiles_empty = pl->tiles_kind[3];
+    info->window_knots = pl->wincap;
     return JB_OK;
 }
 
