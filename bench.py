@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--rows-per-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget")
+    ap.add_argument("--workload", default="chunks", choices=["chunks", "epochs"],
+                    help="chunks: BASELINE configs[3] (default, the metric's config); epochs: configs[4], one chunk "
+                         "of --epochs x --pixels sharded by epoch over the ranks with an NCCL all-reduce of the "
+                         "loss and control-point gradients")
     return ap.parse_args()
 
 
@@ -343,6 +347,85 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_epochs(args, rank, world, local_rank):
+    """BASELINE configs[4]: ONE chunk, epochs sharded contiguously over the ranks; per evaluation the
+    ranks all-reduce [loss, dS, dT] (NCCL over NVLink); per-epoch gradients and Fisher stay local."""
+    import torch
+    from wobble_jax_b200 import engine, synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    E_total = args.epochs
+    per = (E_total + world - 1) // world
+    e0 = rank * per
+    E = max(0, min(per, E_total - e0))
+    # generate and upload in slabs so the host never holds more than a few GB
+    slab = 4096
+    plans, d_p, d_out, sizes = [], [], [], []
+    for s0 in range(0, E, slab):
+        n = min(slab, E - s0)
+        ch = synth.make_chunk(0, n_epochs=n, n_pix=args.pixels, p_val=args.p_val, as_block=True,
+                              epoch_offset=e0 + s0 + 1, total_epochs=E_total)
+        model = synth.fit_all(ch.model)
+        plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
+                           ch.datablock["mask"], ch.metablock, device=local_rank, rows_per_group=args.rows_per_group)
+        plan.sync_from_model()
+        plans.append(plan)
+        p = np.asarray(model.get_parameters())
+        d_p.append(torch.from_numpy(p).cuda())
+        d_out.append(torch.empty(len(p) + 1, dtype=torch.float64, device="cuda"))
+        sizes.append((n, len(ch.grid)))
+        del ch
+    M = sizes[0][1]
+    red = torch.zeros(1 + 2 * M, dtype=torch.float64, device="cuda")     # [loss, dS, dT] of this rank
+    main = torch.cuda.current_stream()
+
+    def step():
+        red.zero_()
+        for pl, dp, do, (n, _) in zip(plans, d_p, d_out, sizes):
+            dp.add_(1e-13)
+            pl.eval_device(dp.data_ptr(), do.data_ptr(), main.cuda_stream)
+            red[0] += do[0]
+            red[1:] += do[1 + n:1 + n + 2 * M]          # fit order: shifts(n), S(M), T(M), airmass(n)
+        if dist is not None:
+            dist.all_reduce(red)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0_.record(main)
+    for _ in range(args.steps):
+        step()
+    e1_.record(main)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0_.elapsed_time(e1_)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for pl in plans:
+        pl.check()
+    ms = float(t[0]) / args.steps
+    if rank == 0:
+        px = E_total * args.pixels
+        peak, src = measured_peaks()
+        print(json.dumps({
+            "metric": METRIC, "value": px / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {E_total} epochs x {args.pixels} px single chunk (BASELINE.json configs[4]), "
+                                   f"epoch-sharded, NCCL all-reduce of [loss, dS, dT] = {8 * (1 + 2 * M)} B per evaluation",
+                       "epochs": E_total, "pixels": args.pixels, "parallelism": f"epoch-sharded x{world}"},
+            "hbm_frac_whole_step": px * 25 / (ms * 1e-3) / 1e9 / peak / world, "loss": float(red[0])}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +436,9 @@ def main():
         return
     if world != max(args.gpus, 1) and world != 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    if args.workload == "epochs":
+        run_epochs(args, rank, world, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 

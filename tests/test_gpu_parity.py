@@ -162,3 +162,23 @@ def test_optimize_reduces_loss_and_unpacks():
     assert f < f0 and d["funcalls"] >= 1
     assert len(model.results) == 1 and model.results["funcalls"][0] == d["funcalls"]
     assert np.array_equal(np.asarray(model.get_parameters()), x)     # _unpack wrote the solution back
+
+
+def test_epoch_sharding_sums_to_the_unsharded_result():
+    """Config-5 style: rows of one chunk split over ranks on key boundaries; [loss, grad] summed over
+    ranks (here: two single-process shards added by hand) equals the unsharded evaluation."""
+    from wobble_jax_b200 import multigpu
+    ch = synth.make_chunk(chunk=4, n_epochs=50, n_pix=900, p_val=3, n_lines=15)
+    model = synth.fit_all(ch.model)
+    db, mb = ch.data.blockify()
+    p = np.asarray(model.get_parameters())
+    loss = jabble.loss.ChiSquare()
+    full = engine.Objective(loss, model, db, mb)
+    f, g = full.value(p), full.gradient(p)
+    fs, gs = 0.0, np.zeros_like(g)
+    for rank in range(2):
+        shard = multigpu.EpochShardedObjective(loss, model, db, mb, rank, 2)
+        assert 20 <= len(shard.rows) <= 30
+        fs += shard.value(p); gs += shard.gradient(p)
+    assert abs(fs - f) <= 1e-12 * abs(f)
+    _check_grad(model, gs, g, tol=1e-12)

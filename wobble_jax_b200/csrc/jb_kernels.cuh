@@ -1,6 +1,7 @@
 // Kernels of libjabble_b200 (sm_100a).  See DESIGN.md for the decomposition.
 //
 //   k_scatter_params   p_fit -> params_all[fit_map]
+//   k_prepare_rows     per-row shift/stretch records in sorted-row order
 //   k_forward          model(p, x, meta) per pixel                       (Model.__call__)
 //   k_fused<NC,PV>     warp->knot, basis weights, gather, residual, chi-square, adjoints of the
 //                      control points (deterministic, no float atomics), of shift/stretch, and the
@@ -23,6 +24,35 @@ struct ScatterParams {
 __global__ void k_scatter_params(ScatterParams a) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < a.n_fit) a.params[a.fit_map[i]] = a.p_fit[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-row parameters in sorted-row order, refreshed every evaluation (the shifts are fit parameters):
+// grouprec[pos] = { shift_c, stretch_c (c < NC), row id } for the row at sorted position pos.
+template <int NC> struct alignas(16) RowRec { double sh[NC]; double st[NC]; int row; int dense; int pad_[2]; };
+
+struct PrepareParams {
+    const int* row_perm;
+    void* grouprec;
+    int64_t n_rows;
+    int n_comp;
+    CompDev comp[kMaxComp];
+};
+
+template <int NC>
+__global__ void k_prepare_rows(PrepareParams a) {
+    const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (pos >= a.n_rows) return;
+    const int r = a.row_perm[pos];
+    RowRec<NC> rec;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const CompDev& cd = a.comp[c];
+        rec.sh[c] = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
+        rec.st[c] = cd.stretch ? cd.stretch[cd.stretch_key[r]] : 1.0;
+    }
+    rec.row = r; rec.dense = 0; rec.pad_[0] = rec.pad_[1] = 0;
+    reinterpret_cast<RowRec<NC>*>(a.grouprec)[pos] = rec;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -109,11 +139,14 @@ __global__ void k_forward(ForwardParams a) {
 // and (row, tile) pairs where that is not enough knots ("dense", decided at upload from x alone:
 // knot distances inside a row do not depend on the shift) are walked lane by lane.
 // Every sum has one fixed order: no float atomics, bit-reproducible.
+// Per (tile, sorted row): extent of the pixels the kernel walks and the path flags
+// (1 = walk lane by lane, 2 = nothing weighted, 4 = general per-pixel path).
+struct alignas(16) TileInfo { double xmin, xmax; int flags; int pad_[3]; };
+
 struct FusedParams {
     const double* data;                         // tile-interleaved x | y | ivar
-    const double* txmin; const double* txmax;   // [E][n_tiles] extent of the weighted pixels of a tile
-    const uint8_t* dense;                       // [E][n_tiles]
-    const int* row_perm;                        // rows sorted so that a group spans few knots
+    const void* grouprec;                       // [E] RowRec<NC> in sorted-row order (k_prepare_rows, every evaluation)
+    const TileInfo* tinfo;                      // [n_tiles][E] in sorted-row order (host, at (re)sort time)
     int64_t n_rows;
     int n_tiles, rows_per_group, n_groups;
     int wincap;          // knots per on-chip window (multiple of 32, <= kWinCapMax)
@@ -128,8 +161,6 @@ struct FusedParams {
 };
 
 template <int NC> struct RowQ { static constexpr int NQP = (NC == 1) ? 4 : 8; };
-
-template <int NC> struct alignas(16) RowRec { double sh[NC]; double st[NC]; int row; int dense; int pad_[2]; };
 
 template <int NC>
 __host__ __device__ constexpr size_t fused_warp_smem(int wincap) {
@@ -327,29 +358,25 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
     RowRec<NC>* recs = reinterpret_cast<RowRec<NC>*>(ring + (size_t)kStages * kTileBytes);
     const uint32_t bar0 = smem_u32(recs + kMaxGroup);                        // [kStages] mbarriers
 
-    // ---- 0. lane i prepares the record of row i of the group ---------------------------------
+    // ---- 0. lane i fetches the record of row i of the group: two independent loads ------------
     int lo[NC], hi[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; }
+    bool has_work = false;
     if (lane < nrow) {
-        const int r = a.row_perm[row0 + lane];
-        RowRec<NC> rec;
-        rec.row = r;
-        rec.dense = a.dense[(int64_t)r * a.n_tiles + tile];
-        rec.pad_[0] = rec.pad_[1] = 0;
-        const double xmin = a.txmin[(int64_t)r * a.n_tiles + tile];
-        const double xmax = a.txmax[(int64_t)r * a.n_tiles + tile];
+        RowRec<NC> rec = reinterpret_cast<const RowRec<NC>*>(a.grouprec)[row0 + lane];
+        const TileInfo ti = a.tinfo[(int64_t)tile * a.n_rows + row0 + lane];
+        rec.dense = ti.flags;
+        has_work = ti.flags != 2;
+        if (has_work) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const CompDev& cd = a.comp[c];
-            rec.sh[c] = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
-            rec.st[c] = cd.stretch ? cd.stretch[cd.stretch_key[r]] : 1.0;
-            if (xmin <= xmax) {
+            for (int c = 0; c < NC; ++c) {
+                const CompDev& cd = a.comp[c];
                 double g; int I0, I1;
-                knot_coord<PV>(xmin, rec.sh[c], cd.xp0, cd.inv_dx, g, I0);
-                knot_coord<PV>(xmax, rec.sh[c], cd.xp0, cd.inv_dx, g, I1);
+                knot_coord<PV>(ti.xmin, rec.sh[c], cd.xp0, cd.inv_dx, g, I0);
+                knot_coord<PV>(ti.xmax, rec.sh[c], cd.xp0, cd.inv_dx, g, I1);
                 // guard the magic-number trick: coordinates must be far inside +-2^31
-                const double t0 = ((xmin - rec.sh[c]) - cd.xp0) * cd.inv_dx, t1 = ((xmax - rec.sh[c]) - cd.xp0) * cd.inv_dx;
+                const double t0 = ((ti.xmin - rec.sh[c]) - cd.xp0) * cd.inv_dx, t1 = ((ti.xmax - rec.sh[c]) - cd.xp0) * cd.inv_dx;
                 if (!(t0 > -1.0e9 && t1 < 1.0e9)) { I0 = -(1 << 30); I1 = (1 << 30); }
                 lo[c] = knot_lo<PV>(I0);
                 hi[c] = knot_lo<PV>(I1) + PV;
@@ -357,38 +384,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
         }
         recs[lane] = rec;
     }
-    // ---- 1. knot window of the task ---------------------------------------------------------
-    bool bad_range = false, bad_window = false, empty = false;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
-            hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
-        }
-        if (lo[c] > hi[c]) empty = true;
-        else {
-            if (lo[c] < 0 || hi[c] > a.comp[c].n_knots - 1) bad_range = true;
-            if (hi[c] - lo[c] + 1 > W) bad_window = true;
-        }
-    }
-    const bool skip = empty || bad_range || bad_window;
-    if (lane == 0) {
-        if (!empty && bad_range) atomicOr(a.status, kStatOutOfRange);
-        else if (!empty && bad_window) atomicOr(a.status, kStatWindow);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) a.part_base[(int64_t)c * a.n_tasks + task] = skip ? INT_MAX : lo[c];
-        if (skip) a.losspart[task] = 0.0;
-    }
-    if (skip) {   // nothing weighted here (or an error): the row sums of this tile are zero
-        for (int i = lane; i < nrow * NQP; i += 32) {
-            const int r = a.row_perm[row0 + i / NQP];
-            a.rowpart[((int64_t)r * a.n_tiles + tile) * NQP + i % NQP] = 0.0;
-        }
-        return;
-    }
-
-    // ---- 2. barriers, first copies, accumulators, control-point window ------------------------
+    const bool empty = !__any_sync(0xffffffffu, has_work);
     auto issue_row = [&](int i, int r) {      // lane 0 only
         const int s = i % kStages;
         const uint32_t bar = bar0 + 8 * s;
@@ -396,16 +392,49 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
         tma_load_1d(smem_u32(ring + (size_t)s * kTileBytes), a.data + ((int64_t)r * a.n_tiles + tile) * kTileDoubles,
                     kTileBytes, bar);
     };
-    if (lane == 0) {
+    // ---- 1. start the first copies as early as possible ------------------------------------------
+    __syncwarp();
+    if (lane == 0 && !empty) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
         mbar_fence_init();
-    }
-    __syncwarp();
-    if (lane == 0) {
         for (int i = 0; i < kStages && i < nrow; ++i) issue_row(i, recs[i].row);
     }
-    for (int i = lane; i < NC * kClasses * W; i += 32) acc_warp[i] = 0.0;
+    // ---- 2. knot window of the task ---------------------------------------------------------
+    bool bad_range = false, bad_window = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if (!empty) {
+            if (lo[c] < 0 || hi[c] > a.comp[c].n_knots - 1) bad_range = true;
+            if (hi[c] - lo[c] + 1 > W) bad_window = true;
+        }
+    }
+    const bool skip = empty || bad_range || bad_window;
+    if (lane == 0) {
+        if (bad_range) atomicOr(a.status, kStatOutOfRange);
+        else if (bad_window) atomicOr(a.status, kStatWindow);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a.part_base[(int64_t)c * a.n_tasks + task] = skip ? INT_MAX : lo[c];
+        if (skip) a.losspart[task] = 0.0;
+    }
+    if (skip) {   // nothing weighted here (or an error): the row sums of this tile are zero
+        for (int i = lane; i < nrow * NQP; i += 32)
+            a.rowpart[((int64_t)recs[i / NQP].row * a.n_tiles + tile) * NQP + i % NQP] = 0.0;
+        if (!empty)   // copies are in flight into this warp's ring: let them land before leaving
+            for (int i = 0; i < kStages && i < nrow; ++i) mbar_wait(bar0 + 8 * (i % kStages), 0);
+        return;
+    }
+
+    // ---- 3. accumulators and control-point window ------------------------------------------------
+    {
+        double2* z = reinterpret_cast<double2*>(acc_warp);
+        for (int i = lane; i < NC * kClasses * W / 2; i += 32) z[i] = make_double2(0.0, 0.0);
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int n = hi[c] - lo[c] + 1;
@@ -424,7 +453,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
     int serial_rows = 0;
     double loss = 0.0;
 
-    // ---- 3. stream the rows of the group ------------------------------------------------------
+    // ---- 4. stream the rows of the group ------------------------------------------------------
     for (int i = 0; i < nrow; ++i) {
         const int s = i % kStages;
         const RowRec<NC> rec = recs[i];
@@ -492,16 +521,12 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
         if (lane == 0 && i + kStages < nrow) issue_row(i + kStages, recs[i + kStages].row);
     }
 
-    // ---- 4. flush, fold the accumulator copies in a fixed order, publish the window ------------
-    // lanes of one class flush one after the other (their last windows may still overlap a
-    // neighbour's after the final turn-around)
-    for (int turn = 0; turn < 32 / kClasses; ++turn) {
-        if ((lane / kClasses) == turn) {
+    // ---- 5. flush, fold the accumulator copies in a fixed order, publish the window ------------
+    // All windows now sit on pixels of the same (last walked) row, so lanes of one class are on
+    // disjoint knots (or hold zeros after a lane-by-lane row): one parallel flush.
 #pragma unroll
-            for (int c = 0; c < NC; ++c) acc_flush<PV>(acc[c], acc_cls + c * kClasses * W, lo[c]);
-        }
-        __syncwarp();
-    }
+    for (int c = 0; c < NC; ++c) acc_flush<PV>(acc[c], acc_cls + c * kClasses * W, lo[c]);
+    __syncwarp();
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const double* ac = acc_warp + c * kClasses * W;

@@ -2,8 +2,8 @@
 //
 // A plan owns: the data block in HBM (canonicalised: every row ascending in x, padded to a
 // multiple of the 128-pixel warp tile), the flat parameter vector, the fit map, the scratch for
-// per-task partials, one CUDA stream.  An evaluation is five launches on that stream:
-//   k_scatter_params -> k_fused -> k_reduce_stage1 -> k_reduce_stage2 -> k_finish
+// per-task partials, one CUDA stream.  An evaluation is six launches on that stream:
+//   k_scatter_params -> k_prepare_rows -> k_fused -> k_reduce_stage1 -> k_reduce_stage2 -> k_finish
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -63,9 +63,12 @@ struct jb_plan {
 
     double* d_data = nullptr;   // tile-interleaved x | y | ivar (jb_kernels.cuh)
     double* d_x = nullptr;      // [E][ppad] original x, canonical orientation (forward kernel)
-    uint8_t *d_row_rev = nullptr, *d_dense = nullptr;
-    double *d_txmin = nullptr, *d_txmax = nullptr;
+    uint8_t* d_row_rev = nullptr;
     int* d_row_perm = nullptr;
+    void* d_grouprec = nullptr;            // [E] RowRec, sorted-row order
+    jb::TileInfo* d_tinfo = nullptr;       // [n_tiles][E], sorted-row order
+    std::vector<double> h_txmin, h_txmax;  // [E][n_tiles]
+    std::vector<uint8_t> h_flags;          // [E][n_tiles]
     std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
     std::vector<uint8_t> h_row_rev;
 
@@ -160,7 +163,16 @@ int resort_rows(jb_plan* pl) {
     std::vector<int> perm(pl->E);
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<jb::TileInfo> tinfo((size_t)pl->n_tiles * pl->E);
+    for (int t = 0; t < pl->n_tiles; ++t)
+        for (int64_t pos = 0; pos < pl->E; ++pos) {
+            const size_t src = (size_t)perm[pos] * pl->n_tiles + t;
+            jb::TileInfo& ti = tinfo[(size_t)t * pl->E + pos];
+            ti.xmin = pl->h_txmin[src]; ti.xmax = pl->h_txmax[src]; ti.flags = pl->h_flags[src];
+            ti.pad_[0] = ti.pad_[1] = ti.pad_[2] = 0;
+        }
     JB_CUDA(cudaMemcpyAsync(pl->d_row_perm, perm.data(), pl->E * sizeof(int), cudaMemcpyHostToDevice, pl->stream));
+    JB_CUDA(cudaMemcpyAsync(pl->d_tinfo, tinfo.data(), tinfo.size() * sizeof(jb::TileInfo), cudaMemcpyHostToDevice, pl->stream));
     JB_CUDA(cudaStreamSynchronize(pl->stream));
     pl->sort_dirty = false;
     return JB_OK;
@@ -236,10 +248,20 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
         jb::k_scatter_params<<<(unsigned)((pl->n_fit + 255) / 256), 256, 0, st>>>(sp);
         pl->launches++;
     }
+    {
+        jb::PrepareParams pp;
+        memset(&pp, 0, sizeof pp);
+        pp.row_perm = pl->d_row_perm; pp.grouprec = pl->d_grouprec; pp.n_rows = pl->E; pp.n_comp = pl->n_comp;
+        for (int c = 0; c < pl->n_comp; ++c) pp.comp[c] = pl->comp[c];
+        const unsigned nb = (unsigned)((pl->E + 127) / 128);
+        if (pl->n_comp == 1) jb::k_prepare_rows<1><<<nb, 128, 0, st>>>(pp);
+        else jb::k_prepare_rows<2><<<nb, 128, 0, st>>>(pp);
+        pl->launches++;
+    }
     jb::FusedParams fp;
     memset(&fp, 0, sizeof fp);
     fp.data = pl->d_data;
-    fp.txmin = pl->d_txmin; fp.txmax = pl->d_txmax; fp.dense = pl->d_dense; fp.row_perm = pl->d_row_perm;
+    fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
     fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
     fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
     fp.n_comp = pl->n_comp;
@@ -483,12 +505,16 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
         }
     }
     int rc;
-    if ((rc = dev_upload(pl, &pl->d_dense, dense))) return rc;
+    pl->h_txmin = txmin; pl->h_txmax = txmax; pl->h_flags = dense;
+    if ((rc = dev_alloc(pl, &pl->d_tinfo, (size_t)NT * E))) return rc;
+    {
+        char* rec = nullptr;
+        if ((rc = dev_alloc(pl, &rec, (size_t)E * sizeof(jb::RowRec<jb::kMaxComp>)))) return rc;
+        pl->d_grouprec = rec;
+    }
     if ((rc = dev_upload(pl, &pl->d_data, hdata))) return rc;
     if ((rc = dev_upload(pl, &pl->d_x, hx))) return rc;
     if ((rc = dev_upload(pl, &pl->d_row_rev, pl->h_row_rev))) return rc;
-    if ((rc = dev_upload(pl, &pl->d_txmin, txmin))) return rc;
-    if ((rc = dev_upload(pl, &pl->d_txmax, txmax))) return rc;
     std::vector<int> perm(E);
     std::iota(perm.begin(), perm.end(), 0);
     if ((rc = dev_upload(pl, &pl->d_row_perm, perm))) return rc;

@@ -1,0 +1,116 @@
+"""One process per GPU: chunk sharding (no collective) and epoch sharding (one all-reduce).
+
+SURVEY.md section 8e.  The reference's only parallelism is a ``multiprocessing.Pool`` over echelle
+orders (notebooks/02-51peg.py:66-78): chunks/orders are independent fits, so they are dealt
+round-robin to the ranks and nothing is exchanged.  When ONE chunk has more epochs than a GPU
+should hold, its rows are split across ranks on ``which_key`` boundaries (every epoch key lives on
+one rank); loss and control-point gradients are sums over rows, so one
+``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs) of the ``[loss, gradient]`` vector
+completes the evaluation -- per-key entries receive zeros from the ranks that do not own the key.
+"""
+
+import numpy as np
+
+from . import engine
+from .dataset import DataBlock
+
+
+def shard_chunks(n_chunks, rank, world_size):
+    """Chunk c -> rank c mod world_size."""
+    return [c for c in range(n_chunks) if c % world_size == rank]
+
+
+def shard_rows_by_key(keys, world_size):
+    """Split rows into ``world_size`` parts of nearly equal row count such that all rows sharing a
+    key are in the same part and parts are contiguous in key order.
+
+    ``keys``: (E,) integer key of every row (the metablock column the epoch-specific models use).
+    Returns a list of row-index arrays (ascending), one per rank.
+    """
+    keys = np.asarray(keys).astype(np.int64).reshape(-1)
+    if keys.size == 0:
+        return [np.zeros(0, dtype=np.int64) for _ in range(world_size)]
+    counts = np.bincount(keys)
+    cum = np.cumsum(counts)
+    total = cum[-1]
+    # key k goes to the part whose row quota contains the midpoint of k's row span
+    mid = cum - counts / 2.0
+    part_of_key = np.minimum((mid * world_size / total).astype(np.int64), world_size - 1)
+    part_of_row = part_of_key[keys]
+    return [np.nonzero(part_of_row == r)[0] for r in range(world_size)]
+
+
+def epoch_keys(model, metablock):
+    """The key column shared by every epoch-specific leaf of the tree (rows are sharded on it)."""
+    spec = engine.TreeSpec(model)
+    names = {getattr(lf.node, "which_key") for lf in spec.leaves if hasattr(lf.node, "which_key")}
+    if not names:
+        return np.arange(len(metablock), dtype=np.int64)
+    if len(names) > 1:
+        cols = [np.asarray(metablock[n]) for n in names]
+        if not all(np.array_equal(cols[0], c) for c in cols[1:]):
+            raise ValueError(f"epoch sharding needs one key column; the model uses {sorted(names)} with different values")
+    return np.asarray(metablock[next(iter(names))]).astype(np.int64)
+
+
+def take_rows(datablock, metablock, rows):
+    """Row subset of a (datablock, metablock) pair; keys keep their GLOBAL values."""
+    db = DataBlock(**{k: np.ascontiguousarray(np.asarray(datablock[k])[rows]) for k in ("xs", "ys", "yivar", "mask")})
+    mb = DataBlock(**{k: np.asarray(metablock[k])[rows] for k in metablock.keys()})
+    return db, mb
+
+
+def all_reduce_sum(vec, group=None):
+    """Sum a [loss, gradient...] vector (torch tensor, CPU or CUDA) over the ranks, in place."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return vec
+
+
+class EpochShardedObjective:
+    """(func, fprime) for ONE chunk whose rows are split over the ranks of ``group``.
+
+    Every rank holds its rows in a plan; an evaluation is the local fused kernel, then one
+    all-reduce of the device-resident ``[loss, grad]`` vector, then a single D2H copy.  All ranks
+    must call ``value``/``gradient`` with the same parameter vector (scipy runs on every rank, or
+    rank 0 broadcasts).
+    """
+
+    def __init__(self, loss, model, datablock, metablock, rank, world_size, device=0, group=None):
+        import torch
+        from . import loss as L
+        if not isinstance(loss, L.ChiSquare):
+            raise NotImplementedError("only ChiSquare runs on the CUDA path")
+        self.torch = torch
+        self.group = group
+        rows = shard_rows_by_key(epoch_keys(model, metablock), world_size)[rank]
+        self.rows = rows
+        db, mb = take_rows(datablock, metablock, rows)
+        self.plan = engine.build_plan(model, db, mb, coefficient=loss.coefficient, device=device)
+        self.n_fit = self.plan.n_fit
+        self.dev = torch.device("cuda", device)
+        self.d_p = torch.empty(max(self.n_fit, 1), dtype=torch.float64, device=self.dev)
+        self.d_out = torch.empty(self.n_fit + 1, dtype=torch.float64, device=self.dev)
+        self._p = None
+        self._f = None
+        self._g = None
+
+    def _eval(self, p):
+        torch = self.torch
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        if self._p is None or not np.array_equal(p, self._p):
+            stream = torch.cuda.current_stream(self.dev)
+            self.d_p[:self.n_fit].copy_(torch.from_numpy(p), non_blocking=True)
+            self.plan.eval_device(self.d_p.data_ptr(), self.d_out.data_ptr(), stream.cuda_stream)
+            all_reduce_sum(self.d_out, self.group)
+            out = self.d_out.cpu().numpy()
+            self.plan.check()
+            self._f, self._g, self._p = float(out[0]), out[1:].copy(), p.copy()
+        return self._f, self._g
+
+    def value(self, p):
+        return self._eval(p)[0]
+
+    def gradient(self, p):
+        return self._eval(p)[1].copy()

@@ -52,25 +52,30 @@ class Chunk:
 
 def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=100, mask_frac=0.01,
                resolution=RESOLUTION, pixel_step=PIXEL_STEP, seed=20260101, descending=False,
-               ragged=False, as_block=False):
+               ragged=False, as_block=False, epoch_offset=0, total_epochs=None):
     """SURVEY.md section 8d "Synthetic inputs -- config 4", chunk ``chunk``.
 
     Returns a Chunk with ``data`` (Data), ``model`` (get_wobble_model tree at the evaluation point:
     templates = truth + N(0, 0.01), shifts = truth + N(0, shifts(100 m/s))), ``truth`` dict.
     """
-    rng = np.random.default_rng(seed + chunk)
+    rng = np.random.default_rng(seed + chunk)          # chunk-level quantities: lines, templates
+    # per-epoch quantities come from their own stream so that a rank holding epochs
+    # [epoch_offset, epoch_offset + n_epochs) of a larger chunk draws different rows than its peers
+    rrng = rng if epoch_offset == 0 else np.random.default_rng([seed + chunk, epoch_offset])
     E, P = n_epochs, n_pix
+    ET = total_epochs or E
     x0 = math.log(4000.0) + CHUNK_STEP * chunk
-    jitter = rng.uniform(-0.5, 0.5, E)
+    jitter = rrng.uniform(-0.5, 0.5, E)
     x = x0 + pixel_step * (np.arange(P)[None, :] + jitter[:, None])            # (E,P) strictly increasing
-    grid = M.create_x_grid(x, VEL_PADDING, 2 * resolution)
+    # the knot grid must not depend on which epochs a rank holds: pad by the full jitter range
+    grid = M.create_x_grid(np.array([x0 - 0.5 * pixel_step, x0 + pixel_step * (P - 0.5)]), VEL_PADDING, 2 * resolution)
     sigma = float(physics.delta_x(resolution))
     span = (x.min(), x.max())
     s_cent = rng.uniform(*span, n_lines); s_depth = rng.uniform(0.0, 0.9, n_lines)
     t_cent = rng.uniform(*span, n_lines); t_depth = rng.uniform(0.0, 0.9, n_lines)
-    vel = 30e3 * np.sin(2 * np.pi * np.arange(E) / E) + rng.uniform(-200, 200, E)
+    vel = 30e3 * np.sin(2 * np.pi * (np.arange(E) + epoch_offset) / ET) + rrng.uniform(-200, 200, E)
     shift_true = physics.shifts(vel)
-    airmass = rng.uniform(1.0, 2.0, E)
+    airmass = rrng.uniform(1.0, 2.0, E)
     # both templates are tabulated once on a uniform grid of 1/32 knot and read back by linear
     # interpolation: the interpolant IS the synthetic truth (smooth to ~1e-5, far below the noise)
     fine = np.linspace(grid[0], grid[-1], 32 * (len(grid) - 1) + 1)
@@ -79,18 +84,18 @@ def make_chunk(chunk=0, n_epochs=2000, n_pix=4096, p_val=3, snr=100.0, n_lines=1
     h = fine[1] - fine[0]
     y = _interp_uniform(x - shift_true[:, None], fine[0], h, s_fine)
     y += airmass[:, None] * _interp_uniform(x, fine[0], h, t_fine)
-    y += rng.normal(0.0, 1.0 / snr, y.shape)
+    y += rrng.normal(0.0, 1.0 / snr, y.shape)
     yivar = np.full_like(x, snr ** 2)
-    mask = rng.uniform(size=x.shape) < mask_frac
+    mask = rrng.uniform(size=x.shape) < mask_frac
     lengths = np.full(E, P)
     if ragged:
-        lengths = P - rng.integers(0, P // 8, E)
+        lengths = P - rrng.integers(0, P // 8, E)
     fact = float(math.factorial(p_val))          # basis is p_val! * B-spline
     S_true = _lines_at(grid, s_cent, s_depth, sigma) / fact
     T_true = _lines_at(grid, t_cent, t_depth, sigma) / fact
     S0 = S_true + rng.normal(0, 0.01 / fact, grid.shape)
     T0 = T_true + rng.normal(0, 0.01 / fact, grid.shape)
-    shift0 = shift_true + rng.normal(0, float(physics.shifts(100.0)), E)
+    shift0 = shift_true + rrng.normal(0, float(physics.shifts(100.0)), E)
 
     model = quickplay.get_wobble_model(np.zeros(E), airmass, grid, p_val)
     model[0][0].p = shift0.copy()
