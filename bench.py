@@ -210,24 +210,21 @@ def run_b200(args, rank, world, local_rank):
     n_fit = info["n_fit"]
     setup_s = time.perf_counter() - t_setup
 
-    # device-resident parameters and outputs
-    d_p = [torch.from_numpy(p).cuda() for p in p_host]
-    d_out = [torch.empty(n_fit + 1, dtype=torch.float64, device="cuda") for _ in plans]
-    streams = [torch.cuda.ExternalStream(pl.stream()) for pl in plans]
-    main = torch.cuda.current_stream()
+    # device-resident parameters and outputs: one flat buffer each, a view per chunk
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in p_host])])
+    P_all = torch.from_numpy(np.concatenate(p_host)).cuda()
+    O_all = torch.empty(int(offs[-1]) + len(plans), dtype=torch.float64, device="cuda")
+    d_p = [P_all[int(offs[i]):int(offs[i + 1])] for i in range(len(plans))]
+    d_out = [O_all[int(offs[i]) + i:int(offs[i + 1]) + i + 1] for i in range(len(plans))]
+    # a real (non-default) stream: the C ABI reads a NULL stream as "the batch's own stream"
+    main = torch.cuda.Stream()
+    torch.cuda.set_stream(main)
+    batch = engine.Batch(plans)            # every kernel of the evaluation launched once for all chunks
+    batch.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
 
     def step_device():
-        # fork: every plan's stream waits for the main stream; join: main waits for every plan
-        ev = torch.cuda.Event()
-        ev.record(main)
-        for pl, s, dp, do in zip(plans, streams, d_p, d_out):
-            s.wait_event(ev)
-            with torch.cuda.stream(s):
-                dp.add_(1e-13)                       # new parameter vector every step
-            pl.eval_device(dp.data_ptr(), do.data_ptr())
-            done = torch.cuda.Event()
-            done.record(s)
-            main.wait_event(done)
+        P_all.add_(1e-13)                  # new parameter vectors every step
+        batch.eval_device(main.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,9 +235,8 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    for pl in plans:
-        pl.check()
-    launches0 = sum(pl.info()["kernel_launches"] for pl in plans)
+    batch.check()
+    launches0 = batch.launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -253,9 +249,8 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    launches = sum(pl.info()["kernel_launches"] for pl in plans) - launches0
-    for pl in plans:
-        pl.check()
+    launches = batch.launches() - launches0
+    batch.check()
     losses = [float(o[0]) for o in d_out]
     assert all(np.isfinite(losses)), "non-finite loss"
 
@@ -316,6 +311,7 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(8 * (n_fit + 1) * args.chunks * world),
                 "ms_per_step": e2e_ms / args.steps,
                 "api": "jb_plan_eval (host p_fit in, host loss+gradient out), 16 host threads over the chunks"},
+        "device_api": "jb_batch_eval_device: 6 launches per step for all chunks of the GPU",
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -381,7 +377,9 @@ def run_epochs(args, rank, world, local_rank):
         del ch
     M = sizes[0][1]
     red = torch.zeros(1 + 2 * M, dtype=torch.float64, device="cuda")     # [loss, dS, dT] of this rank
-    main = torch.cuda.current_stream()
+    main = torch.cuda.Stream()            # non-default: a NULL stream means "the plan's own" to the C ABI
+    main.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(main)
 
     def step():
         red.zero_()

@@ -159,6 +159,23 @@ int jb_plan_fisher(jb_plan *plan, int32_t component, double *f_out, int64_t n_sh
 /* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests). */
 int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);
 
+/*
+ * Batch of independent plans (chunks / echelle orders: separate fits that the reference runs in a
+ * multiprocessing.Pool, notebooks/02-51peg.py:66-78) evaluated together: every kernel of the
+ * evaluation is launched ONCE for the whole batch, so small per-chunk grids do not leave SMs idle.
+ * The plans must live on one device and share the model shape.  jb_batch_bind fixes, per plan, the
+ * device pointers of the fit vector (n_fit doubles; the array may be NULL to keep the parameters)
+ * and of the output (1 + n_fit doubles: loss, gradient); jb_batch_eval_device enqueues one
+ * evaluation of all plans on `stream` (NULL = the batch's own stream) without synchronising.
+ */
+typedef struct jb_batch jb_batch;
+int jb_batch_create(jb_plan *const *plans, int32_t n_plans, jb_batch **out);
+void jb_batch_destroy(jb_batch *batch);
+int jb_batch_bind(jb_batch *batch, const double *const *d_p_fit, double *const *d_out);
+int jb_batch_eval_device(jb_batch *batch, void *stream);
+int jb_batch_check(jb_batch *batch);
+int64_t jb_batch_launches(const jb_batch *batch);
+
 /* The plan's own cudaStream_t (so that a caller can order its work, or time it with events). */
 int jb_plan_stream(jb_plan *plan, void **stream_out);
 

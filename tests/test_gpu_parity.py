@@ -182,3 +182,31 @@ def test_epoch_sharding_sums_to_the_unsharded_result():
         fs += shard.value(p); gs += shard.gradient(p)
     assert abs(fs - f) <= 1e-12 * abs(f)
     _check_grad(model, gs, g, tol=1e-12)
+
+
+def test_batched_launch_equals_per_plan_results():
+    """jb_batch: several chunks evaluated by one launch per kernel give bit-identical results to the
+    per-plan path (same kernels, same fixed summation order)."""
+    import torch
+    chunks = [synth.make_chunk(chunk=c, n_epochs=20 + 7 * c, n_pix=700 + 128 * c, p_val=3, n_lines=10) for c in range(3)]
+    plans, ps, refs = [], [], []
+    for ch in chunks:
+        model = synth.fit_all(ch.model)
+        db, mb = ch.data.blockify()
+        plan = engine.build_plan(model, db, mb)
+        p = np.asarray(model.get_parameters())
+        refs.append(plan.eval(p))
+        plans.append(plan); ps.append(p)
+    d_p = [torch.from_numpy(p + 0.0).cuda() for p in ps]
+    d_out = [torch.zeros(len(p) + 1, dtype=torch.float64, device="cuda") for p in ps]
+    batch = engine.Batch(plans)
+    batch.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
+    for _ in range(2):
+        batch.eval_device(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    batch.check()
+    for (f, g), o in zip(refs, d_out):
+        o = o.cpu().numpy()
+        assert o[0] == f and np.array_equal(o[1:], g)
+    assert batch.launches() == 12
+    batch.close()

@@ -69,6 +69,12 @@ SYMBOLS = [
     ("jb_plan_forward", C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p]),
     ("jb_plan_fisher", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64]),
     ("jb_plan_grad_all", C.c_int, [C.c_void_p, c_f64p, C.c_int64]),
+    ("jb_batch_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
+    ("jb_batch_destroy", None, [C.c_void_p]),
+    ("jb_batch_bind", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("jb_batch_eval_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("jb_batch_check", C.c_int, [C.c_void_p]),
+    ("jb_batch_launches", C.c_int64, [C.c_void_p]),
     ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("jb_plan_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_plan_profile_read", C.c_int, [C.c_void_p, c_f64p, c_i64p]),

@@ -15,15 +15,24 @@ constexpr int kTile = 128;        // pixels per warp tile
 constexpr int kPixPerLane = 4;    // consecutive pixels owned by one lane (one 256-bit load per array)
 constexpr int kWinCapMax = 256;   // knots in a warp's on-chip gradient window: chosen per plan (multiple of 32)
 constexpr int kClasses = 4;       // lane residue classes with private accumulator copies
+// Tuning knobs (measured on B200, profiles/README.md): 2 warps (tasks) per block, 128 registers,
+// a 2-deep copy ring and a rolled pixel loop give 14 resident warps per SM; every larger-register /
+// unrolled variant tried was slower.
 #ifndef JB_WARPS
-#define JB_WARPS 4
+#define JB_WARPS 2
 #endif
 #ifndef JB_MAXREG
-#define JB_MAXREG 255
+#define JB_MAXREG 128
+#endif
+#ifndef JB_UNROLLED
+#define JB_ROLLED 1
 #endif
 constexpr int kWarpsPerBlock = JB_WARPS;   // tasks per block
 constexpr int kRowQ = 3;          // per-component per-row sums: d/dshift, d/dstretch, Fisher
-constexpr int kStages = 4;        // rows in flight per warp (TMA bulk-copy ring)
+#ifndef JB_STAGES
+#define JB_STAGES 2
+#endif
+constexpr int kStages = JB_STAGES;        // rows in flight per warp (TMA bulk-copy ring)
 constexpr int kStageBytes = kTile * 8 * 3 + kTile;   // x, y, ivar (f64) + mask (u8) of one row tile
 constexpr int kMaxGroup = 32;     // rows per group: lane i keeps the parameters of row i
 

@@ -21,9 +21,25 @@ struct ScatterParams {
     int64_t n_fit;
 };
 
-__global__ void k_scatter_params(ScatterParams a) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < a.n_fit) a.params[a.fit_map[i]] = a.p_fit[i];
+// Every evaluation kernel takes an ARRAY of per-plan parameter blocks plus the first block index of
+// each plan (n+1 entries): one launch serves one plan (n = 1) or a whole batch of independent
+// chunks (jb_batch), so that small per-chunk grids do not leave the GPU half empty.
+__device__ __forceinline__ int find_plan(const int* __restrict__ off, int n, int blk) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= blk) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_scatter_params(const ScatterParams* __restrict__ arr, const int* __restrict__ off, int n,
+                                 const double* p_fit_override) {
+    const int pi = find_plan(off, n, blockIdx.x);
+    const ScatterParams a = arr[pi];
+    const double* p_fit = p_fit_override ? p_fit_override : a.p_fit;
+    const int64_t i = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
+    if (p_fit && i < a.n_fit) a.params[a.fit_map[i]] = p_fit[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -40,8 +56,10 @@ struct PrepareParams {
 };
 
 template <int NC>
-__global__ void k_prepare_rows(PrepareParams a) {
-    const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_prepare_rows(const PrepareParams* __restrict__ arr, const int* __restrict__ off, int n) {
+    const int pi = find_plan(off, n, blockIdx.x);
+    const PrepareParams& a = arr[pi];
+    const int64_t pos = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
     if (pos >= a.n_rows) return;
     const int r = a.row_perm[pos];
     RowRec<NC> rec;
@@ -277,15 +295,23 @@ __device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, 
         const int kl = knot_lo<PV>(I);
         step[c] = kl != acc[c].klo;
         double* accw = acc_cls + c * kClasses * W;
+#ifndef JB_EXP_NORMW
         if (step[c]) {                              // retire the knot that leaves the window
             if (DIR > 0) accw[acc[c].klo - lo[c]] += acc[c].a[0];
             else accw[acc[c].klo + PV - lo[c]] += acc[c].a[PV];
         }
+#endif
         acc[c].klo = kl;
         const double* cw = ctrl_warp + c * W + (kl - lo[c]);
         double cv[PV + 1];
+#ifdef JB_EXP_NOCTRL
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) cv[k] = 0.25 * k + g;
+        (void)cw;
+#else
 #pragma unroll
         for (int k = 0; k <= PV; ++k) cv[k] = cw[k];
+#endif
         double dw[PV];
         Basis<PV>::eval(g, w[c], dw);
         double sv = cv[0] * w[c][0];
@@ -318,31 +344,45 @@ __device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, 
     }
 }
 
-// the four pixels of a lane in walking order
+// the four pixels of a lane in walking order; px = the lane's first pixel in the staged row
+// (x at px[j], y at px[kTile + j], ivar at px[2 * kTile + j])
 template <int NC, int PV, int DIR>
-__device__ __forceinline__ void fused_run_fast(const double (&xv)[4], const double (&yv)[4], const double (&iv)[4],
-                                               const double (&sh)[NC], const double (&st)[NC], const CompDev* comp,
-                                               Acc<PV> (&acc)[NC], const double* ctrl_warp, double* acc_cls, const int W,
-                                               const int (&lo)[NC], double& loss, double (&sums)[RowQ<NC>::NQP]) {
+__device__ __forceinline__ void fused_run_fast(const double* px, const double (&sh)[NC], const double (&st)[NC],
+                                               const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
+                                               double* acc_cls, const int W, const int (&lo)[NC], double& loss,
+                                               double (&sums)[RowQ<NC>::NQP]) {
     constexpr int j0 = DIR > 0 ? 0 : 3;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         double g; int I;
-        knot_coord<PV>(xv[j0], sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
+        knot_coord<PV>(px[j0], sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
         acc_reposition<PV, DIR>(acc[c], knot_lo<PV>(I), acc_cls + c * kClasses * W, lo[c]);
     }
+#ifdef JB_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int jj = 0; jj < 4; ++jj) {
         const int j = DIR > 0 ? jj : 3 - jj;
-        fused_pixel_fast<NC, PV, DIR>(xv[j], yv[j], iv[j], sh, st, comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+        fused_pixel_fast<NC, PV, DIR>(px[j], px[kTile + j], px[2 * kTile + j], sh, st, comp, acc, ctrl_warp, acc_cls, W, lo,
+                                      loss, sums);
     }
 }
 
 template <int NC, int PV>
-__global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedParams a) {
+__global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ arr, const int* __restrict__ off, int n) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ FusedParams a;            // this block's plan
+    const int pi = find_plan(off, n, blockIdx.x);
+    {
+        const int* src = reinterpret_cast<const int*>(arr + pi);
+        int* dst = reinterpret_cast<int*>(&a);
+        for (int i = threadIdx.x; i < (int)(sizeof(FusedParams) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t task = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const int64_t task = (int64_t)(blockIdx.x - off[pi]) * kWarpsPerBlock + warp;
     if (task >= a.n_tasks) return;
     const int tile = (int)(task % a.n_tiles);
     const int group = (int)(task / a.n_tiles);
@@ -465,21 +505,15 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
             continue;
         }
 
-        const double2* px = reinterpret_cast<const double2*>(ring + (size_t)s * kTileBytes) + lane * 2;
-        const double2 x01 = px[0], x23 = px[1], y01 = px[kTile / 2], y23 = px[kTile / 2 + 1],
-                      i01 = px[kTile], i23 = px[kTile + 1];
-
         double sums[NQP];
 #pragma unroll
         for (int q = 0; q < NQP; ++q) sums[q] = 0.0;
-        const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
-        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
-        const double wv[4] = {i01.x, i01.y, i23.x, i23.y};
 
         if (rec.dense == 0) {
             // smooth row: branch-free sliding
-            if ((i & 1) == 0) fused_run_fast<NC, PV, +1>(xv, yv, wv, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
-            else fused_run_fast<NC, PV, -1>(xv, yv, wv, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+            const double* pl4 = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane * kPixPerLane;
+            if ((i & 1) == 0) fused_run_fast<NC, PV, +1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+            else fused_run_fast<NC, PV, -1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
         } else {
             // general row (pixels a knot or more apart, non-monotone x), lane by lane when the lanes
             // of one class could touch the same knots (rec.dense & 1)
@@ -491,9 +525,8 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const __grid_constant__ FusedPara
 #pragma unroll 1
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = (i & 1) ? 3 - jj : jj;
-                        const double xj = j == 0 ? xv[0] : j == 1 ? xv[1] : j == 2 ? xv[2] : xv[3];
-                        const double yj = j == 0 ? yv[0] : j == 1 ? yv[1] : j == 2 ? yv[2] : yv[3];
-                        const double wj = j == 0 ? wv[0] : j == 1 ? wv[1] : j == 2 ? wv[2] : wv[3];
+                        const double* pj = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane * kPixPerLane + j;
+                        const double xj = pj[0], yj = pj[kTile], wj = pj[2 * kTile];
                         fused_pixel<NC, PV, +1>(xj, yj, wj, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
                     }
                     if (serial) {   // lanes take turns: nothing may stay in registers across turns
@@ -556,6 +589,7 @@ struct ReduceParams {
     const int* stretch_rowptr[kMaxComp]; const int* stretch_rows[kMaxComp];
     int64_t n_rows, n_tasks;
     int n_tiles, n_groups, wincap;
+    int nb_knot, nb_ctrl;   // block layout of k_reduce_stage1
     const double* part; const int* part_base; const double* rowpart; const double* losspart;
     double* tmp;        // [n_comp][n_groups][max_knots]
     double* rowsum;     // [E][NQ]
@@ -569,12 +603,16 @@ struct ReduceParams {
 
 // blocks [0, nb_ctrl): tmp[c][g][k] = sum over tiles of the group, in tile order, of the windows
 // covering knot k.  blocks [nb_ctrl, ...): rowsum[r][q] = sum over tiles of rowpart.
-__global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
+__global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
+    const int pi = find_plan(off, n, blockIdx.x);
+    const ReduceParams& a = arr[pi];
+    const int blk = blockIdx.x - off[pi];
+    const int nb_knot = a.nb_knot, nb_ctrl = a.nb_ctrl;
     const int NQ = a.n_comp == 1 ? 4 : 8;
-    if ((int)blockIdx.x < nb_ctrl) {
-        const int kb = blockIdx.x % nb_knot;
-        const int g = (blockIdx.x / nb_knot) % a.n_groups;
-        const int c = blockIdx.x / (nb_knot * a.n_groups);
+    if (blk < nb_ctrl) {
+        const int kb = blk % nb_knot;
+        const int g = (blk / nb_knot) % a.n_groups;
+        const int c = blk / (nb_knot * a.n_groups);
         const int k = kb * blockDim.x + threadIdx.x;
         if (k >= a.comp[c].n_knots) return;
         double s = 0.0;
@@ -587,7 +625,7 @@ __global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
         }
         a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + k] = s;
     } else {
-        const int64_t i = (int64_t)(blockIdx.x - nb_ctrl) * blockDim.x + threadIdx.x;
+        const int64_t i = (int64_t)(blk - nb_ctrl) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * NQ) return;
         const int64_t r = i / NQ;
         const int q = (int)(i - r * NQ);
@@ -602,9 +640,11 @@ __global__ void k_reduce_stage1(ReduceParams a, int nb_knot, int nb_ctrl) {
 //   d loss / d shift[key] = +coef * PV/dx * sum wr*a*S'          (d/d shift of S(x - shift) = -S')
 //   d loss / d stretch[k] = -coef * sum wr*S
 //   F[key]                = (PV/dx)^2 * sum ivar*(a*S')^2        (model.py:893-897; no coefficient)
-__global__ void k_reduce_stage2(ReduceParams a) {
+__global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
+    const int pi = find_plan(off, n, blockIdx.x);
+    const ReduceParams& a = arr[pi];
     const int NQ = a.n_comp == 1 ? 4 : 8;
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t i = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
     for (int c = 0; c < a.n_comp; ++c) {
         const int M = a.comp[c].n_knots;
         if (i < M) {
@@ -639,8 +679,12 @@ __global__ void k_reduce_stage2(ReduceParams a) {
 }
 
 // Block 0: loss = 0.5 * coef * sum_tasks losspart, fixed-shape tree.  Other blocks: gather.
-__global__ void k_finish(ReduceParams a) {
-    if (blockIdx.x == 0) {
+__global__ void k_finish(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n, double* out_override) {
+    const int pi = find_plan(off, n, blockIdx.x);
+    const ReduceParams& a = arr[pi];
+    const int blk = blockIdx.x - off[pi];
+    double* out = out_override ? out_override : a.out;
+    if (blk == 0) {
         __shared__ double sh[1024];
         double s = 0.0;
         for (int64_t r = threadIdx.x; r < a.n_tasks; r += blockDim.x) s += a.losspart[r];
@@ -650,10 +694,10 @@ __global__ void k_finish(ReduceParams a) {
             if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) a.out[0] = 0.5 * a.coef * sh[0];
+        if (threadIdx.x == 0) out[0] = 0.5 * a.coef * sh[0];
     } else {
-        const int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
-        if (i < a.n_fit) a.out[1 + i] = a.grad_all[a.fit_map[i]];
+        const int64_t i = (int64_t)(blk - 1) * blockDim.x + threadIdx.x;
+        if (i < a.n_fit) out[1 + i] = a.grad_all[a.fit_map[i]];
     }
 }
 

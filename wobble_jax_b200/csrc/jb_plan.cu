@@ -93,10 +93,33 @@ struct jb_plan {
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
     int64_t tiles_kind[4] = {0, 0, 0, 0};   // smooth, general, serial, empty
 
+    // device-resident parameter blocks of the evaluation kernels (one launch can serve many plans)
+    struct Pack { jb::ScatterParams sc; jb::PrepareParams pr; jb::FusedParams fu; jb::ReduceParams re; };
+    Pack* h_pack = nullptr;   // pinned
+    Pack* d_pack = nullptr;
+    int* d_off = nullptr;     // [6][2] block ranges {0, nb} of the six kernels for this plan alone
+    int nb[6] = {0, 0, 0, 0, 0, 0};
+    bool pack_dirty = true;
+
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // pool, reused
     size_t prof_used = 0;
     cudaStream_t prof_stream = nullptr;
+};
+
+struct jb_batch {
+    std::vector<jb_plan*> plans;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<const double*> p_fit;
+    std::vector<double*> out;
+    std::vector<void*> dev;
+    jb::ScatterParams* d_sc = nullptr; jb::PrepareParams* d_pr = nullptr;
+    jb::FusedParams* d_fu = nullptr; jb::ReduceParams* d_re = nullptr;
+    int* d_off = nullptr;
+    int total[6] = {0, 0, 0, 0, 0, 0};
+    bool scatter = true, dirty = true;
+    int64_t launches = 0;
 };
 
 namespace {
@@ -123,9 +146,10 @@ int dev_upload(jb_plan* pl, T** out, const std::vector<T>& h) {
 
 int choose_rows_per_group(int64_t E, int n_tiles, int requested) {
     if (requested > 0) return (int)std::min<int64_t>(std::min(requested, jb::kMaxGroup), std::max<int64_t>(E, 1));
-    // enough tasks to fill 148 SMs x 12 resident warps several times over, but as many rows per
-    // group as that allows: each task writes one gradient window however many rows it streamed
-    const int64_t want_tasks = 148LL * 12 * 4;
+    // as many rows per group as still leave every resident warp a task: a task pays its set-up
+    // (row records, control-point window, final window write) once however many rows it streams,
+    // and several plans usually run side by side on their own streams
+    const int64_t want_tasks = 148LL * 8 * 3 / 2;   // 1.5 x the warps resident on 148 SMs
     int64_t g = (E * n_tiles) / want_tasks;
     g = std::max<int64_t>(1, std::min<int64_t>(g, jb::kMaxGroup));
     return (int)std::min<int64_t>(g, std::max<int64_t>(E, 1));
@@ -140,6 +164,7 @@ int alloc_scratch(jb_plan* pl) {
     if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_comp * pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_losspart, (size_t)pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_comp * pl->n_groups * pl->max_knots, true))) return rc;
+    pl->pack_dirty = true;
     return JB_OK;
 }
 
@@ -178,29 +203,8 @@ int resort_rows(jb_plan* pl) {
     return JB_OK;
 }
 
-template <int NC, int PV>
-int launch_fused_t(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
-    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>(pl->wincap);
-    JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock;
-    jb::k_fused<NC, PV><<<(unsigned)blocks, jb::kWarpsPerBlock * 32, smem, st>>>(fp);
-    JB_CUDA(cudaGetLastError());
-    pl->launches++;
-    return JB_OK;
-}
-
-int launch_fused(jb_plan* pl, const jb::FusedParams& fp, cudaStream_t st) {
-    const int pv = pl->desc[0].p_val;
-    switch (pl->n_comp * 10 + pv) {
-        case 11: return launch_fused_t<1, 1>(pl, fp, st);
-        case 12: return launch_fused_t<1, 2>(pl, fp, st);
-        case 13: return launch_fused_t<1, 3>(pl, fp, st);
-        case 21: return launch_fused_t<2, 1>(pl, fp, st);
-        case 22: return launch_fused_t<2, 2>(pl, fp, st);
-        case 23: return launch_fused_t<2, 3>(pl, fp, st);
-    }
-    return fail(JB_ERR_UNSUPPORTED, "no fused kernel for %d components of degree %d", pl->n_comp, pv);
-}
+// Kernel ids in launch order.
+enum { K_SCATTER = 0, K_PREPARE, K_FUSED, K_STAGE1, K_STAGE2, K_FINISH, K_COUNT };
 
 int check_supported_for_eval(const jb_plan* pl) {
     if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
@@ -214,11 +218,25 @@ int check_supported_for_eval(const jb_plan* pl) {
     return JB_OK;
 }
 
-void fill_reduce_params(jb_plan* pl, jb::ReduceParams& rp, double* d_out) {
-    memset(&rp, 0, sizeof rp);
+// (Re)build the plan's parameter blocks and block counts; uploaded on the plan's stream.
+int refresh_pack(jb_plan* pl) {
+    if (!pl->pack_dirty) return JB_OK;
+    JB_CUDA(cudaStreamSynchronize(pl->stream));   // the pinned copy may still be in flight
+    jb_plan::Pack& k = *pl->h_pack;
+    memset(&k, 0, sizeof k);
+    k.sc.p_fit = pl->d_pfit; k.sc.fit_map = pl->d_fit_map; k.sc.params = pl->d_params; k.sc.n_fit = pl->n_fit;
+    k.pr.row_perm = pl->d_row_perm; k.pr.grouprec = pl->d_grouprec; k.pr.n_rows = pl->E; k.pr.n_comp = pl->n_comp;
+    jb::FusedParams& fp = k.fu;
+    fp.data = pl->d_data; fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
+    fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
+    fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
+    fp.n_comp = pl->n_comp;
+    fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
+    fp.losspart = pl->d_losspart; fp.status = pl->d_status;
+    jb::ReduceParams& rp = k.re;
     rp.n_comp = pl->n_comp;
     for (int c = 0; c < pl->n_comp; ++c) {
-        rp.comp[c] = pl->comp[c];
+        k.pr.comp[c] = fp.comp[c] = rp.comp[c] = pl->comp[c];
         rp.ctrl_off[c] = pl->desc[c].ctrl_offset;
         rp.shift_off[c] = pl->desc[c].shift_offset;
         rp.stretch_off[c] = pl->desc[c].stretch_offset;
@@ -233,7 +251,83 @@ void fill_reduce_params(jb_plan* pl, jb::ReduceParams& rp, double* d_out) {
     rp.coef = pl->coef;
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
     rp.fit_map = pl->d_fit_map; rp.n_fit = pl->n_fit;
-    rp.out = d_out; rp.status = pl->d_status;
+    rp.out = pl->d_out; rp.status = pl->d_status;
+    const int NQ = pl->n_comp == 1 ? 4 : 8;
+    rp.nb_knot = (int)((pl->max_knots + 127) / 128);
+    rp.nb_ctrl = rp.nb_knot * pl->n_groups * pl->n_comp;
+    int64_t n2 = 0;
+    for (int c = 0; c < pl->n_comp; ++c) n2 += pl->comp[c].n_knots + rp.n_shift[c] + rp.n_stretch[c];
+    pl->nb[K_SCATTER] = (int)std::max<int64_t>(1, (pl->n_fit + 255) / 256);
+    pl->nb[K_PREPARE] = (int)((pl->E + 127) / 128);
+    pl->nb[K_FUSED] = (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
+    pl->nb[K_STAGE1] = rp.nb_ctrl + (int)((pl->E * NQ + 127) / 128);
+    pl->nb[K_STAGE2] = (int)((n2 + 255) / 256);
+    pl->nb[K_FINISH] = (int)(1 + (pl->n_fit + 1023) / 1024);
+    int off[K_COUNT][2];
+    for (int i = 0; i < K_COUNT; ++i) { off[i][0] = 0; off[i][1] = pl->nb[i]; }
+    JB_CUDA(cudaMemcpyAsync(pl->d_pack, pl->h_pack, sizeof k, cudaMemcpyHostToDevice, pl->stream));
+    JB_CUDA(cudaMemcpyAsync(pl->d_off, off, sizeof off, cudaMemcpyHostToDevice, pl->stream));
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    pl->pack_dirty = false;
+    return JB_OK;
+}
+
+// What one launch sequence needs: where the parameter blocks of the n plans live.
+struct LaunchSet {
+    const jb::ScatterParams* sc; const jb::PrepareParams* pr; const jb::FusedParams* fu; const jb::ReduceParams* re;
+    const int* off[K_COUNT]; // n+1 block offsets per kernel
+    int total[K_COUNT];
+    int n;
+    int n_comp, p_val, wincap;
+    bool scatter;
+};
+
+template <int NC, int PV>
+int launch_fused_t(const LaunchSet& L, cudaStream_t st) {
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>(L.wincap);
+    JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jb::k_fused<NC, PV><<<(unsigned)L.total[K_FUSED], jb::kWarpsPerBlock * 32, smem, st>>>(L.fu, L.off[K_FUSED], L.n);
+    JB_CUDA(cudaGetLastError());
+    return JB_OK;
+}
+
+// Six launches for the n plans of L (n = 1: the plan's own blocks; n > 1: the dense arrays of a jb_batch).
+int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override, double* out_override,
+               jb_plan* prof /* may be null */) {
+    if (L.scatter)
+        jb::k_scatter_params<<<(unsigned)L.total[K_SCATTER], 256, 0, st>>>(L.sc, L.off[K_SCATTER], L.n, p_fit_override);
+    if (L.n_comp == 1) jb::k_prepare_rows<1><<<(unsigned)L.total[K_PREPARE], 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+    else jb::k_prepare_rows<2><<<(unsigned)L.total[K_PREPARE], 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+    if (prof && prof->profiling) {
+        if (prof->prof_used == prof->prof_events.size()) {
+            cudaEvent_t a, b;
+            JB_CUDA(cudaEventCreate(&a));
+            JB_CUDA(cudaEventCreate(&b));
+            prof->prof_events.emplace_back(a, b);
+        }
+        JB_CUDA(cudaEventRecord(prof->prof_events[prof->prof_used].first, st));
+    }
+    int rc;
+    switch (L.n_comp * 10 + L.p_val) {
+        case 11: rc = launch_fused_t<1, 1>(L, st); break;
+        case 12: rc = launch_fused_t<1, 2>(L, st); break;
+        case 13: rc = launch_fused_t<1, 3>(L, st); break;
+        case 21: rc = launch_fused_t<2, 1>(L, st); break;
+        case 22: rc = launch_fused_t<2, 2>(L, st); break;
+        case 23: rc = launch_fused_t<2, 3>(L, st); break;
+        default: rc = fail(JB_ERR_UNSUPPORTED, "no fused kernel for %d components of degree %d", L.n_comp, L.p_val);
+    }
+    if (rc) return rc;
+    if (prof && prof->profiling) {
+        JB_CUDA(cudaEventRecord(prof->prof_events[prof->prof_used].second, st));
+        prof->prof_used++;
+        prof->prof_stream = st;
+    }
+    jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], 128, 0, st>>>(L.re, L.off[K_STAGE1], L.n);
+    jb::k_reduce_stage2<<<(unsigned)L.total[K_STAGE2], 256, 0, st>>>(L.re, L.off[K_STAGE2], L.n);
+    jb::k_finish<<<(unsigned)L.total[K_FINISH], 1024, 0, st>>>(L.re, L.off[K_FINISH], L.n, out_override);
+    JB_CUDA(cudaGetLastError());
+    return JB_OK;
 }
 
 // Enqueue one evaluation on `st`.  d_p_fit may be null (keep current parameters).
@@ -242,63 +336,14 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     if (rc) return rc;
     if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "jb_plan_set_params has not been called");
     if (pl->sort_dirty && (rc = resort_rows(pl))) return rc;
-
-    if (d_p_fit && pl->n_fit > 0) {
-        jb::ScatterParams sp{d_p_fit, pl->d_fit_map, pl->d_params, pl->n_fit};
-        jb::k_scatter_params<<<(unsigned)((pl->n_fit + 255) / 256), 256, 0, st>>>(sp);
-        pl->launches++;
-    }
-    {
-        jb::PrepareParams pp;
-        memset(&pp, 0, sizeof pp);
-        pp.row_perm = pl->d_row_perm; pp.grouprec = pl->d_grouprec; pp.n_rows = pl->E; pp.n_comp = pl->n_comp;
-        for (int c = 0; c < pl->n_comp; ++c) pp.comp[c] = pl->comp[c];
-        const unsigned nb = (unsigned)((pl->E + 127) / 128);
-        if (pl->n_comp == 1) jb::k_prepare_rows<1><<<nb, 128, 0, st>>>(pp);
-        else jb::k_prepare_rows<2><<<nb, 128, 0, st>>>(pp);
-        pl->launches++;
-    }
-    jb::FusedParams fp;
-    memset(&fp, 0, sizeof fp);
-    fp.data = pl->d_data;
-    fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
-    fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
-    fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
-    fp.n_comp = pl->n_comp;
-    for (int c = 0; c < pl->n_comp; ++c) fp.comp[c] = pl->comp[c];
-    fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
-    fp.losspart = pl->d_losspart;
-    fp.status = pl->d_status;
-    if (pl->profiling) {
-        if (pl->prof_used == pl->prof_events.size()) {
-            cudaEvent_t a, b;
-            JB_CUDA(cudaEventCreate(&a));
-            JB_CUDA(cudaEventCreate(&b));
-            pl->prof_events.emplace_back(a, b);
-        }
-        JB_CUDA(cudaEventRecord(pl->prof_events[pl->prof_used].first, st));
-    }
-    if ((rc = launch_fused(pl, fp, st))) return rc;
-    if (pl->profiling) {
-        JB_CUDA(cudaEventRecord(pl->prof_events[pl->prof_used].second, st));
-        pl->prof_used++;
-        pl->prof_stream = st;
-    }
-
-    jb::ReduceParams rp;
-    fill_reduce_params(pl, rp, d_out);
-    const int NQ = pl->n_comp == 1 ? 4 : 8;
-    const int tpb = 128;
-    const int nb_knot = (int)((pl->max_knots + tpb - 1) / tpb);
-    const int nb_ctrl = nb_knot * pl->n_groups * pl->n_comp;
-    const int nb_rows = (int)((pl->E * NQ + tpb - 1) / tpb);
-    jb::k_reduce_stage1<<<nb_ctrl + nb_rows, tpb, 0, st>>>(rp, nb_knot, nb_ctrl);
-    int64_t n2 = 0;
-    for (int c = 0; c < pl->n_comp; ++c) n2 += pl->comp[c].n_knots + rp.n_shift[c] + rp.n_stretch[c];
-    jb::k_reduce_stage2<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(rp);
-    jb::k_finish<<<(unsigned)(1 + (pl->n_fit + 1023) / 1024), 1024, 0, st>>>(rp);
-    JB_CUDA(cudaGetLastError());
-    pl->launches += 3;
+    if ((rc = refresh_pack(pl))) return rc;
+    LaunchSet L;
+    L.sc = &pl->d_pack->sc; L.pr = &pl->d_pack->pr; L.fu = &pl->d_pack->fu; L.re = &pl->d_pack->re;
+    for (int i = 0; i < K_COUNT; ++i) { L.off[i] = pl->d_off + 2 * i; L.total[i] = pl->nb[i]; }
+    L.n = 1; L.n_comp = pl->n_comp; L.p_val = pl->desc[0].p_val; L.wincap = pl->wincap;
+    L.scatter = d_p_fit != nullptr && pl->n_fit > 0;
+    if ((rc = launch_all(L, st, d_p_fit, d_out, pl))) return rc;
+    pl->launches += L.scatter ? 6 : 5;
     pl->evaluations++;
     return JB_OK;
 }
@@ -368,6 +413,7 @@ void jb_plan_destroy(jb_plan* pl) {
     if (pl->h_pfit) cudaFreeHost(pl->h_pfit);
     if (pl->h_out) cudaFreeHost(pl->h_out);
     if (pl->h_status) cudaFreeHost(pl->h_status);
+    if (pl->h_pack) cudaFreeHost(pl->h_pack);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
 }
@@ -582,6 +628,9 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     if ((rc = dev_alloc(pl, &pl->d_status, 2))) return rc;
     JB_CUDA(cudaMemset(pl->d_status, 0, 2 * sizeof(int)));
     JB_CUDA(cudaMallocHost(&pl->h_status, 2 * sizeof(int)));
+    if ((rc = dev_alloc(pl, &pl->d_pack, 1))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_off, 2 * K_COUNT))) return rc;
+    JB_CUDA(cudaMallocHost(&pl->h_pack, sizeof(jb_plan::Pack)));
     // a fit map of length zero until jb_plan_set_fit is called
     if ((rc = dev_alloc(pl, &pl->d_fit_map, 1))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_pfit, 1))) return rc;
@@ -643,6 +692,7 @@ int jb_plan_set_fit(jb_plan* pl, const int64_t* fit_index, int64_t n_fit) {
     JB_CUDA(cudaMallocHost(&pl->h_pfit, std::max<int64_t>(n_fit, 1) * sizeof(double)));
     JB_CUDA(cudaMallocHost(&pl->h_out, (n_fit + 1) * sizeof(double)));
     pl->n_fit = n_fit;
+    pl->pack_dirty = true;
     return JB_OK;
 }
 
@@ -687,8 +737,9 @@ int jb_plan_forward(jb_plan* pl, const double* p_fit, int64_t n_fit, double* mod
         if (!p_fit) return fail(JB_ERR_BAD_ARG, "null p_fit");
         memcpy(pl->h_pfit, p_fit, n_fit * sizeof(double));
         JB_CUDA(cudaMemcpyAsync(pl->d_pfit, pl->h_pfit, n_fit * sizeof(double), cudaMemcpyHostToDevice, st));
-        jb::ScatterParams sp{pl->d_pfit, pl->d_fit_map, pl->d_params, n_fit};
-        jb::k_scatter_params<<<(unsigned)((n_fit + 255) / 256), 256, 0, st>>>(sp);
+        int rc = refresh_pack(pl);
+        if (rc) return rc;
+        jb::k_scatter_params<<<(unsigned)pl->nb[K_SCATTER], 256, 0, st>>>(&pl->d_pack->sc, pl->d_off + 2 * K_SCATTER, 1, pl->d_pfit);
         pl->launches++;
     }
     double* d_model = nullptr;
@@ -749,6 +800,121 @@ int jb_plan_profile_read(jb_plan* pl, double* fused_ms_total, int64_t* n_launche
     pl->prof_used = 0;
     return JB_OK;
 }
+
+int jb_batch_create(jb_plan* const* plans, int32_t n, jb_batch** out) {
+    if (!plans || n <= 0 || !out) return fail(JB_ERR_BAD_ARG, "bad batch");
+    *out = nullptr;
+    jb_plan* p0 = plans[0];
+    for (int i = 0; i < n; ++i) {
+        jb_plan* pl = plans[i];
+        if (!pl) return fail(JB_ERR_BAD_ARG, "null plan in batch");
+        int rc = check_supported_for_eval(pl);
+        if (rc) return rc;
+        if (pl->device != p0->device) return fail(JB_ERR_BAD_ARG, "plans of a batch must live on one device");
+        if (pl->n_comp != p0->n_comp || pl->desc[0].p_val != p0->desc[0].p_val)
+            return fail(JB_ERR_UNSUPPORTED, "plans of a batch must share the model shape (components, spline degree)");
+        if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "plan %d: jb_plan_set_params has not been called", i);
+    }
+    JB_CUDA(cudaSetDevice(p0->device));
+    jb_batch* b = new jb_batch;
+    b->plans.assign(plans, plans + n);
+    b->device = p0->device;
+    JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->dirty = true;
+    *out = b;
+    return JB_OK;
+}
+
+void jb_batch_destroy(jb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* q : b->dev) cudaFree(q);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int jb_batch_bind(jb_batch* b, const double* const* d_p_fit, double* const* d_out) {
+    if (!b || !d_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    b->p_fit.assign(b->plans.size(), nullptr);
+    if (d_p_fit) b->p_fit.assign(d_p_fit, d_p_fit + b->plans.size());
+    b->out.assign(d_out, d_out + b->plans.size());
+    b->dirty = true;
+    return JB_OK;
+}
+
+int jb_batch_eval_device(jb_batch* b, void* stream) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    if (b->out.size() != b->plans.size()) return fail(JB_ERR_BAD_ARG, "jb_batch_bind has not been called");
+    JB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    const int n = (int)b->plans.size();
+    int rc;
+    bool regroup = b->dirty;
+    for (jb_plan* pl : b->plans) {
+        if (pl->sort_dirty) { if ((rc = resort_rows(pl))) return rc; }
+        if (pl->pack_dirty) regroup = true;
+        if ((rc = refresh_pack(pl))) return rc;
+        if (pl->wincap != b->plans[0]->wincap) {   // one kernel launch -> one shared-memory layout
+            int w = 0;
+            for (jb_plan* q : b->plans) w = std::max(w, q->wincap);
+            for (jb_plan* q : b->plans)
+                if (q->wincap != w) { q->wincap = w; if ((rc = alloc_scratch(q))) return rc; if ((rc = refresh_pack(q))) return rc; }
+            regroup = true;
+        }
+    }
+    if (regroup) {
+        JB_CUDA(cudaStreamSynchronize(st));
+        for (void* q : b->dev) cudaFree(q);
+        b->dev.clear();
+        std::vector<jb::ScatterParams> sc(n); std::vector<jb::PrepareParams> pr(n);
+        std::vector<jb::FusedParams> fu(n); std::vector<jb::ReduceParams> re(n);
+        std::vector<int> off((size_t)K_COUNT * (n + 1), 0);
+        b->scatter = true;
+        for (int i = 0; i < n; ++i) {
+            const jb_plan::Pack& k = *b->plans[i]->h_pack;
+            sc[i] = k.sc; pr[i] = k.pr; fu[i] = k.fu; re[i] = k.re;
+            sc[i].p_fit = b->p_fit.empty() ? nullptr : b->p_fit[i];
+            re[i].out = b->out[i];
+            for (int q = 0; q < K_COUNT; ++q) off[(size_t)q * (n + 1) + i + 1] = off[(size_t)q * (n + 1) + i] + b->plans[i]->nb[q];
+        }
+        for (int q = 0; q < K_COUNT; ++q) b->total[q] = off[(size_t)q * (n + 1) + n];
+        auto up = [&](const void* h, size_t bytes, void** d) -> int {
+            JB_CUDA(cudaMalloc(d, bytes));
+            b->dev.push_back(*d);
+            JB_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+            return JB_OK;
+        };
+        if ((rc = up(sc.data(), n * sizeof sc[0], (void**)&b->d_sc))) return rc;
+        if ((rc = up(pr.data(), n * sizeof pr[0], (void**)&b->d_pr))) return rc;
+        if ((rc = up(fu.data(), n * sizeof fu[0], (void**)&b->d_fu))) return rc;
+        if ((rc = up(re.data(), n * sizeof re[0], (void**)&b->d_re))) return rc;
+        if ((rc = up(off.data(), off.size() * sizeof(int), (void**)&b->d_off))) return rc;
+        b->dirty = false;
+    }
+    LaunchSet L;
+    L.sc = b->d_sc; L.pr = b->d_pr; L.fu = b->d_fu; L.re = b->d_re;
+    for (int q = 0; q < K_COUNT; ++q) { L.off[q] = b->d_off + (size_t)q * (n + 1); L.total[q] = b->total[q]; }
+    L.n = n; L.n_comp = b->plans[0]->n_comp; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
+    L.scatter = !b->p_fit.empty();
+    if ((rc = launch_all(L, st, nullptr, nullptr, b->plans[0]))) return rc;
+    b->launches += L.scatter ? 6 : 5;
+    for (jb_plan* pl : b->plans) pl->evaluations++;
+    return JB_OK;
+}
+
+int jb_batch_check(jb_batch* b) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    JB_CUDA(cudaSetDevice(b->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    for (jb_plan* pl : b->plans) {
+        int rc = read_status(pl, pl->stream, nullptr);
+        if (rc) return rc;
+    }
+    return JB_OK;
+}
+
+int64_t jb_batch_launches(const jb_batch* b) { return b ? b->launches : 0; }
 
 int jb_plan_grad_all(jb_plan* pl, double* grad_all, int64_t n) {
     if (!pl || !grad_all) return fail(JB_ERR_BAD_ARG, "null argument");

@@ -289,6 +289,40 @@ class Plan:
         return ms.value, n.value
 
 
+class Batch:
+    """Independent plans (chunks) evaluated with one launch per kernel (``jb_batch``)."""
+
+    def __init__(self, plans):
+        self.lib = _lib.load()
+        self.plans = list(plans)
+        arr = (C.c_void_p * len(self.plans))(*[p.handle for p in self.plans])
+        handle = C.c_void_p()
+        _lib.check(self.lib.jb_batch_create(arr, len(self.plans), C.byref(handle)))
+        self.handle = handle
+
+    def bind(self, d_p_fit_ptrs, d_out_ptrs):
+        n = len(self.plans)
+        pf = (C.c_void_p * n)(*d_p_fit_ptrs) if d_p_fit_ptrs is not None else None
+        po = (C.c_void_p * n)(*d_out_ptrs)
+        _lib.check(self.lib.jb_batch_bind(self.handle, pf, po))
+
+    def eval_device(self, stream_ptr=0):
+        _lib.check(self.lib.jb_batch_eval_device(self.handle, C.c_void_p(stream_ptr)))
+
+    def check(self):
+        _lib.check(self.lib.jb_batch_check(self.handle))
+
+    def launches(self):
+        return int(self.lib.jb_batch_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.jb_batch_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
 def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_group=0):
     spec = TreeSpec(model)
     plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,

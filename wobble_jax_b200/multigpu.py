@@ -92,6 +92,9 @@ class EpochShardedObjective:
         self.dev = torch.device("cuda", device)
         self.d_p = torch.empty(max(self.n_fit, 1), dtype=torch.float64, device=self.dev)
         self.d_out = torch.empty(self.n_fit + 1, dtype=torch.float64, device=self.dev)
+        # a real stream (the C ABI reads NULL as "the plan's own stream"), made current for the copies
+        # and the all-reduce so that everything is ordered on it
+        self.stream = torch.cuda.Stream(self.dev)
         self._p = None
         self._f = None
         self._g = None
@@ -100,11 +103,11 @@ class EpochShardedObjective:
         torch = self.torch
         p = np.asarray(p, dtype=np.float64).reshape(-1)
         if self._p is None or not np.array_equal(p, self._p):
-            stream = torch.cuda.current_stream(self.dev)
-            self.d_p[:self.n_fit].copy_(torch.from_numpy(p), non_blocking=True)
-            self.plan.eval_device(self.d_p.data_ptr(), self.d_out.data_ptr(), stream.cuda_stream)
-            all_reduce_sum(self.d_out, self.group)
-            out = self.d_out.cpu().numpy()
+            with torch.cuda.stream(self.stream):
+                self.d_p[:self.n_fit].copy_(torch.from_numpy(p), non_blocking=True)
+                self.plan.eval_device(self.d_p.data_ptr(), self.d_out.data_ptr(), self.stream.cuda_stream)
+                all_reduce_sum(self.d_out, self.group)
+                out = self.d_out.cpu().numpy()
             self.plan.check()
             self._f, self._g, self._p = float(out[0]), out[1:].copy(), p.copy()
         return self._f, self._g
