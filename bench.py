@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -299,6 +299,11 @@ def run_b200(args, rank, world, local_rank):
     e2e_value = px_step * args.steps / (e2e_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     achieved = info["algorithmic_bytes"] / (fused_avg_ms * 1e-3) / 1e9
+    traffic = None     # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and (args.epochs, args.pixels, args.p_val) == (2000, 4096, 3):
+        with open(tpath) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -315,7 +320,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"k_fused<2,{args.p_val}>", "kernel_ms": fused_avg_ms,
+                     "traffic": traffic, "kernel": f"k_fused<2,{args.p_val}>", "kernel_ms": fused_avg_ms,
                      "algorithmic_bytes_per_launch": int(info["algorithmic_bytes"]), "peak_source": peak_src,
                      "timed": "CUDA events around the kernel on its stream, one chunk at a time (no overlap)"},
         "plan": {k: info[k] for k in ("n_tasks", "rows_per_group", "tile_pixels", "device_bytes", "scratch_bytes", "n_fit")},

@@ -76,7 +76,9 @@ __global__ void k_prepare_rows(const PrepareParams* __restrict__ arr, const int*
 // ------------------------------------------------------------------------------------------
 // Data layout in HBM ("tile-interleaved"): for every (row r, tile t) one contiguous record of
 //   x[kTile] | y[kTile] | ivar[kTile]      (3 * kTile doubles = 3072 B)
-// at offset (r * n_tiles + t) * kTileDoubles.  The mask is folded into the data at upload: a masked
+// at offset (r * n_tiles + t) * kTileDoubles; inside each array pixel p of the tile is stored at
+// [(p % 4) * 32 + p / 4], i.e. lane-interleaved: lane l of the warp that owns the tile walks pixels
+// 4l..4l+3 and finds them at l, 32 + l, 64 + l, 96 + l -- one bank per lane.  The mask is folded into the data at upload: a masked
 // or padded pixel gets ivar = 0, y = 0 and the x of the nearest weighted pixel before it in the row
 // (so it is evaluated on knots the lane already holds and contributes exactly 0 to every sum),
 // which is what where(~mask, ., 0) of ChiSquare does to value and cotangent.  The forward kernel
@@ -189,6 +191,7 @@ __host__ __device__ constexpr size_t fused_warp_smem(int wincap) {
 template <int PV>
 struct Acc {
     double a[PV + 1];   // adjoint sums of knots klo .. klo+PV accumulated by this lane
+    double c[PV + 1];   // control points of those knots (fast path only; refreshed at every row start)
     int klo;
 };
 
@@ -272,12 +275,15 @@ __device__ __forceinline__ void fused_pixel(double x, double y, double iv, const
 // direction, so the per-pixel code needs no branch: the slide is folded into the accumulation
 // (the addend of the FMA is the neighbour's accumulator when the window moved).
 template <int PV, int DIR>
-__device__ __forceinline__ void acc_reposition(Acc<PV>& A, int kl, double* accw, int base) {
-    // row start: bring the window to the first pixel of the row (usually already there)
+__device__ __forceinline__ void acc_reposition(Acc<PV>& A, int kl, const double* ctrlw, double* accw, int base) {
+    // row start: bring the window to the first pixel of the row (usually already there) and take
+    // its control points into registers
     if (kl != A.klo) {
         acc_flush<PV>(A, accw, base);
         A.klo = kl;
     }
+#pragma unroll
+    for (int k = 0; k <= PV; ++k) A.c[k] = ctrlw[kl + k - base];
 }
 
 template <int NC, int PV, int DIR>
@@ -293,33 +299,34 @@ __device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, 
         double g; int I;
         knot_coord<PV>(x, sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
         const int kl = knot_lo<PV>(I);
-        step[c] = kl != acc[c].klo;
+        Acc<PV>& A = acc[c];
+        step[c] = kl != A.klo;
         double* accw = acc_cls + c * kClasses * W;
-#ifndef JB_EXP_NORMW
-        if (step[c]) {                              // retire the knot that leaves the window
-            if (DIR > 0) accw[acc[c].klo - lo[c]] += acc[c].a[0];
-            else accw[acc[c].klo + PV - lo[c]] += acc[c].a[PV];
+        const double* ctrlw = ctrl_warp + c * W;
+        // the knot that enters the window / the one that leaves it
+        double cnew = DIR > 0 ? A.c[PV] : A.c[0];
+        if (step[c]) {
+            if (DIR > 0) { accw[A.klo - lo[c]] += A.a[0]; cnew = ctrlw[kl + PV - lo[c]]; }
+            else { accw[A.klo + PV - lo[c]] += A.a[PV]; cnew = ctrlw[kl - lo[c]]; }
         }
-#endif
-        acc[c].klo = kl;
-        const double* cw = ctrl_warp + c * W + (kl - lo[c]);
-        double cv[PV + 1];
-#ifdef JB_EXP_NOCTRL
+        A.klo = kl;
+        if (DIR > 0) {
 #pragma unroll
-        for (int k = 0; k <= PV; ++k) cv[k] = 0.25 * k + g;
-        (void)cw;
-#else
+            for (int k = 0; k < PV; ++k) A.c[k] = step[c] ? A.c[k + 1] : A.c[k];
+            A.c[PV] = cnew;
+        } else {
 #pragma unroll
-        for (int k = 0; k <= PV; ++k) cv[k] = cw[k];
-#endif
+            for (int k = PV; k > 0; --k) A.c[k] = step[c] ? A.c[k - 1] : A.c[k];
+            A.c[0] = cnew;
+        }
         double dw[PV];
         Basis<PV>::eval(g, w[c], dw);
-        double sv = cv[0] * w[c][0];
-        double d = (cv[1] - cv[0]) * dw[0];
+        double sv = A.c[0] * w[c][0];
+        double d = (A.c[1] - A.c[0]) * dw[0];
 #pragma unroll
-        for (int k = 1; k <= PV; ++k) sv = __fma_rn(cv[k], w[c][k], sv);
+        for (int k = 1; k <= PV; ++k) sv = __fma_rn(A.c[k], w[c][k], sv);
 #pragma unroll
-        for (int k = 1; k < PV; ++k) d = __fma_rn(cv[k + 1] - cv[k], dw[k], d);
+        for (int k = 1; k < PV; ++k) d = __fma_rn(A.c[k + 1] - A.c[k], dw[k], d);
         S[c] = sv; dS[c] = d;
         m = __fma_rn(st[c], sv, m);
     }
@@ -344,8 +351,9 @@ __device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, 
     }
 }
 
-// the four pixels of a lane in walking order; px = the lane's first pixel in the staged row
-// (x at px[j], y at px[kTile + j], ivar at px[2 * kTile + j])
+// the four pixels of a lane in walking order; px = the lane's column in the staged record, which
+// is stored pixel-slot-major: pixel 4*lane + j of the tile sits at [j * 32 + lane] (conflict-free
+// shared-memory reads), x | y | ivar kTile doubles apart
 template <int NC, int PV, int DIR>
 __device__ __forceinline__ void fused_run_fast(const double* px, const double (&sh)[NC], const double (&st)[NC],
                                                const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
@@ -355,18 +363,18 @@ __device__ __forceinline__ void fused_run_fast(const double* px, const double (&
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         double g; int I;
-        knot_coord<PV>(px[j0], sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
-        acc_reposition<PV, DIR>(acc[c], knot_lo<PV>(I), acc_cls + c * kClasses * W, lo[c]);
+        knot_coord<PV>(px[32 * j0], sh[c], comp[c].xp0, comp[c].inv_dx, g, I);
+        acc_reposition<PV, DIR>(acc[c], knot_lo<PV>(I), ctrl_warp + c * W, acc_cls + c * kClasses * W, lo[c]);
     }
-#ifdef JB_ROLLED
-#pragma unroll 1
-#else
-#pragma unroll
+#ifndef JB_PIXEL_UNROLL
+#define JB_PIXEL_UNROLL 1
 #endif
+    constexpr int kPixelUnroll = JB_PIXEL_UNROLL;
+#pragma unroll kPixelUnroll
     for (int jj = 0; jj < 4; ++jj) {
         const int j = DIR > 0 ? jj : 3 - jj;
-        fused_pixel_fast<NC, PV, DIR>(px[j], px[kTile + j], px[2 * kTile + j], sh, st, comp, acc, ctrl_warp, acc_cls, W, lo,
-                                      loss, sums);
+        fused_pixel_fast<NC, PV, DIR>(px[32 * j], px[kTile + 32 * j], px[2 * kTile + 32 * j], sh, st, comp, acc, ctrl_warp,
+                                      acc_cls, W, lo, loss, sums);
     }
 }
 
@@ -511,7 +519,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
 
         if (rec.dense == 0) {
             // smooth row: branch-free sliding
-            const double* pl4 = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane * kPixPerLane;
+            const double* pl4 = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane;
             if ((i & 1) == 0) fused_run_fast<NC, PV, +1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
             else fused_run_fast<NC, PV, -1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
         } else {
@@ -525,7 +533,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
 #pragma unroll 1
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = (i & 1) ? 3 - jj : jj;
-                        const double* pj = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane * kPixPerLane + j;
+                        const double* pj = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane + 32 * j;
                         const double xj = pj[0], yj = pj[kTile], wj = pj[2 * kTile];
                         fused_pixel<NC, PV, +1>(xj, yj, wj, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
                     }

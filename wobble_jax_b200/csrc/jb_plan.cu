@@ -503,7 +503,9 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
         for (int64_t p = 0; p < ppad; ++p) {
             const int64_t src = rev ? P - 1 - p : p;
             const int t = (int)(p / jb::kTile);
-            double* rec = hdata.data() + ((size_t)r * NT + t) * jb::kTileDoubles + p % jb::kTile;
+            const int pt = (int)(p % jb::kTile);   // lane-interleaved position inside the record
+            double* rec = hdata.data() + ((size_t)r * NT + t) * jb::kTileDoubles +
+                          (pt % jb::kPixPerLane) * 32 + pt / jb::kPixPerLane;
             const bool w = p < P && weighted(src);
             if (p < P) hx[(size_t)r * ppad + p] = std::isfinite(xr[src]) ? xr[src] : 0.0;
             if (w) {
