@@ -120,7 +120,9 @@ def cpu_baseline(args, budget_s, nthreads=0):
     from oracle import c_oracle
     from wobble_jax_b200 import synth
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    cores = c_oracle.lib().jbo_max_threads() if nthreads <= 0 else nthreads
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the
+    # CPU arm is about)
+    cores = len(os.sched_getaffinity(0)) if nthreads <= 0 else nthreads
     rows = min(args.epochs, max(8 * cores, 64))
     ch = synth.make_chunk(0, n_epochs=rows, n_pix=args.pixels, p_val=args.p_val, as_block=True)
     model = synth.fit_all(ch.model)
