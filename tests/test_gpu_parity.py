@@ -210,3 +210,49 @@ def test_batched_launch_equals_per_plan_results():
         assert o[0] == f and np.array_equal(o[1:], g)
     assert batch.launches() == 12
     batch.close()
+
+
+def test_golden_pseudonormal():
+    """Wobble + normalisation tree (quickplay.get_wobble_model + get_normalization_model,
+    07-apogee-cframes shape): loss, gradient incl. the per-row control points, forward, Fisher."""
+    from helpers import pseudonormal_from_golden
+    g = load_golden("pseudonormal.npz")
+    data = dataset_from_golden(g)
+    model, meta = pseudonormal_from_golden(g, data)
+    db, mb, dbd, mbd = _blocks(data)
+    loss = jabble.loss.ChiSquare()
+    for ci, fits in enumerate(json.loads(str(g["cases"]))):
+        set_fit(model, fits)
+        p = g[f"pn_case{ci}_p"]
+        obj = engine.Objective(loss, model, db, mb)
+        val, grad = obj.value(p), obj.gradient(p)
+        assert abs(val - float(g[f"pn_case{ci}_loss"])) <= TOL * abs(val), ci
+        _check_grad(model, grad, g[f"pn_case{ci}_grad"])
+    model.fix()
+    fwd = engine.build_plan(model, db, mb).forward()
+    keep = ~db["mask"]
+    assert rel_err(fwd[keep], g["forward"][keep]) < TOL
+    assert rel_err(model[0][0].f_info(model, data), g["f_info"]) < TOL
+
+
+@pytest.mark.parametrize("p_val,npv,npts,E,P", [(3, 2, 4, 24, 1100), (2, 3, 6, 9, 700), (3, 1, 3, 40, 2048)])
+def test_normalisation_vs_c_oracle(p_val, npv, npts, E, P):
+    import subprocess, os
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")])
+    from oracle import c_oracle
+    ch = synth.make_chunk(chunk=5, n_epochs=E, n_pix=P, p_val=p_val, n_lines=15, ragged=True)
+    rng = np.random.default_rng(7)
+    model = ch.model + jabble.quickplay.get_normalization_model(ch.data, npv, npts)
+    model[2][1].p = rng.normal(0, 0.02, model[2][1].p.shape)
+    model.fix()
+    for f in [(0, 0), (0, 1), (1, 1), (1, 2), (2, 0), (2, 1)]:
+        model.fit(*f)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    obj = engine.Objective(jabble.loss.ChiSquare(), model, db, mb)
+    val, grad = obj.value(p), obj.gradient(p)
+    oval, ograd, _, _ = c_oracle.evaluate(p, dbd, mbd, model)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    obj._p = None
+    assert obj.value(p) == val and np.array_equal(obj.gradient(p), grad)

@@ -45,7 +45,12 @@ __global__ void k_scatter_params(const ScatterParams* __restrict__ arr, const in
 // ------------------------------------------------------------------------------------------
 // Per-row parameters in sorted-row order, refreshed every evaluation (the shifts are fit parameters):
 // grouprec[pos] = { shift_c, stretch_c (c < NC), row id } for the row at sorted position pos.
-template <int NC> struct alignas(16) RowRec { double sh[NC]; double st[NC]; int row; int dense; int pad_[2]; };
+// HN = 1 when the plan has a per-key (NormalizationModel) spline component: its shift, stretch and
+// key ride in the same record.
+template <int NC, int HN> struct alignas(16) RowRec {
+    double sh[NC + HN]; double st[NC + HN]; int row; int dense; int nkey; int pad_;
+};
+constexpr int kNormMaxKnots = 32;   // knots per key of a normalisation spline handled on chip
 
 struct PrepareParams {
     const int* row_perm;
@@ -55,22 +60,23 @@ struct PrepareParams {
     CompDev comp[kMaxComp];
 };
 
-template <int NC>
+template <int NC, int HN>
 __global__ void k_prepare_rows(const PrepareParams* __restrict__ arr, const int* __restrict__ off, int n) {
     const int pi = find_plan(off, n, blockIdx.x);
     const PrepareParams& a = arr[pi];
     const int64_t pos = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
     if (pos >= a.n_rows) return;
     const int r = a.row_perm[pos];
-    RowRec<NC> rec;
+    RowRec<NC, HN> rec;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
+    for (int c = 0; c < NC + HN; ++c) {
         const CompDev& cd = a.comp[c];
         rec.sh[c] = cd.shift ? cd.shift[cd.shift_key[r]] : 0.0;
         rec.st[c] = cd.stretch ? cd.stretch[cd.stretch_key[r]] : 1.0;
     }
-    rec.row = r; rec.dense = 0; rec.pad_[0] = rec.pad_[1] = 0;
-    reinterpret_cast<RowRec<NC>*>(a.grouprec)[pos] = rec;
+    rec.row = r; rec.dense = 0; rec.pad_ = 0;
+    rec.nkey = HN ? a.comp[NC].ctrl_key[r] : 0;
+    reinterpret_cast<RowRec<NC, HN>*>(a.grouprec)[pos] = rec;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -177,16 +183,95 @@ struct FusedParams {
     int* part_base;      // [n_comp][n_tasks] first knot of the window (INT_MAX: empty)
     double* rowpart;     // [E][n_tiles][NQP]   per-row sums: (d/dshift, d/dstretch, Fisher) per component
     double* losspart;    // [n_tasks] sum of ivar*res^2 of the task
+    double* normpart;    // [E][n_tiles][norm_stride] gradient of the row's normalisation control points
+    int norm_stride;     // knots per key rounded up to 4 (<= 32)
     int* status;         // [0] error bits  [1] rows that took the serial path
 };
 
-template <int NC> struct RowQ { static constexpr int NQP = (NC == 1) ? 4 : 8; };
+// per-row sums: (d/dshift, d/dstretch, Fisher) per global component, (d/dshift, d/dstretch) for the
+// normalisation component; padded to 4 or 8 for the multi-value warp reduction
+template <int NC, int HN> struct RowQ { static constexpr int NQ = NC * kRowQ + HN * 2; static constexpr int NQP = NQ <= 4 ? 4 : 8; };
+__host__ __device__ constexpr int row_sum_stride(int n_global, int has_norm) { return (n_global * kRowQ + has_norm * 2) <= 4 ? 4 : 8; }
 
-template <int NC>
+template <int NC, int HN>
 __host__ __device__ constexpr size_t fused_warp_smem(int wincap) {
     return ((size_t)NC * kClasses * wincap * 8 + (size_t)NC * wincap * 8 + (size_t)kStages * kTileBytes +
-            (size_t)kMaxGroup * sizeof(RowRec<NC>) + kStages * 8 + 127) / 128 * 128;
+            (size_t)kMaxGroup * sizeof(RowRec<NC, HN>) + (size_t)HN * 3 * kNormMaxKnots * 8 + kStages * 8 + 127) / 128 * 128;
 }
+
+// ---- normalisation component (NormalizationModel over a CardinalSplineMixture, model.py:1110-1143)
+// Few knots, hundreds of pixels per knot interval: a lane's 4 pixels sit in one interval or straddle
+// one knot (enforced at upload), so the lane keeps PVN+2 control points and PVN+2 adjoint sums for
+// the whole row in registers, indexed from the interval of its lowest pixel; after the row the lanes
+// are summed by knot with warp shuffles (lanes grouped by base knot, in lane order).
+template <int PVN>
+struct NormLane {
+    static constexpr int NS = PVN + 2;
+    double c[PVN + 2];
+    double a[PVN + 2];
+    int kbase;
+};
+
+template <int PVN>
+__device__ __forceinline__ void norm_begin(NormLane<PVN>& N, double x_low, double sh, const CompDev& cd, const double* nctrl, int& bad) {
+    double g; int I;
+    knot_coord<PVN>(x_low, sh, cd.xp0, cd.inv_dx, g, I);
+    N.kbase = knot_lo<PVN>(I);
+    const double t = ((x_low - sh) - cd.xp0) * cd.inv_dx;
+    if (!(t > -1.0e9 && t < 1.0e9) || N.kbase < 0 || N.kbase + PVN + 1 > cd.n_knots) { bad = 1; N.kbase = 0; }
+#pragma unroll
+    for (int s = 0; s < PVN + 2; ++s) {
+        N.c[s] = nctrl[min(N.kbase + s, kNormMaxKnots - 1)];
+        N.a[s] = 0.0;
+    }
+}
+
+// value S and derivative dS (per knot, before the PVN/dx factor) at x; ws = basis weights placed on
+// the lane's PVN+2 slots
+template <int PVN>
+__device__ __forceinline__ void norm_eval(const NormLane<PVN>& N, double x, double sh, const CompDev& cd,
+                                          double (&ws)[PVN + 2], double& S, double& dS, int& bad) {
+    double g; int I;
+    knot_coord<PVN>(x, sh, cd.xp0, cd.inv_dx, g, I);
+    const int o = knot_lo<PVN>(I) - N.kbase;            // 0 or 1 by construction of the plan
+    if (o < 0 || o > 1 || (o == 1 && N.kbase + PVN + 2 > cd.n_knots)) bad = 1;
+    const bool up = o >= 1;
+    double w[PVN + 1], dw[PVN];
+    Basis<PVN>::eval(g, w, dw);
+    double e[PVN + 1];                                   // dS = sum_k c[k] * e[k]
+    e[0] = -dw[0];
+#pragma unroll
+    for (int k = 1; k < PVN; ++k) e[k] = dw[k - 1] - dw[k];
+    e[PVN] = dw[PVN - 1];
+    S = 0.0; dS = 0.0;
+#pragma unroll
+    for (int s = 0; s < PVN + 2; ++s) {
+        const double wl = s <= PVN ? w[s] : 0.0, wh = s >= 1 ? w[s - 1] : 0.0;
+        const double el = s <= PVN ? e[s] : 0.0, eh = s >= 1 ? e[s - 1] : 0.0;
+        ws[s] = up ? wh : wl;
+        S = __fma_rn(N.c[s], ws[s], S);
+        dS = __fma_rn(N.c[s], up ? eh : el, dS);
+    }
+}
+
+// sum the lanes' adjoints by knot into rowg[0..K) (shared memory, this warp), lanes grouped by base knot
+template <int PVN>
+__device__ __forceinline__ void norm_reduce(const NormLane<PVN>& N, int lane, double* rowg) {
+    unsigned remaining = 0xffffffffu;
+    while (remaining) {
+        const int cur = __shfl_sync(0xffffffffu, N.kbase, __ffs(remaining) - 1);
+        const bool mine = N.kbase == cur;
+        double v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = (s < PVN + 2 && mine) ? N.a[s < PVN + 2 ? s : 0] : 0.0;
+        const double tot = warp_sum_multi<8>(v, lane);
+        const int s = lane >> 2;
+        if ((lane & 3) == 0 && s < PVN + 2 && cur + s < kNormMaxKnots) rowg[cur + s] += tot;
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
+        __syncwarp();
+    }
+}
+
 
 template <int PV>
 struct Acc {
@@ -229,13 +314,19 @@ __device__ __forceinline__ void acc_move(Acc<PV>& A, int kl, double* accw, int b
     A.klo += step ? DIR : 0;
 }
 
-template <int NC, int PV, int DIR>
-__device__ __forceinline__ void fused_pixel(double x, double y, double iv, const double (&sh)[NC], const double (&st)[NC],
+template <int NC, int PV, int PVN, int DIR>
+__device__ __forceinline__ void fused_pixel(double x, double y, double iv, const double* sh, const double* st,
                                             const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
                                             double* acc_cls, const int W, const int (&lo)[NC], double& loss,
-                                            double (&sums)[RowQ<NC>::NQP]) {
+                                            double (&sums)[RowQ<NC, (PVN > 0)>::NQP], NormLane<PVN>& nl, int& bad) {
     double w[NC][PV + 1], S[NC], dS[NC];
     double m = 0.0;
+    double nws[PVN + 2], nS = 0.0, ndS = 0.0;
+    (void)nws; (void)ndS;
+    if constexpr (PVN > 0) {
+        norm_eval<PVN>(nl, x, sh[NC], comp[NC], nws, nS, ndS, bad);
+        m = st[NC] * nS;
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         double g; int I;
@@ -268,6 +359,13 @@ __device__ __forceinline__ void fused_pixel(double x, double y, double iv, const
         sums[c * kRowQ + 1] = __fma_rn(wr, S[c], sums[c * kRowQ + 1]);              // d/d stretch
         sums[c * kRowQ + 2] = __fma_rn(iv * dS[c], dS[c], sums[c * kRowQ + 2]);     // Fisher
     }
+    if constexpr (PVN > 0) {
+        const double q = wr * st[NC];
+#pragma unroll
+        for (int k = 0; k < PVN + 2; ++k) nl.a[k] = __fma_rn(q, nws[k], nl.a[k]);
+        sums[NC * kRowQ + 0] = __fma_rn(q, ndS, sums[NC * kRowQ + 0]);
+        sums[NC * kRowQ + 1] = __fma_rn(wr, nS, sums[NC * kRowQ + 1]);
+    }
 }
 
 // ---- fast path: rows whose consecutive pixels are less than one knot apart ("smooth" rows) ------
@@ -286,14 +384,20 @@ __device__ __forceinline__ void acc_reposition(Acc<PV>& A, int kl, const double*
     for (int k = 0; k <= PV; ++k) A.c[k] = ctrlw[kl + k - base];
 }
 
-template <int NC, int PV, int DIR>
-__device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, const double (&sh)[NC], const double (&st)[NC],
+template <int NC, int PV, int PVN, int DIR>
+__device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, const double* sh, const double* st,
                                                  const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
                                                  double* acc_cls, const int W, const int (&lo)[NC], double& loss,
-                                                 double (&sums)[RowQ<NC>::NQP]) {
+                                                 double (&sums)[RowQ<NC, (PVN > 0)>::NQP], NormLane<PVN>& nl, int& bad) {
     double w[NC][PV + 1], S[NC], dS[NC];
     bool step[NC];
     double m = 0.0;
+    double nws[PVN + 2], nS = 0.0, ndS = 0.0;
+    (void)nws; (void)ndS;
+    if constexpr (PVN > 0) {
+        norm_eval<PVN>(nl, x, sh[NC], comp[NC], nws, nS, ndS, bad);
+        m = st[NC] * nS;
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         double g; int I;
@@ -349,16 +453,23 @@ __device__ __forceinline__ void fused_pixel_fast(double x, double y, double iv, 
         sums[c * kRowQ + 1] = __fma_rn(wr, S[c], sums[c * kRowQ + 1]);
         sums[c * kRowQ + 2] = __fma_rn(iv * dS[c], dS[c], sums[c * kRowQ + 2]);
     }
+    if constexpr (PVN > 0) {
+        const double q = wr * st[NC];
+#pragma unroll
+        for (int k = 0; k < PVN + 2; ++k) nl.a[k] = __fma_rn(q, nws[k], nl.a[k]);
+        sums[NC * kRowQ + 0] = __fma_rn(q, ndS, sums[NC * kRowQ + 0]);
+        sums[NC * kRowQ + 1] = __fma_rn(wr, nS, sums[NC * kRowQ + 1]);
+    }
 }
 
 // the four pixels of a lane in walking order; px = the lane's column in the staged record, which
 // is stored pixel-slot-major: pixel 4*lane + j of the tile sits at [j * 32 + lane] (conflict-free
 // shared-memory reads), x | y | ivar kTile doubles apart
-template <int NC, int PV, int DIR>
-__device__ __forceinline__ void fused_run_fast(const double* px, const double (&sh)[NC], const double (&st)[NC],
+template <int NC, int PV, int PVN, int DIR>
+__device__ __forceinline__ void fused_run_fast(const double* px, const double* sh, const double* st,
                                                const CompDev* comp, Acc<PV> (&acc)[NC], const double* ctrl_warp,
                                                double* acc_cls, const int W, const int (&lo)[NC], double& loss,
-                                               double (&sums)[RowQ<NC>::NQP]) {
+                                               double (&sums)[RowQ<NC, (PVN > 0)>::NQP], NormLane<PVN>& nl, int& bad) {
     constexpr int j0 = DIR > 0 ? 0 : 3;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -373,12 +484,12 @@ __device__ __forceinline__ void fused_run_fast(const double* px, const double (&
 #pragma unroll kPixelUnroll
     for (int jj = 0; jj < 4; ++jj) {
         const int j = DIR > 0 ? jj : 3 - jj;
-        fused_pixel_fast<NC, PV, DIR>(px[32 * j], px[kTile + 32 * j], px[2 * kTile + 32 * j], sh, st, comp, acc, ctrl_warp,
-                                      acc_cls, W, lo, loss, sums);
+        fused_pixel_fast<NC, PV, PVN, DIR>(px[32 * j], px[kTile + 32 * j], px[2 * kTile + 32 * j], sh, st, comp, acc,
+                                           ctrl_warp, acc_cls, W, lo, loss, sums, nl, bad);
     }
 }
 
-template <int NC, int PV>
+template <int NC, int PV, int PVN>
 __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ arr, const int* __restrict__ off, int n) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ FusedParams a;            // this block's plan
@@ -396,15 +507,19 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
     const int group = (int)(task / a.n_tiles);
     const int row0 = group * a.rows_per_group;
     const int nrow = min(a.rows_per_group, (int)a.n_rows - row0);
-    constexpr int NQP = RowQ<NC>::NQP;
+    constexpr int HN = PVN > 0 ? 1 : 0;
+    constexpr int NQP = RowQ<NC, HN>::NQP;
+    using Rec = RowRec<NC, HN>;
     const int W = a.wincap;
 
-    unsigned char* wbase = smem_raw + (size_t)warp * fused_warp_smem<NC>(W);
+    unsigned char* wbase = smem_raw + (size_t)warp * fused_warp_smem<NC, HN>(W);
     double* acc_warp = reinterpret_cast<double*>(wbase);                     // [NC][kClasses][W]
     double* ctrl_warp = acc_warp + NC * kClasses * W;                        // [NC][W]
     unsigned char* ring = reinterpret_cast<unsigned char*>(ctrl_warp + NC * W);   // [kStages][kTileBytes]
-    RowRec<NC>* recs = reinterpret_cast<RowRec<NC>*>(ring + (size_t)kStages * kTileBytes);
-    const uint32_t bar0 = smem_u32(recs + kMaxGroup);                        // [kStages] mbarriers
+    Rec* recs = reinterpret_cast<Rec*>(ring + (size_t)kStages * kTileBytes);
+    double* nctrl = reinterpret_cast<double*>(recs + kMaxGroup);             // [2][kNormMaxKnots] control points of the row's key
+    double* rowg = nctrl + 2 * kNormMaxKnots * HN;                            // [kNormMaxKnots] gradient of the row's key
+    const uint32_t bar0 = smem_u32(rowg + kNormMaxKnots * HN);               // [kStages] mbarriers
 
     // ---- 0. lane i fetches the record of row i of the group: two independent loads ------------
     int lo[NC], hi[NC];
@@ -412,7 +527,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
     for (int c = 0; c < NC; ++c) { lo[c] = INT_MAX; hi[c] = INT_MIN; }
     bool has_work = false;
     if (lane < nrow) {
-        RowRec<NC> rec = reinterpret_cast<const RowRec<NC>*>(a.grouprec)[row0 + lane];
+        Rec rec = reinterpret_cast<const Rec*>(a.grouprec)[row0 + lane];
         const TileInfo ti = a.tinfo[(int64_t)tile * a.n_rows + row0 + lane];
         rec.dense = ti.flags;
         has_work = ti.flags != 2;
@@ -473,6 +588,9 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
     if (skip) {   // nothing weighted here (or an error): the row sums of this tile are zero
         for (int i = lane; i < nrow * NQP; i += 32)
             a.rowpart[((int64_t)recs[i / NQP].row * a.n_tiles + tile) * NQP + i % NQP] = 0.0;
+        if (HN)
+            for (int i = lane; i < nrow * a.norm_stride; i += 32)
+                a.normpart[((int64_t)recs[i / a.norm_stride].row * a.n_tiles + tile) * a.norm_stride + i % a.norm_stride] = 0.0;
         if (!empty)   // copies are in flight into this warp's ring: let them land before leaving
             for (int i = 0; i < kStages && i < nrow; ++i) mbar_wait(bar0 + 8 * (i % kStages), 0);
         return;
@@ -500,18 +618,33 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
     }
     int serial_rows = 0;
     double loss = 0.0;
+    int bad = 0;
+    NormLane<PVN> nl;
+    const int nK = HN ? a.comp[NC].n_knots : 0;
+    double nnext = 0.0;                  // control point `lane` of the NEXT row's key, fetched one row ahead
+    if (HN) {
+        if (lane < kNormMaxKnots) { rowg[lane] = 0.0; nctrl[lane] = lane < nK ? __ldg(a.comp[NC].ctrl + (int64_t)recs[0].nkey * nK + lane) : 0.0; }
+        __syncwarp();
+    }
 
     // ---- 4. stream the rows of the group ------------------------------------------------------
     for (int i = 0; i < nrow; ++i) {
         const int s = i % kStages;
-        const RowRec<NC> rec = recs[i];
+        const Rec rec = recs[i];
+        if (HN && i + 1 < nrow && lane < nK) nnext = __ldg(a.comp[NC].ctrl + (int64_t)recs[i + 1].nkey * nK + lane);
         mbar_wait(bar0 + 8 * s, (uint32_t)((i / kStages) & 1));
         if (rec.dense == 2) {          // no weighted pixel in this row of the tile
             if (lane < NQP) a.rowpart[((int64_t)rec.row * a.n_tiles + tile) * NQP + lane] = 0.0;
+            if (HN) {
+                if (lane < a.norm_stride) a.normpart[((int64_t)rec.row * a.n_tiles + tile) * a.norm_stride + lane] = 0.0;
+                if (lane < kNormMaxKnots) nctrl[((i + 1) & 1) * kNormMaxKnots + lane] = nnext;
+            }
             __syncwarp();
             if (lane == 0 && i + kStages < nrow) issue_row(i + kStages, recs[i + kStages].row);
             continue;
         }
+        const double* pl4 = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane;
+        if constexpr (HN != 0) norm_begin<PVN>(nl, pl4[0], rec.sh[NC], a.comp[NC], nctrl + (i & 1) * kNormMaxKnots, bad);
 
         double sums[NQP];
 #pragma unroll
@@ -519,9 +652,8 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
 
         if (rec.dense == 0) {
             // smooth row: branch-free sliding
-            const double* pl4 = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane;
-            if ((i & 1) == 0) fused_run_fast<NC, PV, +1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
-            else fused_run_fast<NC, PV, -1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+            if ((i & 1) == 0) fused_run_fast<NC, PV, PVN, +1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums, nl, bad);
+            else fused_run_fast<NC, PV, PVN, -1>(pl4, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums, nl, bad);
         } else {
             // general row (pixels a knot or more apart, non-monotone x), lane by lane when the lanes
             // of one class could touch the same knots (rec.dense & 1)
@@ -535,7 +667,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
                         const int j = (i & 1) ? 3 - jj : jj;
                         const double* pj = reinterpret_cast<const double*>(ring + (size_t)s * kTileBytes) + lane + 32 * j;
                         const double xj = pj[0], yj = pj[kTile], wj = pj[2 * kTile];
-                        fused_pixel<NC, PV, +1>(xj, yj, wj, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums);
+                        fused_pixel<NC, PV, PVN, +1>(xj, yj, wj, rec.sh, rec.st, a.comp, acc, ctrl_warp, acc_cls, W, lo, loss, sums, nl, bad);
                     }
                     if (serial) {   // lanes take turns: nothing may stay in registers across turns
 #pragma unroll
@@ -556,6 +688,11 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
             for (int c = 0; c < NC; ++c)
                 if (q == c * kRowQ + 2) s2 = rec.st[c] * rec.st[c];
             a.rowpart[((int64_t)rec.row * a.n_tiles + tile) * NQP + q] = tot * s2;
+        }
+        if constexpr (HN != 0) {   // gradient of the row's own control points: lanes summed by knot, then one store per knot
+            norm_reduce<PVN>(nl, lane, rowg);
+            if (lane < a.norm_stride) a.normpart[((int64_t)rec.row * a.n_tiles + tile) * a.norm_stride + lane] = lane < kNormMaxKnots ? rowg[lane] : 0.0;
+            if (lane < kNormMaxKnots) { rowg[lane] = 0.0; nctrl[((i + 1) & 1) * kNormMaxKnots + lane] = nnext; }
         }
         // every lane has consumed stage s (the sums above depend on all of its data): refill it
         __syncwarp();
@@ -580,9 +717,11 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused(const FusedParams* __restrict__ a
         }
     }
     loss = warp_sum(loss);
+    bad = __any_sync(0xffffffffu, bad != 0);
     if (lane == 0) {
         a.losspart[task] = loss;
         if (serial_rows) atomicAdd(a.status + 1, serial_rows);
+        if (bad) atomicOr(a.status, kStatOutOfRange);
     }
 }
 
@@ -599,6 +738,12 @@ struct ReduceParams {
     int n_tiles, n_groups, wincap;
     int nb_knot, nb_ctrl;   // block layout of k_reduce_stage1
     const double* part; const int* part_base; const double* rowpart; const double* losspart;
+    // normalisation component (index n_comp, when has_norm): per-row gradients of its control points
+    int has_norm, norm_stride, norm_knots, n_norm_keys;
+    int64_t norm_ctrl_off;
+    const double* normpart; double* normrow;           // [E][n_tiles][norm_stride] -> [E][norm_stride]
+    const int* norm_rowptr; const int* norm_rows;      // key -> rows (CSR)
+    int nb_stage1_rows;                                 // blocks of the per-row tile sums in stage 1
     double* tmp;        // [n_comp][n_groups][max_knots]
     double* rowsum;     // [E][NQ]
     int64_t max_knots;
@@ -616,7 +761,7 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
     const ReduceParams& a = arr[pi];
     const int blk = blockIdx.x - off[pi];
     const int nb_knot = a.nb_knot, nb_ctrl = a.nb_ctrl;
-    const int NQ = a.n_comp == 1 ? 4 : 8;
+    const int NQ = row_sum_stride(a.n_comp, a.has_norm);
     if (blk < nb_ctrl) {
         const int kb = blk % nb_knot;
         const int g = (blk / nb_knot) % a.n_groups;
@@ -632,7 +777,7 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
                 s += a.part[((int64_t)c * a.n_tasks + task) * a.wincap + w];
         }
         a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + k] = s;
-    } else {
+    } else if (blk < nb_ctrl + a.nb_stage1_rows) {
         const int64_t i = (int64_t)(blk - nb_ctrl) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * NQ) return;
         const int64_t r = i / NQ;
@@ -640,6 +785,14 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
         double s = 0.0;
         for (int t = 0; t < a.n_tiles; ++t) s += a.rowpart[(r * a.n_tiles + t) * NQ + q];
         a.rowsum[i] = s;
+    } else {   // normalisation control points: per row, sum of the tile partials
+        const int64_t i = (int64_t)(blk - nb_ctrl - a.nb_stage1_rows) * blockDim.x + threadIdx.x;
+        if (i >= a.n_rows * a.norm_stride) return;
+        const int64_t r = i / a.norm_stride;
+        const int k = (int)(i - r * a.norm_stride);
+        double s = 0.0;
+        for (int t = 0; t < a.n_tiles; ++t) s += a.normpart[(r * a.n_tiles + t) * a.norm_stride + k];
+        a.normrow[i] = s;
     }
 }
 
@@ -651,11 +804,20 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
 __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
     const int pi = find_plan(off, n, blockIdx.x);
     const ReduceParams& a = arr[pi];
-    const int NQ = a.n_comp == 1 ? 4 : 8;
+    const int NQ = row_sum_stride(a.n_comp, a.has_norm);
     int64_t i = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
-    for (int c = 0; c < a.n_comp; ++c) {
-        const int M = a.comp[c].n_knots;
+    for (int c = 0; c < a.n_comp + a.has_norm; ++c) {
+        const bool is_norm = c == a.n_comp;
+        const int M = is_norm ? a.n_norm_keys * a.norm_knots : a.comp[c].n_knots;
         if (i < M) {
+            if (is_norm) {   // control point k of key: sum over the key's rows, in row order
+                const int key = (int)(i / a.norm_knots), k = (int)(i % a.norm_knots);
+                double s = 0.0;
+                for (int e = a.norm_rowptr[key]; e < a.norm_rowptr[key + 1]; ++e)
+                    s += a.normrow[(int64_t)a.norm_rows[e] * a.norm_stride + k];
+                a.grad_all[a.norm_ctrl_off + i] = -a.coef * s;
+                return;
+            }
             double s = 0.0;
             for (int g = 0; g < a.n_groups; ++g) s += a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + i];
             a.grad_all[a.ctrl_off[c] + i] = -a.coef * s;
@@ -667,11 +829,11 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
             for (int e = a.shift_rowptr[c][i]; e < a.shift_rowptr[c][i + 1]; ++e) {
                 const int64_t r = a.shift_rows[c][e];
                 gs += a.rowsum[r * NQ + c * kRowQ + 0];
-                fs += a.rowsum[r * NQ + c * kRowQ + 2];
+                if (!is_norm) fs += a.rowsum[r * NQ + c * kRowQ + 2];
             }
             const double sc = a.comp[c].p_val * a.comp[c].inv_dx;
             a.grad_all[a.shift_off[c] + i] = a.coef * sc * gs;
-            a.fisher_all[a.shift_off[c] + i] = sc * sc * fs;
+            if (!is_norm) a.fisher_all[a.shift_off[c] + i] = sc * sc * fs;
             return;
         }
         i -= a.n_shift[c];

@@ -54,7 +54,10 @@ struct jb_plan {
     bool has_data = false;   // ys / yivar present
     double coef = 1.0;
 
-    int n_comp = 0;
+    int n_comp = 0;            // components, stored globals (SPLINE) first, per-key (NORM_SPLINE) last
+    int n_glob = 0, has_norm = 0;
+    int ext_of[jb::kMaxComp] = {0, 1, 2};   // caller's index of the component stored at position i
+    bool norm_smooth = true;   // every lane run (4 pixels) spans less than one knot of the normalisation grid
     jb_component_desc desc[jb::kMaxComp];
     jb::CompDev comp[jb::kMaxComp];
 
@@ -84,10 +87,12 @@ struct jb_plan {
     int G = 0, n_groups = 0, wincap = 0;
     int64_t n_tasks = 0;
     double *d_part = nullptr, *d_rowpart = nullptr, *d_tmp = nullptr, *d_rowsum = nullptr, *d_losspart = nullptr;
+    double *d_normpart = nullptr, *d_normrow = nullptr;
+    int norm_stride = 0;
     int* d_part_base = nullptr;
     int64_t max_knots = 0;
-    int* d_key_ptr[jb::kMaxComp][2] = {};   // [comp][0 shift,1 stretch] CSR rowptr
-    int* d_key_rows[jb::kMaxComp][2] = {};
+    int* d_key_ptr[jb::kMaxComp][3] = {};   // [comp][0 shift, 1 stretch, 2 per-key control points] CSR rowptr
+    int* d_key_rows[jb::kMaxComp][3] = {};
     int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
 
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
@@ -160,10 +165,10 @@ int alloc_scratch(jb_plan* pl) {
     pl->n_groups = (int)((pl->E + pl->G - 1) / pl->G);
     pl->n_tasks = (int64_t)pl->n_groups * pl->n_tiles;
     int rc;
-    if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_comp * pl->n_tasks * pl->wincap, true))) return rc;
-    if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_comp * pl->n_tasks, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_glob * pl->n_tasks * pl->wincap, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_glob * pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_losspart, (size_t)pl->n_tasks, true))) return rc;
-    if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_comp * pl->n_groups * pl->max_knots, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_glob * pl->n_groups * pl->max_knots, true))) return rc;
     pl->pack_dirty = true;
     return JB_OK;
 }
@@ -208,13 +213,18 @@ enum { K_SCATTER = 0, K_PREPARE, K_FUSED, K_STAGE1, K_STAGE2, K_FINISH, K_COUNT 
 
 int check_supported_for_eval(const jb_plan* pl) {
     if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
-    for (int c = 0; c < pl->n_comp; ++c) {
-        if (pl->desc[c].kind != JB_COMP_SPLINE)
-            return fail(JB_ERR_UNSUPPORTED, "component %d: per-key (normalisation) splines are not in the fused kernel yet", c);
+    if (pl->n_glob < 1 || pl->n_glob > 2)
+        return fail(JB_ERR_UNSUPPORTED, "%d CardinalSplineMixture components (the fused kernel takes 1 or 2)", pl->n_glob);
+    if (pl->n_comp - pl->n_glob > 1) return fail(JB_ERR_UNSUPPORTED, "more than one NormalizationModel component");
+    for (int c = 0; c < pl->n_glob; ++c)
         if (pl->desc[c].p_val != pl->desc[0].p_val)
             return fail(JB_ERR_UNSUPPORTED, "components with different spline degrees (%d vs %d)", pl->desc[c].p_val, pl->desc[0].p_val);
+    if (pl->has_norm) {
+        if (pl->desc[pl->n_glob].n_knots > jb::kNormMaxKnots)
+            return fail(JB_ERR_UNSUPPORTED, "NormalizationModel with %lld knots per key (<= %d supported)", (long long)pl->desc[pl->n_glob].n_knots, jb::kNormMaxKnots);
+        if (!pl->norm_smooth)
+            return fail(JB_ERR_UNSUPPORTED, "normalisation knot grid finer than 4 pixels somewhere");
     }
-    if (pl->n_comp > 2) return fail(JB_ERR_UNSUPPORTED, "more than two spline components");
     return JB_OK;
 }
 
@@ -230,11 +240,20 @@ int refresh_pack(jb_plan* pl) {
     fp.data = pl->d_data; fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
     fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
     fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
-    fp.n_comp = pl->n_comp;
+    fp.n_comp = pl->n_glob;
+    fp.normpart = pl->d_normpart; fp.norm_stride = pl->norm_stride;
     fp.part = pl->d_part; fp.part_base = pl->d_part_base; fp.rowpart = pl->d_rowpart;
     fp.losspart = pl->d_losspart; fp.status = pl->d_status;
     jb::ReduceParams& rp = k.re;
-    rp.n_comp = pl->n_comp;
+    rp.n_comp = pl->n_glob;
+    rp.has_norm = pl->has_norm;
+    if (pl->has_norm) {
+        const int c = pl->n_glob;
+        rp.norm_stride = pl->norm_stride; rp.norm_knots = (int)pl->desc[c].n_knots; rp.n_norm_keys = (int)pl->desc[c].n_ctrl_keys;
+        rp.norm_ctrl_off = pl->desc[c].ctrl_offset;
+        rp.normpart = pl->d_normpart; rp.normrow = pl->d_normrow;
+        rp.norm_rowptr = pl->d_key_ptr[c][2]; rp.norm_rows = pl->d_key_rows[c][2];
+    }
     for (int c = 0; c < pl->n_comp; ++c) {
         k.pr.comp[c] = fp.comp[c] = rp.comp[c] = pl->comp[c];
         rp.ctrl_off[c] = pl->desc[c].ctrl_offset;
@@ -252,15 +271,17 @@ int refresh_pack(jb_plan* pl) {
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
     rp.fit_map = pl->d_fit_map; rp.n_fit = pl->n_fit;
     rp.out = pl->d_out; rp.status = pl->d_status;
-    const int NQ = pl->n_comp == 1 ? 4 : 8;
+    const int NQ = jb::row_sum_stride(pl->n_glob, pl->has_norm);
     rp.nb_knot = (int)((pl->max_knots + 127) / 128);
-    rp.nb_ctrl = rp.nb_knot * pl->n_groups * pl->n_comp;
+    rp.nb_ctrl = rp.nb_knot * pl->n_groups * pl->n_glob;
+    rp.nb_stage1_rows = (int)((pl->E * NQ + 127) / 128);
     int64_t n2 = 0;
-    for (int c = 0; c < pl->n_comp; ++c) n2 += pl->comp[c].n_knots + rp.n_shift[c] + rp.n_stretch[c];
+    for (int c = 0; c < pl->n_comp; ++c)
+        n2 += (c < pl->n_glob ? pl->comp[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys) + rp.n_shift[c] + rp.n_stretch[c];
     pl->nb[K_SCATTER] = (int)std::max<int64_t>(1, (pl->n_fit + 255) / 256);
     pl->nb[K_PREPARE] = (int)((pl->E + 127) / 128);
     pl->nb[K_FUSED] = (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
-    pl->nb[K_STAGE1] = rp.nb_ctrl + (int)((pl->E * NQ + 127) / 128);
+    pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + 127) / 128) : 0);
     pl->nb[K_STAGE2] = (int)((n2 + 255) / 256);
     pl->nb[K_FINISH] = (int)(1 + (pl->n_fit + 1023) / 1024);
     int off[K_COUNT][2];
@@ -278,17 +299,28 @@ struct LaunchSet {
     const int* off[K_COUNT]; // n+1 block offsets per kernel
     int total[K_COUNT];
     int n;
-    int n_comp, p_val, wincap;
+    int n_comp, p_val, pvn, wincap;   // global components, their degree, degree of the normalisation spline (0: none)
     bool scatter;
 };
 
-template <int NC, int PV>
+template <int NC, int PV, int PVN>
 int launch_fused_t(const LaunchSet& L, cudaStream_t st) {
-    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC>(L.wincap);
-    JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jb::k_fused<NC, PV><<<(unsigned)L.total[K_FUSED], jb::kWarpsPerBlock * 32, smem, st>>>(L.fu, L.off[K_FUSED], L.n);
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused_warp_smem<NC, (PVN > 0)>(L.wincap);
+    JB_CUDA(cudaFuncSetAttribute(jb::k_fused<NC, PV, PVN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jb::k_fused<NC, PV, PVN><<<(unsigned)L.total[K_FUSED], jb::kWarpsPerBlock * 32, smem, st>>>(L.fu, L.off[K_FUSED], L.n);
     JB_CUDA(cudaGetLastError());
     return JB_OK;
+}
+
+template <int NC, int PV>
+int launch_fused_n(const LaunchSet& L, cudaStream_t st) {
+    switch (L.pvn) {
+        case 0: return launch_fused_t<NC, PV, 0>(L, st);
+        case 1: return launch_fused_t<NC, PV, 1>(L, st);
+        case 2: return launch_fused_t<NC, PV, 2>(L, st);
+        case 3: return launch_fused_t<NC, PV, 3>(L, st);
+    }
+    return fail(JB_ERR_UNSUPPORTED, "normalisation spline of degree %d", L.pvn);
 }
 
 // Six launches for the n plans of L (n = 1: the plan's own blocks; n > 1: the dense arrays of a jb_batch).
@@ -296,8 +328,13 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
                jb_plan* prof /* may be null */) {
     if (L.scatter)
         jb::k_scatter_params<<<(unsigned)L.total[K_SCATTER], 256, 0, st>>>(L.sc, L.off[K_SCATTER], L.n, p_fit_override);
-    if (L.n_comp == 1) jb::k_prepare_rows<1><<<(unsigned)L.total[K_PREPARE], 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
-    else jb::k_prepare_rows<2><<<(unsigned)L.total[K_PREPARE], 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+    {
+        const unsigned nb = (unsigned)L.total[K_PREPARE];
+        if (L.n_comp == 1 && !L.pvn) jb::k_prepare_rows<1, 0><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+        else if (L.n_comp == 1) jb::k_prepare_rows<1, 1><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+        else if (!L.pvn) jb::k_prepare_rows<2, 0><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+        else jb::k_prepare_rows<2, 1><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
+    }
     if (prof && prof->profiling) {
         if (prof->prof_used == prof->prof_events.size()) {
             cudaEvent_t a, b;
@@ -309,12 +346,12 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
     }
     int rc;
     switch (L.n_comp * 10 + L.p_val) {
-        case 11: rc = launch_fused_t<1, 1>(L, st); break;
-        case 12: rc = launch_fused_t<1, 2>(L, st); break;
-        case 13: rc = launch_fused_t<1, 3>(L, st); break;
-        case 21: rc = launch_fused_t<2, 1>(L, st); break;
-        case 22: rc = launch_fused_t<2, 2>(L, st); break;
-        case 23: rc = launch_fused_t<2, 3>(L, st); break;
+        case 11: rc = launch_fused_n<1, 1>(L, st); break;
+        case 12: rc = launch_fused_n<1, 2>(L, st); break;
+        case 13: rc = launch_fused_n<1, 3>(L, st); break;
+        case 21: rc = launch_fused_n<2, 1>(L, st); break;
+        case 22: rc = launch_fused_n<2, 2>(L, st); break;
+        case 23: rc = launch_fused_n<2, 3>(L, st); break;
         default: rc = fail(JB_ERR_UNSUPPORTED, "no fused kernel for %d components of degree %d", L.n_comp, L.p_val);
     }
     if (rc) return rc;
@@ -340,7 +377,8 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     LaunchSet L;
     L.sc = &pl->d_pack->sc; L.pr = &pl->d_pack->pr; L.fu = &pl->d_pack->fu; L.re = &pl->d_pack->re;
     for (int i = 0; i < K_COUNT; ++i) { L.off[i] = pl->d_off + 2 * i; L.total[i] = pl->nb[i]; }
-    L.n = 1; L.n_comp = pl->n_comp; L.p_val = pl->desc[0].p_val; L.wincap = pl->wincap;
+    L.n = 1; L.n_comp = pl->n_glob; L.p_val = pl->desc[0].p_val; L.wincap = pl->wincap;
+    L.pvn = pl->has_norm ? pl->desc[pl->n_glob].p_val : 0;
     L.scatter = d_p_fit != nullptr && pl->n_fit > 0;
     if ((rc = launch_all(L, st, d_p_fit, d_out, pl))) return rc;
     pl->launches += L.scatter ? 6 : 5;
@@ -455,6 +493,16 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->has_data = d->ys != nullptr;
     pl->coef = d->coefficient;
     pl->n_comp = d->n_components;
+    // store the components globals first, the per-key (normalisation) ones last
+    std::vector<jb_component_desc> comps;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int c = 0; c < d->n_components; ++c)
+            if ((d->components[c].kind == JB_COMP_NORM_SPLINE) == (pass == 1)) {
+                pl->ext_of[comps.size()] = c;
+                comps.push_back(d->components[c]);
+                if (pass == 0) pl->n_glob++;
+            }
+    pl->has_norm = pl->n_comp - pl->n_glob == 1 ? 1 : 0;
     pl->n_params = d->n_params;
     const int64_t ppad = pl->ppad;
 
@@ -474,10 +522,12 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     std::vector<double> txmin((size_t)E * NT, INFINITY), txmax((size_t)E * NT, -INFINITY);
     std::vector<uint8_t> dense((size_t)E * NT, 0);
     double need = 0.0;   // knots two lanes of one class must be apart, in x units, 1 % margin
-    for (int c = 0; c < d->n_components; ++c)
-        need = std::max(need, (d->components[c].p_val + 1.01) * d->components[c].dx);
+    for (int c = 0; c < pl->n_glob; ++c)
+        need = std::max(need, (comps[c].p_val + 1.01) * comps[c].dx);
     double smooth = INFINITY;   // two pixels closer than this are at most one knot interval apart
-    for (int c = 0; c < d->n_components; ++c) smooth = std::min(smooth, 0.99 * d->components[c].dx);
+    for (int c = 0; c < pl->n_glob; ++c) smooth = std::min(smooth, 0.99 * comps[c].dx);
+    double norm_dx = INFINITY;  // a lane's 4 pixels must span less than one knot of every normalisation grid
+    for (int c = pl->n_glob; c < pl->n_comp; ++c) norm_dx = std::min(norm_dx, 0.99 * comps[c].dx);
     double any_x = 0.0;
     for (int64_t i = 0; i < E * P && any_x == 0.0; ++i)
         if ((!d->mask || !d->mask[i]) && std::isfinite(d->xs[i])) any_x = d->xs[i];
@@ -539,6 +589,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                     // inside a lane's run: a step of less than one knot of the finest grid, never backwards
                     if (j > 0 && !(hxf[i] >= hxf[i - 1] && hxf[i] - hxf[i - 1] < smooth)) jumpy = true;
                 }
+                if (any_w && !(lmax - lmin < norm_dx)) pl->norm_smooth = false;
                 double& cm = cmax[l % jb::kClasses];
                 if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
                 cm = std::max(cm, lmax);
@@ -557,7 +608,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     if ((rc = dev_alloc(pl, &pl->d_tinfo, (size_t)NT * E))) return rc;
     {
         char* rec = nullptr;
-        if ((rc = dev_alloc(pl, &rec, (size_t)E * sizeof(jb::RowRec<jb::kMaxComp>)))) return rc;
+        if ((rc = dev_alloc(pl, &rec, (size_t)E * sizeof(jb::RowRec<2, 1>)))) return rc;
         pl->d_grouprec = rec;
     }
     if ((rc = dev_upload(pl, &pl->d_data, hdata))) return rc;
@@ -578,7 +629,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     std::vector<int> ident(E);
     std::iota(ident.begin(), ident.end(), 0);
     for (int c = 0; c < pl->n_comp; ++c) {
-        const jb_component_desc& cd = d->components[c];
+        const jb_component_desc& cd = comps[c];
         pl->desc[c] = cd;
         pl->desc[c].ctrl_key = pl->desc[c].shift_key = pl->desc[c].stretch_key = nullptr;  // host pointers are not retained
         jb::CompDev& cv = pl->comp[c];
@@ -586,7 +637,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
         cv.kind = cd.kind; cv.p_val = cd.p_val; cv.n_knots = (int)cd.n_knots;
         cv.xp0 = cd.xp0; cv.inv_dx = 1.0 / cd.dx;
         cv.ctrl = pl->d_params + cd.ctrl_offset;
-        pl->max_knots = std::max<int64_t>(pl->max_knots, cd.n_knots);
+        if (cd.kind == JB_COMP_SPLINE) pl->max_knots = std::max<int64_t>(pl->max_knots, cd.n_knots);
         const int32_t* keys[3] = {cd.shift_key, cd.stretch_key, cd.ctrl_key};
         const int64_t nkeys[3] = {cd.shift_offset >= 0 ? cd.n_shift : 0, cd.stretch_offset >= 0 ? cd.n_stretch : 0,
                                   cd.kind == JB_COMP_NORM_SPLINE ? cd.n_ctrl_keys : 0};
@@ -598,7 +649,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                 if (k[r] < 0 || k[r] >= nkeys[s]) return fail(JB_ERR_BAD_ARG, "component %d: key %d of row %lld outside [0,%lld)", c, k[r], (long long)r, (long long)nkeys[s]);
             }
             if ((rc = dev_upload(pl, &pl->d_keys[c][s], k))) return rc;
-            if (s < 2) {   // CSR key -> rows, rows ascending: the fixed order of the per-key sums
+            {   // CSR key -> rows, rows ascending: the fixed order of the per-key sums
                 std::vector<int> ptr(nkeys[s] + 1, 0), rows(E);
                 for (int64_t r = 0; r < E; ++r) ptr[k[r] + 1]++;
                 for (int64_t i = 0; i < nkeys[s]; ++i) ptr[i + 1] += ptr[i];
@@ -619,10 +670,15 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     double max_knots_tile = 0.0;
     for (size_t i = 0; i < txmin.size(); ++i)
         if (txmin[i] <= txmax[i])
-            for (int c = 0; c < pl->n_comp; ++c)
-                max_knots_tile = std::max(max_knots_tile, (txmax[i] - txmin[i]) / d->components[c].dx + d->components[c].p_val + 2);
+            for (int c = 0; c < pl->n_glob; ++c)
+                max_knots_tile = std::max(max_knots_tile, (txmax[i] - txmin[i]) / comps[c].dx + comps[c].p_val + 2);
     pl->wincap = (int)std::min<double>(jb::kWinCapMax, std::max(64.0, std::ceil((max_knots_tile + 8) / 32.0) * 32.0));
-    const int NQ = pl->n_comp == 1 ? 4 : 8;
+    const int NQ = jb::row_sum_stride(pl->n_glob, pl->has_norm);
+    if (pl->has_norm) {
+        pl->norm_stride = (int)std::min<int64_t>(32, (comps[pl->n_glob].n_knots + 3) / 4 * 4);
+        if ((rc = dev_alloc(pl, &pl->d_normpart, (size_t)E * pl->n_tiles * pl->norm_stride, true))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_normrow, (size_t)E * pl->norm_stride, true))) return rc;
+    }
     pl->G = choose_rows_per_group(E, pl->n_tiles, d->rows_per_group);
     if ((rc = dev_alloc(pl, &pl->d_rowpart, (size_t)E * pl->n_tiles * NQ, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_rowsum, (size_t)E * NQ, true))) return rc;
@@ -765,7 +821,10 @@ int jb_plan_forward(jb_plan* pl, const double* p_fit, int64_t n_fit, double* mod
 int jb_plan_fisher(jb_plan* pl, int32_t component, double* f_out, int64_t n_shift) {
     if (!pl || !f_out) return fail(JB_ERR_BAD_ARG, "null argument");
     if (component < 0 || component >= pl->n_comp) return fail(JB_ERR_BAD_ARG, "component %d", component);
-    const jb_component_desc& cd = pl->desc[component];
+    int ci = 0;
+    while (pl->ext_of[ci] != component) ++ci;
+    if (ci >= pl->n_glob) return fail(JB_ERR_UNSUPPORTED, "Fisher information of a NormalizationModel shift is not computed");
+    const jb_component_desc& cd = pl->desc[ci];
     if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
     if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
     JB_CUDA(cudaSetDevice(pl->device));
@@ -813,7 +872,8 @@ int jb_batch_create(jb_plan* const* plans, int32_t n, jb_batch** out) {
         int rc = check_supported_for_eval(pl);
         if (rc) return rc;
         if (pl->device != p0->device) return fail(JB_ERR_BAD_ARG, "plans of a batch must live on one device");
-        if (pl->n_comp != p0->n_comp || pl->desc[0].p_val != p0->desc[0].p_val)
+        if (pl->n_glob != p0->n_glob || pl->has_norm != p0->has_norm || pl->desc[0].p_val != p0->desc[0].p_val ||
+            (pl->has_norm && pl->desc[pl->n_glob].p_val != p0->desc[p0->n_glob].p_val))
             return fail(JB_ERR_UNSUPPORTED, "plans of a batch must share the model shape (components, spline degree)");
         if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "plan %d: jb_plan_set_params has not been called", i);
     }
@@ -897,7 +957,8 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     LaunchSet L;
     L.sc = b->d_sc; L.pr = b->d_pr; L.fu = b->d_fu; L.re = b->d_re;
     for (int q = 0; q < K_COUNT; ++q) { L.off[q] = b->d_off + (size_t)q * (n + 1); L.total[q] = b->total[q]; }
-    L.n = n; L.n_comp = b->plans[0]->n_comp; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
+    L.n = n; L.n_comp = b->plans[0]->n_glob; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
+    L.pvn = b->plans[0]->has_norm ? b->plans[0]->desc[b->plans[0]->n_glob].p_val : 0;
     L.scatter = !b->p_fit.empty();
     if ((rc = launch_all(L, st, nullptr, nullptr, b->plans[0]))) return rc;
     b->launches += L.scatter ? 6 : 5;
