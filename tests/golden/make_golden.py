@@ -272,8 +272,42 @@ def fixture_pseudonormal():
     print("pseudonormal.npz", len(out))
 
 
+def fixture_regularised():
+    """ChiSquare + L2Reg on both templates + L1Reg on the shifts (02-51peg.ipynb cell 20 style), and L2Loss."""
+    rng = np.random.default_rng(404)
+    out = {}
+    E, P, R, pv = 5, 70, 100000, 3
+    xs, ys, ivs, ms, vel, air = make_rows(rng, E, P, R)
+    dataset = jabble.dataset.Data.from_lists(xs, ys, ivs, ms)
+    grid = jabble.model.create_x_grid(np.concatenate(xs), 60e3, 2 * R)
+    init_v = vel + rng.normal(0, 50.0, E)
+    model = jabble.quickplay.get_wobble_model(init_v, air, grid, pv)
+    model[0][1].p = jnp.array(perturb(rng, grid))
+    model[1][1].p = jnp.array(perturb(rng, grid))
+    loss = jabble.loss.ChiSquare() + jabble.loss.L2Reg([0, 1], coefficient=3.5, constant=0.01) \
+        + jabble.loss.L2Reg([1, 1], coefficient=0.7) + jabble.loss.L1Reg([0, 0], coefficient=11.0, constant=1e-5)
+    cases = [[(0, 0), (0, 1), (1, 1)], [(0, 0), (0, 1), (1, 1), (1, 2)]]
+    db, mb = run_fit_cases(model, dataset, cases, loss, out, "rg")
+    out["cases"] = json.dumps(cases)
+    out["repr"] = repr(loss)
+    l2 = jabble.loss.L2Loss() * 2.5
+    model.fix(); model.fit(0, 1); model.fit(1, 2)
+    p = model.get_parameters()
+    out["l2_p"] = npy(p)
+    out["l2_loss"] = npy(l2.loss_all(p, db, mb, model, DEV, 100))
+    out["l2_grad"] = npy(fakejax.jax.grad(l2.loss_all)(p, db, mb, model, DEV, 100))
+    model.fix()
+    for k, rows in (("xs", xs), ("ys", ys), ("ivs", ivs), ("ms", ms)):
+        ragged_pack(out, k, rows)
+    out.update(grid=grid, init_v=init_v, rest_v=np.zeros(E), airmass=air, S=npy(model[0][1].p), T=npy(model[1][1].p),
+               shift_p=npy(model[0][0].p), tshift_p=npy(model[1][0].p), stretch_p=npy(model[1][2].p),
+               meta=json.dumps({"E": E, "P": P, "p_val": pv, "R": R, "which_key": "index"}))
+    np.savez(os.path.join(HERE, "regularised.npz"), **out)
+    print("regularised.npz", len(out))
+
+
 if __name__ == "__main__":
-    todo = sys.argv[1:] or ["basis", "stellar", "wobble", "pseudonormal"]
+    todo = sys.argv[1:] or ["basis", "stellar", "wobble", "pseudonormal", "regularised"]
     if "basis" in todo:
         fixture_basis()
     if "stellar" in todo:
@@ -285,3 +319,5 @@ if __name__ == "__main__":
         fixture_wobble(3, "wobble_p3_keyed.npz", keyed=True, ragged=True)
     if "pseudonormal" in todo:
         fixture_pseudonormal()
+    if "regularised" in todo:
+        fixture_regularised()

@@ -256,3 +256,24 @@ def test_normalisation_vs_c_oracle(p_val, npv, npts, E, P):
     _check_grad(model, grad, ograd)
     obj._p = None
     assert obj.value(p) == val and np.array_equal(obj.gradient(p), grad)
+
+
+def test_golden_regularised_objective():
+    """ChiSquare + L2Reg + L2Reg + L1Reg and L2Loss through the reference-facing objects."""
+    g = load_golden("regularised.npz")
+    data = dataset_from_golden(g)
+    model, meta = wobble_from_golden(g)
+    db, mb = data.blockify()
+    loss = jabble.loss.ChiSquare() + jabble.loss.L2Reg([0, 1], coefficient=3.5, constant=0.01) \
+        + jabble.loss.L2Reg([1, 1], coefficient=0.7) + jabble.loss.L1Reg([0, 0], coefficient=11.0, constant=1e-5)
+    for ci, fits in enumerate(json.loads(str(g["cases"]))):
+        set_fit(model, fits)
+        model.get_parameters()
+        loss.ready_indices(model)
+        p = g[f"rg_case{ci}_p"]
+        assert abs(loss.loss_all(p, db, mb, model, None, 3) - float(g[f"rg_case{ci}_loss"])) <= TOL * abs(float(g[f"rg_case{ci}_loss"]))
+        _check_grad(model, loss.grad_all(p, db, mb, model, None, 3), g[f"rg_case{ci}_grad"])
+    set_fit(model, [(0, 1), (1, 2)])
+    l2 = jabble.loss.L2Loss() * 2.5
+    assert abs(l2.loss_all(g["l2_p"], db, mb, model) - float(g["l2_loss"])) <= TOL * abs(float(g["l2_loss"]))
+    _check_grad(model, l2.grad_all(g["l2_p"], db, mb, model), g["l2_grad"])

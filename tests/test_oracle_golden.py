@@ -147,3 +147,37 @@ def test_golden_pseudonormal():
     dbd, mbd = _check_cases(model, data, g, "pn", json.loads(str(g["cases"])))
     model.fix(); model[0][0].fit()
     assert rel_err(O.f_info(model[0][0].p, dbd, mbd, model), g["f_info"]) < 1e-11
+
+
+def test_golden_regularisers_host_algebra():
+    """ChiSquare + L2Reg + L2Reg + L1Reg from the reference's own code: the data term from the oracle
+    plus the shim's host-side regulariser algebra (counted once per row, loss.py:61-74) must give the
+    golden loss and gradient."""
+    import wobble_jax_b200 as jabble
+    g = load_golden("regularised.npz")
+    data = dataset_from_golden(g)
+    model, meta = wobble_from_golden(g)
+    db, mb = data.blockify()
+    dbd = {k: db[k] for k in ("xs", "ys", "yivar", "mask")}
+    mbd = {k: mb[k] for k in mb.keys()}
+    loss = jabble.loss.ChiSquare() + jabble.loss.L2Reg([0, 1], coefficient=3.5, constant=0.01) \
+        + jabble.loss.L2Reg([1, 1], coefficient=0.7) + jabble.loss.L1Reg([0, 0], coefficient=11.0, constant=1e-5)
+    assert repr(loss) == str(g["repr"])
+    for ci, fits in enumerate(json.loads(str(g["cases"]))):
+        set_fit(model, fits)
+        model.get_parameters()
+        loss.ready_indices(model)
+        p = g[f"rg_case{ci}_p"]
+        val, grad = O.loss_and_grad(p, dbd, mbd, model)
+        for r in loss.loss_funcs[1:]:
+            rv, rgrad = r.value_and_grad(p)
+            val += len(db) * rv
+            grad = grad + len(db) * rgrad
+        assert abs(val - float(g[f"rg_case{ci}_loss"])) <= 1e-12 * abs(val)
+        assert rel_err(grad, g[f"rg_case{ci}_grad"]) < 1e-11
+    # L2Loss == ChiSquare with weights 2 (loss.py:175-184)
+    set_fit(model, [(0, 1), (1, 2)])
+    dbd2 = dict(dbd, yivar=np.full_like(dbd["ys"], 2.0))
+    val, grad = O.loss_and_grad(g["l2_p"], dbd2, mbd, model, coefficient=2.5)
+    assert abs(val - float(g["l2_loss"])) <= 1e-12 * abs(val)
+    assert rel_err(grad, g["l2_grad"]) < 1e-11

@@ -339,10 +339,26 @@ class Objective:
 
     def __init__(self, loss, model, datablock, metablock, device=0):
         from . import loss as L
-        if not isinstance(loss, L.ChiSquare):
-            raise NotImplementedError(
-                f"{type(loss).__name__}: only ChiSquare runs on the CUDA path so far (SURVEY.md section 8f-1)")
-        self.plan = build_plan(model, datablock, metablock, coefficient=loss.coefficient, device=device)
+        terms = loss.loss_funcs if isinstance(loss, L.LossSequential) else [loss]
+        data_terms = [t for t in terms if isinstance(t, (L.ChiSquare, L.L2Loss))]
+        self.regs = [t for t in terms if isinstance(t, L.L2Reg)]          # L1Reg is an L2Reg subclass
+        other = [t for t in terms if t not in data_terms and t not in self.regs]
+        if other:
+            raise NotImplementedError(f"{type(other[0]).__name__} is not a loss this package evaluates")
+        if len(data_terms) != 1:
+            raise NotImplementedError("exactly one data term (ChiSquare or L2Loss) per objective is supported")
+        term = data_terms[0]
+        yivar = datablock["yivar"]
+        if isinstance(term, L.L2Loss):      # (ys - m)**2 == 0.5 * 2 * (ys - m)**2 : ChiSquare with unit weights x 2
+            yivar = np.full_like(np.asarray(datablock["ys"], dtype=np.float64), 2.0)
+        spec = TreeSpec(model)
+        self.plan = Plan(spec, datablock["xs"], datablock["ys"], yivar, datablock["mask"], metablock,
+                         coefficient=term.coefficient, device=device)
+        self.plan.sync_from_model()
+        self.n_rows = len(datablock)
+        for r in self.regs:
+            if r.indices is None:
+                r.ready_indices(model)
         self.n_evals = 0
         self._p = None
         self._f = None
@@ -352,7 +368,7 @@ class Objective:
     def cached(cls, loss, model, datablock, metablock):
         """Reuse the resident data block between loss_all / grad_all calls on the same objects;
         parameters and fit flags are re-read from the model tree every time."""
-        key = (id(datablock), id(metablock), id(model), type(loss).__name__, float(loss.coefficient))
+        key = (id(datablock), id(metablock), id(model), repr(loss))
         obj = cls._cache.get(key)
         sig = TreeSpec(model).signature()
         if obj is None or obj._sig != sig or obj._db is not datablock:
@@ -370,6 +386,12 @@ class Objective:
         p = np.asarray(p, dtype=np.float64).reshape(-1)
         if self._p is None or p.shape != self._p.shape or not np.array_equal(p, self._p):
             self._f, self._g = self.plan.eval(p)
+            for r in self.regs:
+                # the reference's loss_all evaluates a regulariser inside the vmap over rows
+                # (loss.py:61-74): its value and gradient are counted once per row of the block
+                rv, rg = r.value_and_grad(p)
+                self._f += self.n_rows * rv
+                self._g = self._g + self.n_rows * rg
             self._p = p.copy()
             self.n_evals += 1
         return self._f, self._g

@@ -6,8 +6,11 @@
 (``jb_plan_eval``); ``batch_size``/``device_op`` are accepted and ignored because the data stay
 resident in HBM inside the plan.
 
-``L2Loss``/``L2Reg``/``L1Reg``/``LossSequential`` (loss.py:95-161, 175-222) are SURVEY.md
-section 8f-1 ("next").
+``L2Loss`` (loss.py:175-184) is the same kernel with unit weights.  ``L2Reg``/``L1Reg``
+(loss.py:187-222) depend on the parameters only; they are O(n_fit) host arithmetic added to the
+device result, including the reference's quirk that ``loss_all`` evaluates them once per row of the
+block (loss.py:61-74), i.e. scaled by the number of rows.  ``LossSequential`` (loss.py:95-161) is
+the sum.
 """
 
 import numpy as np
@@ -18,6 +21,9 @@ class LossFunc:
 
     def __init__(self, coefficient=1.0):
         self.coefficient = coefficient
+
+    def __add__(self, x):
+        return LossSequential(loss_funcs=[self, x])
 
     def __mul__(self, x):
         self.coefficient *= x
@@ -54,3 +60,75 @@ class ChiSquare(LossFunc):
         ys = datarow["ys"]
         return self.coefficient * np.where(~np.asarray(datarow["mask"]).astype(bool),
                                            0.5 * datarow["yivar"] * (ys - m) ** 2, 0.0)
+
+
+class L2Loss(LossFunc):
+    """loss.py:175-184 -- unweighted squared residuals: coef * where(~mask, (ys - model)**2, 0)."""
+
+
+class L2Reg(LossFunc):
+    """loss.py:187-215 -- coef * 0.5 * (p[indices] - constant)**2 on the fit-vector entries of the
+    sub-model reached by ``submodel_inds`` (an index path, e.g. [0, 1])."""
+
+    def __init__(self, submodel_inds=True, coefficient=1.0, constant=0.0):
+        super(L2Reg, self).__init__(coefficient)
+        self.constant = constant
+        self.submodel_inds = submodel_inds
+        self.indices = None
+
+    def ready_indices(self, model):
+        from . import model as M
+        self.indices = np.asarray(M.get_submodel_indices(model, *self.submodel_inds), dtype=np.int64)
+
+    def value_and_grad(self, p):
+        """(sum over the selected entries, gradient w.r.t. the whole fit vector) for ONE row."""
+        d = p[self.indices] - self.constant
+        g = np.zeros_like(p)
+        g[self.indices] = self.coefficient * d
+        return self.coefficient * 0.5 * float(np.sum(d * d)), g
+
+    def __repr__(self):
+        return str(self.coefficient) + " {obj.__class__.__name__}".format(obj=self) + "({obj.submodel_inds})".format(obj=self)
+
+
+class L1Reg(L2Reg):
+    """loss.py:217-222 -- coef * |p[indices] - constant|."""
+
+    def value_and_grad(self, p):
+        d = p[self.indices] - self.constant
+        g = np.zeros_like(p)
+        g[self.indices] = self.coefficient * np.sign(d)
+        return self.coefficient * float(np.sum(np.abs(d))), g
+
+
+class LossSequential(LossFunc):
+    """loss.py:95-161 -- sum of losses; ``*`` scales every term."""
+
+    def __init__(self, loss_funcs):
+        self.loss_funcs = list(loss_funcs)
+
+    @property
+    def coefficient(self):
+        raise AttributeError("a LossSequential has no single coefficient")
+
+    def __add__(self, x):
+        if isinstance(x, LossSequential):
+            return LossSequential(loss_funcs=[*self.loss_funcs, *x.loss_funcs])
+        return LossSequential(loss_funcs=[*self.loss_funcs, x])
+
+    def __radd__(self, x):
+        return self.__add__(x)
+
+    def __mul__(self, x):
+        for loss in self.loss_funcs:
+            loss.coefficient *= x
+        return self
+
+    __rmul__ = __mul__
+
+    def ready_indices(self, model):
+        for loss in self.loss_funcs:
+            loss.ready_indices(model)
+
+    def __repr__(self):
+        return " + ".join(repr(loss) for loss in self.loss_funcs)
