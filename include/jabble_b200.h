@@ -114,7 +114,7 @@ typedef struct {
     int64_t tiles_serial;         /* ... walked lane by lane (lanes of a class may share knots)      */
     int64_t tiles_empty;          /* ... without any weighted pixel                                  */
     int32_t window_knots;         /* on-chip gradient window per warp and component                  */
-    int32_t reserved;
+    int32_t fused_variant;        /* kernel of the last evaluation: -1 general k_fused, >= 0 flags of k_fused2 */
 } jb_plan_info_t;
 
 const char *jb_last_error(void);

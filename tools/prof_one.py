@@ -30,4 +30,4 @@ info = plan.info()
 print(f"loss {f:.6e} fused {ms / n * 1e3:.1f} us/launch  {info['algorithmic_bytes'] / (ms / n * 1e-3) / 1e9:.0f} GB/s  "
       f"tasks {info['n_tasks']} G {info['rows_per_group']} serial_rows {info['serial_rows']} "
       f"tiles smooth/general/serial/empty {info['tiles_smooth']}/{info['tiles_general']}/{info['tiles_serial']}/{info['tiles_empty']} "
-      f"window {info['window_knots']}")
+      f"window {info['window_knots']} variant {info['fused_variant']}")

@@ -736,7 +736,7 @@ struct ReduceParams {
     const int* stretch_rowptr[kMaxComp]; const int* stretch_rows[kMaxComp];
     int64_t n_rows, n_tasks;
     int n_tiles, n_groups, wincap;
-    int nb_knot, nb_ctrl;   // block layout of k_reduce_stage1
+    int nb_ctrl;            // blocks of k_reduce_stage1 that sum gradient windows (n_comp * n_groups)
     const double* part; const int* part_base; const double* rowpart; const double* losspart;
     // normalisation component (index n_comp, when has_norm): per-row gradients of its control points
     int has_norm, norm_stride, norm_knots, n_norm_keys;
@@ -744,6 +744,11 @@ struct ReduceParams {
     const double* normpart; double* normrow;           // [E][n_tiles][norm_stride] -> [E][norm_stride]
     const int* norm_rowptr; const int* norm_rows;      // key -> rows (CSR)
     int nb_stage1_rows;                                 // blocks of the per-row tile sums in stage 1
+    // layout of a row of rowpart / rowsum: nq values; rq[c][kind] = position of component c's
+    // shift-gradient (0), stretch-gradient (1), Fisher (2) sum, -1 when the fused kernel of this
+    // plan does not compute it
+    int nq;
+    int rq[kMaxComp][3];
     double* tmp;        // [n_comp][n_groups][max_knots]
     double* rowsum;     // [E][NQ]
     int64_t max_knots;
@@ -757,26 +762,33 @@ struct ReduceParams {
 // blocks [0, nb_ctrl): tmp[c][g][k] = sum over tiles of the group, in tile order, of the windows
 // covering knot k.  blocks [nb_ctrl, ...): rowsum[r][q] = sum over tiles of rowpart.
 __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
+    extern __shared__ double sacc[];     // [max_knots] of the launch
     const int pi = find_plan(off, n, blockIdx.x);
     const ReduceParams& a = arr[pi];
     const int blk = blockIdx.x - off[pi];
-    const int nb_knot = a.nb_knot, nb_ctrl = a.nb_ctrl;
-    const int NQ = row_sum_stride(a.n_comp, a.has_norm);
+    const int nb_ctrl = a.nb_ctrl;       // = n_comp * n_groups: one block per (component, row group)
+    const int NQ = a.nq;
     if (blk < nb_ctrl) {
-        const int kb = blk % nb_knot;
-        const int g = (blk / nb_knot) % a.n_groups;
-        const int c = blk / (nb_knot * a.n_groups);
-        const int k = kb * blockDim.x + threadIdx.x;
-        if (k >= a.comp[c].n_knots) return;
-        double s = 0.0;
+        // tmp[c][g][:] = sum over the group's tasks, in tile order, of their gradient windows: the
+        // windows of consecutive tiles overlap, so the block adds them one tile at a time into a
+        // shared-memory copy of the knot axis (distinct addresses within a tile, a barrier between
+        // tiles): coalesced reads of `part`, no scan, one fixed order.
+        const int g = blk % a.n_groups;
+        const int c = blk / a.n_groups;
+        const int M = a.comp[c].n_knots;
+        for (int k = threadIdx.x; k < M; k += blockDim.x) sacc[k] = 0.0;
+        __syncthreads();
         for (int t = 0; t < a.n_tiles; ++t) {
             const int64_t task = (int64_t)g * a.n_tiles + t;
             const int base = a.part_base[(int64_t)c * a.n_tasks + task];
-            const int w = k - base;
-            if (base != INT_MAX && w >= 0 && w < a.wincap)
-                s += a.part[((int64_t)c * a.n_tasks + task) * a.wincap + w];
+            if (base == INT_MAX) continue;          // uniform over the block
+            const double* src = a.part + ((int64_t)c * a.n_tasks + task) * a.wincap;
+            for (int w = threadIdx.x; w < a.wincap; w += blockDim.x)
+                if (base + w < M) sacc[base + w] += src[w];
+            __syncthreads();
         }
-        a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + k] = s;
+        double* dst = a.tmp + ((int64_t)c * a.n_groups + g) * a.max_knots;
+        for (int k = threadIdx.x; k < M; k += blockDim.x) dst[k] = sacc[k];
     } else if (blk < nb_ctrl + a.nb_stage1_rows) {
         const int64_t i = (int64_t)(blk - nb_ctrl) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * NQ) return;
@@ -804,7 +816,7 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
 __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
     const int pi = find_plan(off, n, blockIdx.x);
     const ReduceParams& a = arr[pi];
-    const int NQ = row_sum_stride(a.n_comp, a.has_norm);
+    const int NQ = a.nq;
     int64_t i = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
     for (int c = 0; c < a.n_comp + a.has_norm; ++c) {
         const bool is_norm = c == a.n_comp;
@@ -826,10 +838,11 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
         i -= M;
         if (i < a.n_shift[c]) {
             double gs = 0.0, fs = 0.0;
+            const int qg = a.rq[c][0], qf = a.rq[c][2];
             for (int e = a.shift_rowptr[c][i]; e < a.shift_rowptr[c][i + 1]; ++e) {
                 const int64_t r = a.shift_rows[c][e];
-                gs += a.rowsum[r * NQ + c * kRowQ + 0];
-                if (!is_norm) fs += a.rowsum[r * NQ + c * kRowQ + 2];
+                if (qg >= 0) gs += a.rowsum[r * NQ + qg];
+                if (qf >= 0) fs += a.rowsum[r * NQ + qf];
             }
             const double sc = a.comp[c].p_val * a.comp[c].inv_dx;
             a.grad_all[a.shift_off[c] + i] = a.coef * sc * gs;
@@ -839,8 +852,9 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
         i -= a.n_shift[c];
         if (i < a.n_stretch[c]) {
             double gs = 0.0;
+            const int qs = a.rq[c][1];
             for (int e = a.stretch_rowptr[c][i]; e < a.stretch_rowptr[c][i + 1]; ++e)
-                gs += a.rowsum[(int64_t)a.stretch_rows[c][e] * NQ + c * kRowQ + 1];
+                if (qs >= 0) gs += a.rowsum[(int64_t)a.stretch_rows[c][e] * NQ + qs];
             a.grad_all[a.stretch_off[c] + i] = -a.coef * gs;
             return;
         }

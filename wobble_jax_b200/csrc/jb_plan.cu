@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -16,6 +17,7 @@
 
 #include "../../include/jabble_b200.h"
 #include "jb_kernels.cuh"
+#include "jb_fused2.cuh"
 
 namespace {
 
@@ -79,6 +81,10 @@ struct jb_plan {
     double *d_params = nullptr, *d_grad_all = nullptr, *d_fisher_all = nullptr;
     std::vector<double> h_params;
     bool params_set = false, sort_dirty = true;
+    bool fit_shift[jb::kMaxComp] = {false, false, false};   // some shift of the component is in fit mode
+    bool force_der = false;    // jb_plan_fisher: derivative sums whatever the fit flags say
+    bool force_v1 = false;     // a batch whose plans disagree on the kernel variant falls back to k_fused
+    int variant = -1;          // fused kernel of this plan: -1 k_fused (general), else the FL flags of k_fused2
     int64_t* d_fit_map = nullptr;
     double *d_pfit = nullptr, *d_out = nullptr;
     double *h_pfit = nullptr, *h_out = nullptr;   // pinned
@@ -228,9 +234,24 @@ int check_supported_for_eval(const jb_plan* pl) {
     return JB_OK;
 }
 
+// Which fused kernel serves the plan.  k_fused2 (jb_fused2.cuh) takes plans without a per-key
+// component whose every tile is smooth; its flags say what the fit state asks for.  JB_FUSED_V1 in
+// the environment keeps the general kernel (A/B measurements).
+int plan_variant(const jb_plan* pl) {
+    static const bool env_v1 = getenv("JB_FUSED_V1") != nullptr;
+    if (env_v1 || pl->force_v1 || pl->has_norm || pl->n_glob > 2 || pl->tiles_kind[1] || pl->tiles_kind[2]) return -1;
+    int fl = 0;
+    for (int c = 0; c < pl->n_glob; ++c) {
+        if (pl->desc[c].shift_offset >= 0 && (pl->fit_shift[c] || pl->force_der)) fl |= 1 << c;
+        if (pl->desc[c].stretch_offset >= 0) fl |= 4 << c;
+    }
+    return fl;
+}
+
 // (Re)build the plan's parameter blocks and block counts; uploaded on the plan's stream.
 int refresh_pack(jb_plan* pl) {
     if (!pl->pack_dirty) return JB_OK;
+    pl->variant = plan_variant(pl);
     JB_CUDA(cudaStreamSynchronize(pl->stream));   // the pinned copy may still be in flight
     jb_plan::Pack& k = *pl->h_pack;
     memset(&k, 0, sizeof k);
@@ -271,17 +292,28 @@ int refresh_pack(jb_plan* pl) {
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
     rp.fit_map = pl->d_fit_map; rp.n_fit = pl->n_fit;
     rp.out = pl->d_out; rp.status = pl->d_status;
-    const int NQ = jb::row_sum_stride(pl->n_glob, pl->has_norm);
-    rp.nb_knot = (int)((pl->max_knots + 127) / 128);
-    rp.nb_ctrl = rp.nb_knot * pl->n_groups * pl->n_glob;
-    rp.nb_stage1_rows = (int)((pl->E * NQ + 127) / 128);
+    int NQ = jb::row_sum_stride(pl->n_glob, pl->has_norm);
+    for (int c = 0; c < jb::kMaxComp; ++c)
+        for (int q = 0; q < 3; ++q) rp.rq[c][q] = -1;
+    if (pl->variant < 0) {
+        for (int c = 0; c < pl->n_glob; ++c)
+            for (int q = 0; q < 3; ++q) rp.rq[c][q] = c * jb::kRowQ + q;
+        if (pl->has_norm) { rp.rq[pl->n_glob][0] = pl->n_glob * jb::kRowQ; rp.rq[pl->n_glob][1] = pl->n_glob * jb::kRowQ + 1; }
+    } else {
+        NQ = jb::f2_pad(jb::f2_nsums(pl->n_glob, pl->variant));
+        for (int c = 0; c < pl->n_glob; ++c)
+            for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, pl->variant, c, q);
+    }
+    rp.nq = NQ;
+    rp.nb_ctrl = pl->n_groups * pl->n_glob;
+    rp.nb_stage1_rows = (int)((pl->E * NQ + 255) / 256);
     int64_t n2 = 0;
     for (int c = 0; c < pl->n_comp; ++c)
         n2 += (c < pl->n_glob ? pl->comp[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys) + rp.n_shift[c] + rp.n_stretch[c];
     pl->nb[K_SCATTER] = (int)std::max<int64_t>(1, (pl->n_fit + 255) / 256);
     pl->nb[K_PREPARE] = (int)((pl->E + 127) / 128);
     pl->nb[K_FUSED] = (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
-    pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + 127) / 128) : 0);
+    pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + 255) / 256) : 0);
     pl->nb[K_STAGE2] = (int)((n2 + 255) / 256);
     pl->nb[K_FINISH] = (int)(1 + (pl->n_fit + 1023) / 1024);
     int off[K_COUNT][2];
@@ -300,6 +332,8 @@ struct LaunchSet {
     int total[K_COUNT];
     int n;
     int n_comp, p_val, pvn, wincap;   // global components, their degree, degree of the normalisation spline (0: none)
+    int variant;                      // -1: k_fused, else the FL flags of k_fused2 (same for every plan of the launch)
+    int64_t max_knots;                // longest knot axis among the plans of the launch
     bool scatter;
 };
 
@@ -321,6 +355,34 @@ int launch_fused_n(const LaunchSet& L, cudaStream_t st) {
         case 3: return launch_fused_t<NC, PV, 3>(L, st);
     }
     return fail(JB_ERR_UNSUPPORTED, "normalisation spline of degree %d", L.pvn);
+}
+
+template <int NC, int PV, int FL>
+int launch_fused2_t(const LaunchSet& L, cudaStream_t st) {
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused2_warp_smem<NC>(L.wincap);
+    JB_CUDA(cudaFuncSetAttribute(jb::k_fused2<NC, PV, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jb::k_fused2<NC, PV, FL><<<(unsigned)L.total[K_FUSED], jb::kWarpsPerBlock * 32, smem, st>>>(L.fu, L.off[K_FUSED], L.n);
+    JB_CUDA(cudaGetLastError());
+    return JB_OK;
+}
+
+template <int NC, int PV>
+int launch_fused2_f(const LaunchSet& L, cudaStream_t st) {
+#define JB_F2(f) case f: return launch_fused2_t<NC, PV, f>(L, st);
+#ifdef JB_F2_FAST_BUILD   // kernel-tuning builds: only the benchmark's variant
+    if constexpr (NC == 2 && PV == 3) { switch (L.variant) { JB_F2(9) } }
+    else
+#endif
+    if constexpr (NC == 1) {
+        switch (L.variant) { JB_F2(0) JB_F2(1) JB_F2(4) JB_F2(5) }
+    } else {
+        switch (L.variant) {
+            JB_F2(0) JB_F2(1) JB_F2(2) JB_F2(3) JB_F2(4) JB_F2(5) JB_F2(6) JB_F2(7)
+            JB_F2(8) JB_F2(9) JB_F2(10) JB_F2(11) JB_F2(12) JB_F2(13) JB_F2(14) JB_F2(15)
+        }
+    }
+#undef JB_F2
+    return fail(JB_ERR_UNSUPPORTED, "no k_fused2 for flags %d", L.variant);
 }
 
 // Six launches for the n plans of L (n = 1: the plan's own blocks; n > 1: the dense arrays of a jb_batch).
@@ -345,6 +407,17 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
         JB_CUDA(cudaEventRecord(prof->prof_events[prof->prof_used].first, st));
     }
     int rc;
+    if (L.variant >= 0) {
+        switch (L.n_comp * 10 + L.p_val) {
+            case 11: rc = launch_fused2_f<1, 1>(L, st); break;
+            case 12: rc = launch_fused2_f<1, 2>(L, st); break;
+            case 13: rc = launch_fused2_f<1, 3>(L, st); break;
+            case 21: rc = launch_fused2_f<2, 1>(L, st); break;
+            case 22: rc = launch_fused2_f<2, 2>(L, st); break;
+            case 23: rc = launch_fused2_f<2, 3>(L, st); break;
+            default: rc = fail(JB_ERR_UNSUPPORTED, "no fused kernel for %d components of degree %d", L.n_comp, L.p_val);
+        }
+    } else
     switch (L.n_comp * 10 + L.p_val) {
         case 11: rc = launch_fused_n<1, 1>(L, st); break;
         case 12: rc = launch_fused_n<1, 2>(L, st); break;
@@ -360,7 +433,12 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
         prof->prof_used++;
         prof->prof_stream = st;
     }
-    jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], 128, 0, st>>>(L.re, L.off[K_STAGE1], L.n);
+    {
+        const size_t smem1 = (size_t)L.max_knots * sizeof(double);
+        if (smem1 > 200 * 1024) return fail(JB_ERR_UNSUPPORTED, "%lld knots per template (the reducer holds one knot axis in shared memory)", (long long)L.max_knots);
+        JB_CUDA(cudaFuncSetAttribute(jb::k_reduce_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
+        jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], 256, smem1, st>>>(L.re, L.off[K_STAGE1], L.n);
+    }
     jb::k_reduce_stage2<<<(unsigned)L.total[K_STAGE2], 256, 0, st>>>(L.re, L.off[K_STAGE2], L.n);
     jb::k_finish<<<(unsigned)L.total[K_FINISH], 1024, 0, st>>>(L.re, L.off[K_FINISH], L.n, out_override);
     JB_CUDA(cudaGetLastError());
@@ -379,6 +457,8 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     for (int i = 0; i < K_COUNT; ++i) { L.off[i] = pl->d_off + 2 * i; L.total[i] = pl->nb[i]; }
     L.n = 1; L.n_comp = pl->n_glob; L.p_val = pl->desc[0].p_val; L.wincap = pl->wincap;
     L.pvn = pl->has_norm ? pl->desc[pl->n_glob].p_val : 0;
+    L.max_knots = pl->max_knots;
+    L.variant = pl->variant;
     L.scatter = d_p_fit != nullptr && pl->n_fit > 0;
     if ((rc = launch_all(L, st, d_p_fit, d_out, pl))) return rc;
     pl->launches += L.scatter ? 6 : 5;
@@ -719,6 +799,7 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     info->tiles_smooth = pl->tiles_kind[0]; info->tiles_general = pl->tiles_kind[1];
     info->tiles_serial = pl->tiles_kind[2]; info->tiles_empty = pl->tiles_kind[3];
     info->window_knots = pl->wincap;
+    info->fused_variant = pl->variant;
     return JB_OK;
 }
 
@@ -750,6 +831,13 @@ int jb_plan_set_fit(jb_plan* pl, const int64_t* fit_index, int64_t n_fit) {
     JB_CUDA(cudaMallocHost(&pl->h_pfit, std::max<int64_t>(n_fit, 1) * sizeof(double)));
     JB_CUDA(cudaMallocHost(&pl->h_out, (n_fit + 1) * sizeof(double)));
     pl->n_fit = n_fit;
+    for (int c = 0; c < pl->n_comp; ++c) {
+        pl->fit_shift[c] = false;
+        const jb_component_desc& cd = pl->desc[c];
+        if (cd.shift_offset < 0) continue;
+        for (int64_t i = 0; i < n_fit; ++i)
+            if (fit_index[i] >= cd.shift_offset && fit_index[i] < cd.shift_offset + cd.n_shift) { pl->fit_shift[c] = true; break; }
+    }
     pl->pack_dirty = true;
     return JB_OK;
 }
@@ -828,7 +916,9 @@ int jb_plan_fisher(jb_plan* pl, int32_t component, double* f_out, int64_t n_shif
     if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
     if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
     JB_CUDA(cudaSetDevice(pl->device));
+    pl->force_der = true; pl->pack_dirty = true;     // the Fisher sums of every shift, whatever is in fit mode
     int rc = eval_sync(pl, nullptr);
+    pl->force_der = false; pl->pack_dirty = true;
     if (rc) return rc;
     JB_CUDA(cudaMemcpy(f_out, pl->d_fisher_all + cd.shift_offset, n_shift * sizeof(double), cudaMemcpyDeviceToHost));
     return JB_OK;
@@ -913,6 +1003,12 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     const int n = (int)b->plans.size();
     int rc;
     bool regroup = b->dirty;
+    {   // one launch -> one kernel: plans that disagree on the variant all take the general kernel
+        bool same = true;
+        for (jb_plan* pl : b->plans) same = same && plan_variant(pl) == plan_variant(b->plans[0]);
+        for (jb_plan* pl : b->plans)
+            if (pl->force_v1 != !same) { pl->force_v1 = !same; pl->pack_dirty = true; }
+    }
     for (jb_plan* pl : b->plans) {
         if (pl->sort_dirty) { if ((rc = resort_rows(pl))) return rc; }
         if (pl->pack_dirty) regroup = true;
@@ -959,6 +1055,9 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     for (int q = 0; q < K_COUNT; ++q) { L.off[q] = b->d_off + (size_t)q * (n + 1); L.total[q] = b->total[q]; }
     L.n = n; L.n_comp = b->plans[0]->n_glob; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
     L.pvn = b->plans[0]->has_norm ? b->plans[0]->desc[b->plans[0]->n_glob].p_val : 0;
+    L.max_knots = 0;
+    for (jb_plan* q : b->plans) L.max_knots = std::max(L.max_knots, q->max_knots);
+    L.variant = b->plans[0]->variant;
     L.scatter = !b->p_fit.empty();
     if ((rc = launch_all(L, st, nullptr, nullptr, b->plans[0]))) return rc;
     b->launches += L.scatter ? 6 : 5;
