@@ -63,6 +63,13 @@ __device__ __forceinline__ double warp_sum_n(double (&v)[NV], int lane) {
     return v[0];
 }
 
+// lane l accumulates into copy l % kClasses2 of the gradient window: lanes l and l + kClasses2 are
+// 4 * kClasses2 pixels apart, which the plan checks is more than a spline support (jb_plan.cu)
+#ifndef JB_F2_CLASSES
+#define JB_F2_CLASSES 3
+#endif
+constexpr int kClasses2 = JB_F2_CLASSES;
+
 template <int PV>
 struct Win2 {
     double c[PV + 1];   // control points of knots klo .. klo+PV, klo = I + KOFF
@@ -241,13 +248,13 @@ __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc,
 
 __shared__ FusedParams g_f2_plan;     // the block's plan
 
-// Per-warp shared memory: [ring kStages x kTileBytes][recs kMaxGroup][mbarriers kStages][pad to 128]
-// at fixed offsets, then the control-point windows [NC][W] and the class copies [kClasses][NC][W].
+// Per-warp shared memory: [ring kStages x kTileBytes][recs kMaxGroup][mbarriers kStages][pad to 16]
+// at fixed offsets, then the control-point windows [NC][W] and the class copies [kClasses2][NC][W].
 template <int NC> struct F2Lay {
     static constexpr uint32_t ring = 0;
     static constexpr uint32_t recs = kStages * kTileBytes;
     static constexpr uint32_t bars = recs + kMaxGroup * sizeof(RowRec<NC, 0>);
-    static constexpr uint32_t ctrl = (bars + kStages * 8 + 127) / 128 * 128;
+    static constexpr uint32_t ctrl = (bars + kStages * 8 + 15) / 16 * 16;
 };
 // what a row needs besides the windows
 template <int NC> struct F2Ctx {
@@ -295,7 +302,7 @@ __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<N
 
 template <int NC>
 __host__ __device__ constexpr size_t fused2_warp_smem(int wincap) {
-    return (F2Lay<NC>::ctrl + (size_t)NC * wincap * 8 + (size_t)NC * kClasses * wincap * 8 + 127) / 128 * 128;
+    return (F2Lay<NC>::ctrl + (size_t)NC * wincap * 8 + (size_t)NC * kClasses2 * wincap * 8 + 15) / 16 * 16;   // 16 B: bulk-copy destination, double2 stores
 }
 
 template <int NC, int PV, int FL>
@@ -326,7 +333,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
     Rec* recs = reinterpret_cast<Rec*>(wbase + L::recs);
     const uint32_t bar0 = smem_u32(wbase + L::bars);                         // [kStages] mbarriers
     double* ctrl_warp = reinterpret_cast<double*>(wbase + L::ctrl);          // [NC][W]
-    double* acc_warp = ctrl_warp + NC * W;                                   // [kClasses][NC][W]
+    double* acc_warp = ctrl_warp + NC * W;                                   // [kClasses2][NC][W]
 
     // ---- 0. lane i fetches the record of row i of the group ------------------------------------
     int lo[NC], hi[NC];
@@ -403,7 +410,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
     // ---- 3. accumulators and control-point window ------------------------------------------------
     {
         double2* z = reinterpret_cast<double2*>(acc_warp);
-        for (int i = lane; i < NC * kClasses * W / 2; i += 32) z[i] = make_double2(0.0, 0.0);
+        for (int i = lane; i < NC * kClasses2 * W / 2; i += 32) z[i] = make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -413,7 +420,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
     __syncwarp();
 
     constexpr int KOFF = (PV + 1) / 2 - PV;          // klo = I + KOFF (knot_lo)
-    const int cls = lane & (kClasses - 1);
+    const int cls = lane % kClasses2;
     // address of the class copy's entry for knot klo of interval I: abase[c] + 8 * I
     uint32_t abase[NC];
     Win2<PV> win[NC];
@@ -457,7 +464,7 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
         for (int k = lane; k < W; k += 32) {
             double sacc = acc_warp[(size_t)c * W + k];
 #pragma unroll
-            for (int q = 1; q < kClasses; ++q) sacc += acc_warp[(size_t)(q * NC + c) * W + k];
+            for (int q = 1; q < kClasses2; ++q) sacc += acc_warp[(size_t)(q * NC + c) * W + k];
             dst[k] = sacc;
         }
     }

@@ -83,6 +83,7 @@ struct jb_plan {
     bool params_set = false, sort_dirty = true;
     bool fit_shift[jb::kMaxComp] = {false, false, false};   // some shift of the component is in fit mode
     bool force_der = false;    // jb_plan_fisher: derivative sums whatever the fit flags say
+    bool f2_classes_ok = true; // lanes sharing a gradient-window copy of k_fused2 never meet on a knot
     bool force_v1 = false;     // a batch whose plans disagree on the kernel variant falls back to k_fused
     int variant = -1;          // fused kernel of this plan: -1 k_fused (general), else the FL flags of k_fused2
     int64_t* d_fit_map = nullptr;
@@ -157,12 +158,14 @@ int dev_upload(jb_plan* pl, T** out, const std::vector<T>& h) {
 
 int choose_rows_per_group(int64_t E, int n_tiles, int requested) {
     if (requested > 0) return (int)std::min<int64_t>(std::min(requested, jb::kMaxGroup), std::max<int64_t>(E, 1));
-    // as many rows per group as still leave every resident warp a task: a task pays its set-up
-    // (row records, control-point window, final window write) once however many rows it streams,
-    // and several plans usually run side by side on their own streams
-    const int64_t want_tasks = 148LL * 8 * 3 / 2;   // 1.5 x the warps resident on 148 SMs
-    int64_t g = (E * n_tiles) / want_tasks;
-    g = std::max<int64_t>(1, std::min<int64_t>(g, jb::kMaxGroup));
+    // A task pays its set-up (row records, control-point window, final window write) once however
+    // many rows it streams, so groups are as long as possible (kMaxGroup) -- unless the whole plan
+    // then leaves warp slots empty: a lone plan is one wave of equal tasks, and its time is the time
+    // of one task.  16 warps are resident per SM (128 registers, < 14 KB of shared memory each).
+    const int64_t slots = 148LL * 16;
+    const int64_t groups_that_fit = std::max<int64_t>(1, slots / std::max(n_tiles, 1));
+    int64_t g = (E + groups_that_fit - 1) / groups_that_fit;
+    g = std::max<int64_t>(std::min<int64_t>(g, jb::kMaxGroup), std::min<int64_t>(8, jb::kMaxGroup));
     return (int)std::min<int64_t>(g, std::max<int64_t>(E, 1));
 }
 
@@ -239,7 +242,7 @@ int check_supported_for_eval(const jb_plan* pl) {
 // the environment keeps the general kernel (A/B measurements).
 int plan_variant(const jb_plan* pl) {
     static const bool env_v1 = getenv("JB_FUSED_V1") != nullptr;
-    if (env_v1 || pl->force_v1 || pl->has_norm || pl->n_glob > 2 || pl->tiles_kind[1] || pl->tiles_kind[2]) return -1;
+    if (env_v1 || pl->force_v1 || !pl->f2_classes_ok || pl->has_norm || pl->n_glob > 2 || pl->tiles_kind[1] || pl->tiles_kind[2]) return -1;
     int fl = 0;
     for (int c = 0; c < pl->n_glob; ++c) {
         if (pl->desc[c].shift_offset >= 0 && (pl->fit_shift[c] || pl->force_der)) fl |= 1 << c;
@@ -657,8 +660,10 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
         for (int t = 0; t < NT; ++t) {
             const size_t ti = (size_t)r * NT + t;
             bool any_w = false;
-            double cmax[jb::kClasses];
+            double cmax[jb::kClasses], cmax2[jb::kClasses2];
             for (int q = 0; q < jb::kClasses; ++q) cmax[q] = -INFINITY;
+            for (int q = 0; q < jb::kClasses2; ++q) cmax2[q] = -INFINITY;
+            bool bad2 = false;   // the same test for the class layout of k_fused2
             bool bad = false, jumpy = false;
             for (int l = 0; l < 32; ++l) {
                 double lmin = INFINITY, lmax = -INFINITY;
@@ -673,6 +678,9 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                 double& cm = cmax[l % jb::kClasses];
                 if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
                 cm = std::max(cm, lmax);
+                double& cm2 = cmax2[l % jb::kClasses2];
+                if (!(lmin - cm2 >= need)) bad2 = true;
+                cm2 = std::max(cm2, lmax);
                 txmin[ti] = std::min(txmin[ti], lmin);
                 txmax[ti] = std::max(txmax[ti], lmax);
             }
@@ -681,6 +689,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             dense[ti] = !any_w ? 2 : ((bad ? 1 : 0) | (jumpy ? 4 : 0));
             if (!any_w) { txmin[ti] = INFINITY; txmax[ti] = -INFINITY; }
             pl->tiles_kind[!any_w ? 3 : bad ? 2 : jumpy ? 1 : 0]++;
+            if (any_w && bad2) pl->f2_classes_ok = false;
         }
     }
     int rc;
