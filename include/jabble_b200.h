@@ -91,8 +91,12 @@ typedef struct {
     int64_t n_params;           /* length of params_all                                          */
     double coefficient;         /* LossFunc.coefficient (loss.py:31)                             */
     int32_t rows_per_group;     /* 0 = choose; rows accumulated on chip before a partial is written */
-    int32_t reserved;
+    int32_t flags;              /* JB_PLAN_* bits; 0 = defaults                                      */
 } jb_plan_desc;
+
+/* jb_plan_desc.flags */
+#define JB_PLAN_GENERAL_KERNEL 1   /* always evaluate with the general fused kernel (k_fused), never the
+                                      specialised one (k_fused2): cross-checks and A/B measurements   */
 
 typedef struct jb_plan jb_plan;
 

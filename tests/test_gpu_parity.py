@@ -277,3 +277,58 @@ def test_golden_regularised_objective():
     l2 = jabble.loss.L2Loss() * 2.5
     assert abs(l2.loss_all(g["l2_p"], db, mb, model) - float(g["l2_loss"])) <= TOL * abs(float(g["l2_loss"]))
     _check_grad(model, l2.grad_all(g["l2_p"], db, mb, model), g["l2_grad"])
+
+
+@pytest.mark.parametrize("p_val", [1, 2, 3])
+def test_specialised_kernel_agrees_with_general_kernel_for_every_fit_state(p_val):
+    """k_fused2 (smooth plans; what the fit flags do not ask for is not computed) against the general
+    k_fused on the same plan data, for every combination of leaves in fit mode, and against the oracle."""
+    import itertools
+    ch = synth.make_chunk(chunk=5, n_epochs=45, n_pix=1100, p_val=p_val, n_lines=15)
+    model = ch.model
+    db, mb, dbd, mbd = _blocks(ch.data)
+    leaves = [(0, 0), (0, 1), (1, 0), (1, 1), (1, 2)]   # stellar shift, S, telluric shift, T, airmass
+    seen = set()
+    for r in range(1, len(leaves) + 1):
+        for fits in itertools.combinations(leaves, r):
+            set_fit(model, fits)
+            p = np.asarray(model.get_parameters())
+            fast = engine.build_plan(model, db, mb)
+            slow = engine.build_plan(model, db, mb, general_kernel=True)
+            vf, gf = fast.eval(p)
+            vs, gs = slow.eval(p)
+            assert fast.info()["fused_variant"] >= 0 and slow.info()["fused_variant"] == -1
+            seen.add(fast.info()["fused_variant"])
+            assert abs(vf - vs) <= 1e-12 * abs(vs), fits
+            _check_grad(model, gf, gs, tol=1e-11)
+            if r in (1, len(leaves)):
+                oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+                assert abs(vf - oval) <= TOL * abs(oval)
+                _check_grad(model, gf, ograd)
+            fast.close(); slow.close()
+    assert len(seen) == 4          # the telluric stretch is always there; shifts in or out of fit mode
+    # Fisher information does not depend on what is in fit mode
+    model.fix(); model.fit(0, 1)
+    plan = engine.build_plan(model, db, mb)
+    ref = engine.build_plan(model, db, mb, general_kernel=True)
+    for comp in (0, 1):
+        assert rel_err(plan.fisher(comp), ref.fisher(comp)) < 1e-12
+    plan.close(); ref.close()
+
+
+def test_stellar_only_specialised_kernel():
+    g = load_golden("stellar.npz")
+    data = dataset_from_golden(g)
+    model, meta = stellar_from_golden(g)
+    db, mb, dbd, mbd = _blocks(data)
+    for fits in ([(0,)], [(1,)], [(0,), (1,)]):
+        set_fit(model, fits)
+        p = np.asarray(model.get_parameters())
+        fast = engine.build_plan(model, db, mb)
+        slow = engine.build_plan(model, db, mb, general_kernel=True)
+        vf, gf = fast.eval(p)
+        vs, gs = slow.eval(p)
+        assert slow.info()["fused_variant"] == -1
+        assert abs(vf - vs) <= 1e-12 * abs(vs)
+        _check_grad(model, gf, gs, tol=1e-11)
+        fast.close(); slow.close()

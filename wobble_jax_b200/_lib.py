@@ -15,6 +15,7 @@ JB_OK = 0
 JB_ERR_BAD_ARG, JB_ERR_UNSUPPORTED, JB_ERR_CUDA = -1, -2, -3
 JB_ERR_OUT_OF_RANGE, JB_ERR_WINDOW, JB_ERR_NONFINITE = -4, -5, -6
 JB_COMP_SPLINE, JB_COMP_NORM_SPLINE = 0, 1
+JB_PLAN_GENERAL_KERNEL = 1
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)
@@ -40,7 +41,7 @@ class PlanDesc(C.Structure):
         ("xs", c_f64p), ("ys", c_f64p), ("yivar", c_f64p), ("mask", c_u8p),
         ("n_components", C.c_int32), ("components", C.POINTER(ComponentDesc)),
         ("n_params", C.c_int64), ("coefficient", C.c_double),
-        ("rows_per_group", C.c_int32), ("reserved", C.c_int32),
+        ("rows_per_group", C.c_int32), ("flags", C.c_int32),
     ]
 
 

@@ -102,28 +102,38 @@ __device__ __forceinline__ void step_if_ne(double& cnew, uint32_t ca, uint32_t r
 // retired to the class copy, the other sums move over); further away (first row of a task, rows of
 // a group far apart) everything is retired.  The control points are re-read when the window moved.
 template <int PV>
-__device__ __forceinline__ void win_turn(Win2<PV>& w, int In, uint32_t abase, uint32_t cdelta) {
+__device__ __forceinline__ void win_turn(Win2<PV>& w, int In, uint32_t abase, uint32_t cdelta, bool resync, int lane,
+                                         bool first_row) {
     const int d = In - w.I;
     const bool up = d == 1, dn = d == -1;
-    const bool far = (unsigned)(d + 1) > 2u;
-    if (__any_sync(0xffffffffu, far)) {
+    // resync: the lane sat out the previous row (no weighted pixel), so its window is where an
+    // earlier row left it and the per-row disjointness of the lanes of a class says nothing about it
+    const bool far = (unsigned)(d + 1) > 2u || (resync && d != 0);
+    if (!first_row && __any_sync(0xffffffffu, far)) {      // (first row of a task: the sums are still zero)
+        // windows from different rows may overlap inside a class: one lane of the class at a time
+#pragma unroll 1
+        for (int m = 0; m < (32 + kClasses2 - 1) / kClasses2; ++m) {
+            const int mine = (far && lane / kClasses2 == m) ? 1 : 0;
 #pragma unroll
-        for (int k = 0; k <= PV; ++k) {
-            rmw_if(w.pa + 8u * k, w.a[k], far ? 1 : 0);
-            w.a[k] = far ? 0.0 : w.a[k];
+            for (int k = 0; k <= PV; ++k) rmw_if(w.pa + 8u * k, w.a[k], mine);
+            __syncwarp();
         }
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) w.a[k] = far ? 0.0 : w.a[k];
     }
-    rmw_if(w.pa + (dn ? 8u * PV : 0u), dn ? w.a[PV] : w.a[0], (up || dn) ? 1 : 0);
+    rmw_if(w.pa + (dn ? 8u * PV : 0u), dn ? w.a[PV] : w.a[0], (!far && (up || dn)) ? 1 : 0);
     // slide in place: one pass upwards, one downwards (no temporaries)
+    const bool su = up && !far, sd = dn && !far;
 #pragma unroll
-    for (int k = 0; k < PV; ++k) w.a[k] = up ? w.a[k + 1] : w.a[k];
-    w.a[PV] = up ? 0.0 : w.a[PV];
+    for (int k = 0; k < PV; ++k) w.a[k] = su ? w.a[k + 1] : w.a[k];
+    w.a[PV] = su ? 0.0 : w.a[PV];
 #pragma unroll
-    for (int k = PV; k > 0; --k) w.a[k] = dn ? w.a[k - 1] : w.a[k];
-    w.a[0] = dn ? 0.0 : w.a[0];
+    for (int k = PV; k > 0; --k) w.a[k] = sd ? w.a[k - 1] : w.a[k];
+    w.a[0] = sd ? 0.0 : w.a[0];
     const uint32_t pa = abase + 8u * (uint32_t)In;
+    const int iold = resync ? In + 1 : w.I;      // after sitting out (and at the first row): always re-read
 #pragma unroll
-    for (int k = 0; k <= PV; ++k) lds_if_ne(w.c[k], pa + cdelta + 8u * k, In, w.I);
+    for (int k = 0; k <= PV; ++k) lds_if_ne(w.c[k], pa + cdelta + 8u * k, In, iold);
     w.I = In;
     w.pa = pa;
 }
@@ -213,7 +223,11 @@ __device__ __forceinline__ void f2_pixel(const double (&g)[NC], double y, double
 template <int NC, int PV, int FL, int DIR>
 __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc, Win2<PV> (&win)[NC],
                                        const uint32_t (&abase)[NC], uint32_t cdelta, double& loss,
-                                       double (&sums)[f2_pad(f2_nsums(NC, FL))]) {
+                                       double (&sums)[f2_pad(f2_nsums(NC, FL))], bool live, bool resync, int lane,
+                                       bool first_row) {
+    // live = the lane owns a weighted pixel in this row.  A lane that does not keeps its windows
+    // where they are (its filled pixels carry ivar = 0 and an x on its neighbours' knots: every
+    // sum gets exactly zero from them, wherever the window sits).
     double g[NC];
     bool step[NC];
     {
@@ -223,7 +237,8 @@ __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc,
         for (int c = 0; c < NC; ++c) {
             int In;
             knot_coord<PV>(x, rc.sh[c], rc.xp0[c], rc.inv_dx[c], g[c], In);
-            win_turn<PV>(win[c], In, abase[c], cdelta);
+            In = live ? In : win[c].I;
+            win_turn<PV>(win[c], In, abase[c], cdelta, resync, lane, first_row);
             step[c] = false;
         }
         f2_pixel<NC, PV, FL, 0>(g, y, iv, rc, win, step, loss, sums);
@@ -240,6 +255,7 @@ __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc,
         for (int c = 0; c < NC; ++c) {
             int In;
             knot_coord<PV>(x, rc.sh[c], rc.xp0[c], rc.inv_dx[c], g[c], In);
+            In = live ? In : win[c].I;
             step[c] = win_step<PV, DIR>(win[c], In, abase[c], cdelta);
         }
         f2_pixel<NC, PV, FL, DIR>(g, y, iv, rc, win, step, loss, sums);
@@ -266,7 +282,7 @@ template <int NC> struct F2Ctx {
 // refill the ring stage.
 template <int NC, int PV, int FL, int DIR>
 __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<NC>& rc, Win2<PV> (&win)[NC],
-                                          const uint32_t (&abase)[NC], uint32_t cdelta, double& loss) {
+                                          const uint32_t (&abase)[NC], uint32_t cdelta, double& loss, bool& was_live) {
     constexpr int NS = f2_nsums(NC, FL), NSP = f2_pad(NS);
     using L = F2Lay<NC>;
     const FusedParams& a = g_f2_plan;
@@ -275,16 +291,22 @@ __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<N
     const RowRec<NC, 0>& rec = recs[i];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { rc.sh[c] = rec.sh[c]; rc.st[c] = rec.st[c]; }
-    const int flags = rec.dense;
+    const unsigned live_mask = (unsigned)rec.nkey;      // lanes that own a weighted pixel in this row of the tile
     const uint32_t bar = smem_u32(cx.wb + L::bars) + 8 * s;
     mbar_wait(bar, (uint32_t)((i / kStages) & 1));
     double sums[NSP];
 #pragma unroll
     for (int q = 0; q < NSP; ++q) sums[q] = 0.0;
-    if (flags != 2) {          // some weighted pixel in this row of the tile
+    if (live_mask != 0) {      // some weighted pixel in this row of the tile
         const double* px = reinterpret_cast<const double*>(cx.wb + L::ring + (size_t)s * kTileBytes) + cx.lane;
-        f2_row<NC, PV, FL, DIR>(px, rc, win, abase, cdelta, loss, sums);
-    }
+#ifdef JB_F2_ALL_LIVE   // tuning builds: what the frozen-lane logic costs
+        const bool live = true;
+#else
+        const bool live = (live_mask >> cx.lane) & 1u;
+#endif
+        f2_row<NC, PV, FL, DIR>(px, rc, win, abase, cdelta, loss, sums, live, !was_live, cx.lane, DIR > 0 && i == 0);
+        was_live = live;
+    } else was_live = false;
     if (NS > 0) {
         // per-row sums of this tile (fixed order); the total of value q sits on lanes q*(32/NSP)..
         const double tot = warp_sum_n<NSP>(sums, cx.lane);
@@ -344,7 +366,8 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
         Rec rec = reinterpret_cast<const Rec*>(a.grouprec)[row0 + lane];
         const TileInfo ti = a.tinfo[(int64_t)tile * a.n_rows + row0 + lane];
         rec.dense = ti.flags;
-        has_work = ti.flags != 2;
+        rec.nkey = (int)ti.live;
+        has_work = ti.live != 0;
         if (has_work) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -438,25 +461,37 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
     }
     // control point of knot k of component c sits cdelta bytes behind the class copy's entry
     const uint32_t cdelta = smem_u32(ctrl_warp) - smem_u32(acc_warp + (size_t)cls * NC * W);
-    // the first row start must read its control points even if its interval is the initial one
-#pragma unroll
-    for (int c = 0; c < NC; ++c) win[c].I -= 4;   // "far": retires zeros, reads the control points
 
     double loss = 0.0;
     F2Ctx<NC> cx;
     cx.wb = wbase; cx.nrow = nrow; cx.tile = tile; cx.lane = lane;
 
     // ---- 4. stream the rows of the group, two at a time (up, down) ------------------------------
+    bool was_live = false;
     for (int i = 0; i < nrow; i += 2) {
-        f2_do_row<NC, PV, FL, +1>(i, cx, rc, win, abase, cdelta, loss);
-        if (i + 1 < nrow) f2_do_row<NC, PV, FL, -1>(i + 1, cx, rc, win, abase, cdelta, loss);
+        f2_do_row<NC, PV, FL, +1>(i, cx, rc, win, abase, cdelta, loss, was_live);
+        if (i + 1 < nrow) f2_do_row<NC, PV, FL, -1>(i + 1, cx, rc, win, abase, cdelta, loss, was_live);
     }
 
     // ---- 5. flush, fold the accumulator copies in a fixed order, publish the window ------------
+    if (__all_sync(0xffffffffu, was_live)) {
+        // every window sits on the last row: lanes of a class are on disjoint knots
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int k = 0; k <= PV; ++k) rmw_if(win[c].pa + 8u * k, win[c].a[k], 1);
+            for (int k = 0; k <= PV; ++k) rmw_if(win[c].pa + 8u * k, win[c].a[k], 1);
+    } else {
+        // windows from different rows may overlap inside a class: one lane of the class at a time
+#pragma unroll 1
+        for (int m = 0; m < (32 + kClasses2 - 1) / kClasses2; ++m) {
+            const int mine = lane / kClasses2 == m ? 1 : 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int k = 0; k <= PV; ++k) rmw_if(win[c].pa + 8u * k, win[c].a[k], mine);
+            __syncwarp();
+        }
+    }
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < NC; ++c) {

@@ -167,7 +167,7 @@ __global__ void k_forward(ForwardParams a) {
 // Every sum has one fixed order: no float atomics, bit-reproducible.
 // Per (tile, sorted row): extent of the pixels the kernel walks and the path flags
 // (1 = walk lane by lane, 2 = nothing weighted, 4 = general per-pixel path).
-struct alignas(16) TileInfo { double xmin, xmax; int flags; int pad_[3]; };
+struct alignas(16) TileInfo { double xmin, xmax; int flags; unsigned live; int pad_[2]; };   // live: lanes with a weighted pixel
 
 struct FusedParams {
     const double* data;                         // tile-interleaved x | y | ivar
@@ -778,14 +778,34 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
         const int M = a.comp[c].n_knots;
         for (int k = threadIdx.x; k < M; k += blockDim.x) sacc[k] = 0.0;
         __syncthreads();
-        for (int t = 0; t < a.n_tiles; ++t) {
-            const int64_t task = (int64_t)g * a.n_tiles + t;
-            const int base = a.part_base[(int64_t)c * a.n_tasks + task];
-            if (base == INT_MAX) continue;          // uniform over the block
-            const double* src = a.part + ((int64_t)c * a.n_tasks + task) * a.wincap;
-            for (int w = threadIdx.x; w < a.wincap; w += blockDim.x)
-                if (base + w < M) sacc[base + w] += src[w];
-            __syncthreads();
+        // kPre windows are fetched before the first of them is added: the loads of a block overlap
+        constexpr int kPre = 8;
+        for (int t0 = 0; t0 < a.n_tiles; t0 += kPre) {
+            double v[kPre][2];
+            int base[kPre];
+#pragma unroll
+            for (int j = 0; j < kPre; ++j) {
+                base[j] = INT_MAX; v[j][0] = v[j][1] = 0.0;
+                if (t0 + j < a.n_tiles) {
+                    const int64_t task = (int64_t)g * a.n_tiles + t0 + j;
+                    base[j] = a.part_base[(int64_t)c * a.n_tasks + task];        // uniform over the block
+                    const double* src = a.part + ((int64_t)c * a.n_tasks + task) * a.wincap;
+                    if (base[j] != INT_MAX) {
+                        if ((int)threadIdx.x < a.wincap) v[j][0] = src[threadIdx.x];
+                        if ((int)(threadIdx.x + blockDim.x) < a.wincap) v[j][1] = src[threadIdx.x + blockDim.x];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPre; ++j) {
+                if (base[j] == INT_MAX) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int w = threadIdx.x + h * blockDim.x;
+                    if (w < a.wincap && base[j] + w < M) sacc[base[j] + w] += v[j][h];
+                }
+                __syncthreads();
+            }
         }
         double* dst = a.tmp + ((int64_t)c * a.n_groups + g) * a.max_knots;
         for (int k = threadIdx.x; k < M; k += blockDim.x) dst[k] = sacc[k];
@@ -795,6 +815,7 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
         const int64_t r = i / NQ;
         const int q = (int)(i - r * NQ);
         double s = 0.0;
+#pragma unroll 8
         for (int t = 0; t < a.n_tiles; ++t) s += a.rowpart[(r * a.n_tiles + t) * NQ + q];
         a.rowsum[i] = s;
     } else {   // normalisation control points: per row, sum of the tile partials
@@ -831,6 +852,7 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
                 return;
             }
             double s = 0.0;
+#pragma unroll 8
             for (int g = 0; g < a.n_groups; ++g) s += a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + i];
             a.grad_all[a.ctrl_off[c] + i] = -a.coef * s;
             return;

@@ -74,6 +74,7 @@ struct jb_plan {
     jb::TileInfo* d_tinfo = nullptr;       // [n_tiles][E], sorted-row order
     std::vector<double> h_txmin, h_txmax;  // [E][n_tiles]
     std::vector<uint8_t> h_flags;          // [E][n_tiles]
+    std::vector<uint32_t> h_live;          // [E][n_tiles] lanes of the tile's warp that own a weighted pixel
     std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
     std::vector<uint8_t> h_row_rev;
 
@@ -83,7 +84,8 @@ struct jb_plan {
     bool params_set = false, sort_dirty = true;
     bool fit_shift[jb::kMaxComp] = {false, false, false};   // some shift of the component is in fit mode
     bool force_der = false;    // jb_plan_fisher: derivative sums whatever the fit flags say
-    bool f2_classes_ok = true; // lanes sharing a gradient-window copy of k_fused2 never meet on a knot
+    bool f2_ok = true;         // every tile suits k_fused2: live lanes smooth, lanes sharing a window copy never on one knot
+    bool general_only = false; // JB_PLAN_GENERAL_KERNEL
     bool force_v1 = false;     // a batch whose plans disagree on the kernel variant falls back to k_fused
     int variant = -1;          // fused kernel of this plan: -1 k_fused (general), else the FL flags of k_fused2
     int64_t* d_fit_map = nullptr;
@@ -208,7 +210,7 @@ int resort_rows(jb_plan* pl) {
             const size_t src = (size_t)perm[pos] * pl->n_tiles + t;
             jb::TileInfo& ti = tinfo[(size_t)t * pl->E + pos];
             ti.xmin = pl->h_txmin[src]; ti.xmax = pl->h_txmax[src]; ti.flags = pl->h_flags[src];
-            ti.pad_[0] = ti.pad_[1] = ti.pad_[2] = 0;
+            ti.live = pl->h_live[src]; ti.pad_[0] = ti.pad_[1] = 0;
         }
     JB_CUDA(cudaMemcpyAsync(pl->d_row_perm, perm.data(), pl->E * sizeof(int), cudaMemcpyHostToDevice, pl->stream));
     JB_CUDA(cudaMemcpyAsync(pl->d_tinfo, tinfo.data(), tinfo.size() * sizeof(jb::TileInfo), cudaMemcpyHostToDevice, pl->stream));
@@ -242,7 +244,7 @@ int check_supported_for_eval(const jb_plan* pl) {
 // the environment keeps the general kernel (A/B measurements).
 int plan_variant(const jb_plan* pl) {
     static const bool env_v1 = getenv("JB_FUSED_V1") != nullptr;
-    if (env_v1 || pl->force_v1 || !pl->f2_classes_ok || pl->has_norm || pl->n_glob > 2 || pl->tiles_kind[1] || pl->tiles_kind[2]) return -1;
+    if (env_v1 || pl->general_only || pl->force_v1 || !pl->f2_ok || pl->has_norm || pl->n_glob > 2) return -1;
     int fl = 0;
     for (int c = 0; c < pl->n_glob; ++c) {
         if (pl->desc[c].shift_offset >= 0 && (pl->fit_shift[c] || pl->force_der)) fl |= 1 << c;
@@ -575,6 +577,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->n_tiles = (int)(pl->ppad / jb::kTile);
     pl->has_data = d->ys != nullptr;
     pl->coef = d->coefficient;
+    pl->general_only = (d->flags & JB_PLAN_GENERAL_KERNEL) != 0;
     pl->n_comp = d->n_components;
     // store the components globals first, the per-key (normalisation) ones last
     std::vector<jb_component_desc> comps;
@@ -604,6 +607,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->h_xfirst.assign(E, INFINITY);
     std::vector<double> txmin((size_t)E * NT, INFINITY), txmax((size_t)E * NT, -INFINITY);
     std::vector<uint8_t> dense((size_t)E * NT, 0);
+    std::vector<uint32_t> live((size_t)E * NT, 0);
     double need = 0.0;   // knots two lanes of one class must be apart, in x units, 1 % margin
     for (int c = 0; c < pl->n_glob; ++c)
         need = std::max(need, (comps[c].p_val + 1.01) * comps[c].dx);
@@ -663,37 +667,47 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             double cmax[jb::kClasses], cmax2[jb::kClasses2];
             for (int q = 0; q < jb::kClasses; ++q) cmax[q] = -INFINITY;
             for (int q = 0; q < jb::kClasses2; ++q) cmax2[q] = -INFINITY;
-            bool bad2 = false;   // the same test for the class layout of k_fused2
-            bool bad = false, jumpy = false;
+            // k_fused2 freezes a lane that owns no weighted pixel in a row (its filled x values sit on
+            // its neighbours' knots), so its own tests only look at the other lanes
+            bool bad = false, jumpy = false, bad2 = false, jumpy2 = false;
+            unsigned lv = 0;
             for (int l = 0; l < 32; ++l) {
                 double lmin = INFINITY, lmax = -INFINITY;
+                bool lane_w = false, lane_jumpy = false;
                 for (int j = 0; j < jb::kPixPerLane; ++j) {
                     const size_t i = (size_t)r * ppad + (size_t)t * jb::kTile + l * jb::kPixPerLane + j;
                     lmin = std::min(lmin, hxf[i]); lmax = std::max(lmax, hxf[i]);
                     any_w |= !hm[i];
+                    lane_w |= !hm[i];
                     // inside a lane's run: a step of less than one knot of the finest grid, never backwards
-                    if (j > 0 && !(hxf[i] >= hxf[i - 1] && hxf[i] - hxf[i - 1] < smooth)) jumpy = true;
+                    if (j > 0 && !(hxf[i] >= hxf[i - 1] && hxf[i] - hxf[i - 1] < smooth)) lane_jumpy = true;
                 }
+                jumpy |= lane_jumpy;
                 if (any_w && !(lmax - lmin < norm_dx)) pl->norm_smooth = false;
                 double& cm = cmax[l % jb::kClasses];
                 if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
                 cm = std::max(cm, lmax);
-                double& cm2 = cmax2[l % jb::kClasses2];
-                if (!(lmin - cm2 >= need)) bad2 = true;
-                cm2 = std::max(cm2, lmax);
+                if (lane_w) {
+                    lv |= 1u << l;
+                    jumpy2 |= lane_jumpy;
+                    double& cm2 = cmax2[l % jb::kClasses2];
+                    if (!(lmin - cm2 >= need)) bad2 = true;
+                    cm2 = std::max(cm2, lmax);
+                }
                 txmin[ti] = std::min(txmin[ti], lmin);
                 txmax[ti] = std::max(txmax[ti], lmax);
             }
+            live[ti] = lv;
+            if (lv && (bad2 || jumpy2)) pl->f2_ok = false;
             // flags: 1 = lanes of a class may collide (walk lane by lane), 2 = nothing weighted (skip),
             //        4 = consecutive pixels a knot or more apart somewhere (general per-pixel path)
             dense[ti] = !any_w ? 2 : ((bad ? 1 : 0) | (jumpy ? 4 : 0));
             if (!any_w) { txmin[ti] = INFINITY; txmax[ti] = -INFINITY; }
             pl->tiles_kind[!any_w ? 3 : bad ? 2 : jumpy ? 1 : 0]++;
-            if (any_w && bad2) pl->f2_classes_ok = false;
         }
     }
     int rc;
-    pl->h_txmin = txmin; pl->h_txmax = txmax; pl->h_flags = dense;
+    pl->h_txmin = txmin; pl->h_txmax = txmax; pl->h_flags = dense; pl->h_live = live;
     if ((rc = dev_alloc(pl, &pl->d_tinfo, (size_t)NT * E))) return rc;
     {
         char* rec = nullptr;
