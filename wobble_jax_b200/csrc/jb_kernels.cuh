@@ -778,32 +778,45 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
         const int M = a.comp[c].n_knots;
         for (int k = threadIdx.x; k < M; k += blockDim.x) sacc[k] = 0.0;
         __syncthreads();
-        // kPre windows are fetched before the first of them is added: the loads of a block overlap
-        constexpr int kPre = 8;
-        for (int t0 = 0; t0 < a.n_tiles; t0 += kPre) {
-            double v[kPre][2];
-            int base[kPre];
-#pragma unroll
-            for (int j = 0; j < kPre; ++j) {
-                base[j] = INT_MAX; v[j][0] = v[j][1] = 0.0;
-                if (t0 + j < a.n_tiles) {
-                    const int64_t task = (int64_t)g * a.n_tiles + t0 + j;
-                    base[j] = a.part_base[(int64_t)c * a.n_tasks + task];        // uniform over the block
-                    const double* src = a.part + ((int64_t)c * a.n_tasks + task) * a.wincap;
-                    if (base[j] != INT_MAX) {
-                        if ((int)threadIdx.x < a.wincap) v[j][0] = src[threadIdx.x];
-                        if ((int)(threadIdx.x + blockDim.x) < a.wincap) v[j][1] = src[threadIdx.x + blockDim.x];
-                    }
-                }
+        // Windows of tiles two apart normally do not overlap (a tile is wider than the window's
+        // margin): then all even tiles are added at once (disjoint addresses, every load of the
+        // block in flight together), a barrier, then all odd tiles.  Otherwise one tile at a time.
+        // Either way each knot sums its contributions in one fixed order.
+        __shared__ int sbase[256];
+        __shared__ int s_disjoint;
+        const int NT = a.n_tiles;
+        const int64_t task0 = (int64_t)c * a.n_tasks + (int64_t)g * NT;
+        if (threadIdx.x == 0) s_disjoint = NT <= 256 ? 1 : 0;
+        __syncthreads();
+        if (NT <= 256) {
+            for (int t = threadIdx.x; t < NT; t += blockDim.x) sbase[t] = a.part_base[task0 + t];
+            __syncthreads();
+            for (int t = threadIdx.x; t + 2 < NT; t += blockDim.x) {
+                // the next valid tile of the same parity must start behind this tile's window
+                if (sbase[t] == INT_MAX) continue;
+                int u = t + 2;
+                while (u < NT && sbase[u] == INT_MAX) u += 2;
+                if (u < NT && sbase[u] - sbase[t] < a.wincap) s_disjoint = 0;
             }
-#pragma unroll
-            for (int j = 0; j < kPre; ++j) {
-                if (base[j] == INT_MAX) continue;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int w = threadIdx.x + h * blockDim.x;
-                    if (w < a.wincap && base[j] + w < M) sacc[base[j] + w] += v[j][h];
+            __syncthreads();
+        }
+        if (s_disjoint) {
+            for (int par = 0; par < 2; ++par) {
+                const int n_par = (NT - par + 1) / 2;              // tiles par, par+2, ...
+                for (int e = threadIdx.x; e < n_par * a.wincap; e += blockDim.x) {
+                    const int t = par + 2 * (e / a.wincap), w = e % a.wincap;
+                    const int base = sbase[t];
+                    if (base != INT_MAX && base + w < M) sacc[base + w] += a.part[(task0 + t) * a.wincap + w];
                 }
+                __syncthreads();
+            }
+        } else {
+            for (int t = 0; t < NT; ++t) {
+                const int base = a.part_base[task0 + t];      // uniform over the block
+                if (base == INT_MAX) continue;
+                const double* src = a.part + (task0 + t) * a.wincap;
+                for (int w = threadIdx.x; w < a.wincap; w += blockDim.x)
+                    if (base + w < M) sacc[base + w] += src[w];
                 __syncthreads();
             }
         }
