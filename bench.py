@@ -401,14 +401,21 @@ def run_epochs(args, rank, world, local_rank):
     main = torch.cuda.Stream()            # non-default: a NULL stream means "the plan's own" to the C ABI
     main.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(main)
+    # the slabs of this rank are evaluated by ONE launch per kernel (jb_batch); their parameter
+    # vectors live in one flat buffer so that one add perturbs them all
+    offs = np.concatenate([[0], np.cumsum([t.numel() for t in d_p])])
+    P_all = torch.cat(d_p)
+    d_p = [P_all[int(offs[i]):int(offs[i + 1])] for i in range(len(plans))]
+    batch = engine.Batch(plans)
+    batch.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
+    views = [do[1 + n:1 + n + 2 * M] for do, (n, _) in zip(d_out, sizes)]   # fit order: shifts(n), S(M), T(M), airmass(n)
+    heads = [do[0:1] for do in d_out]
 
     def step():
-        red.zero_()
-        for pl, dp, do, (n, _) in zip(plans, d_p, d_out, sizes):
-            dp.add_(1e-13)
-            pl.eval_device(dp.data_ptr(), do.data_ptr(), main.cuda_stream)
-            red[0] += do[0]
-            red[1:] += do[1 + n:1 + n + 2 * M]          # fit order: shifts(n), S(M), T(M), airmass(n)
+        P_all.add_(1e-13)
+        batch.eval_device(main.cuda_stream)
+        torch.sum(torch.stack(views), dim=0, out=red[1:])
+        torch.sum(torch.cat(heads), dim=0, out=red[0])
         if dist is not None:
             dist.all_reduce(red)
 
