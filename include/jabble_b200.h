@@ -160,7 +160,19 @@ int jb_plan_forward(jb_plan *plan, const double *p_fit, int64_t n_fit, double *m
  */
 int jb_plan_fisher(jb_plan *plan, int32_t component, double *f_out, int64_t n_shift);
 
-/* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests). */
+/*
+ * EpochSpecificModel.grid_search (jabble/model.py:738-786) for the ShiftingModel of additive
+ * component `component`: loss_out[k * n_grid + j] = the loss (coefficient * chi-square) of the rows
+ * whose shift key is k, evaluated with that shift replaced by grid[k * n_grid + j] and every other
+ * parameter as stored (jb_plan_set_params).  The reference evaluates the n_grid columns under
+ * jax.vmap and sums rows into keys on the host; here one kernel forms every (row, candidate) sum
+ * and the rows of a key are added in row order.  Called by parabola_fit (model.py:788-831).
+ */
+int jb_plan_grid_search(jb_plan *plan, int32_t component, const double *grid, int64_t n_shift,
+                        int64_t n_grid, double *loss_out);
+
+/* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests).  Entries of
+ * parameters that are not in fit mode hold only what the kernel variant of that evaluation formed. */
 int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);
 
 /*

@@ -368,6 +368,67 @@ def rv_error_fisher(shift_values, finfo) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# RV grid search and parabola refinement        reference: model.py:738-831
+# --------------------------------------------------------------------------
+
+def grid_search(grid, which_key, datablock, metablock, model, coefficient=1.0) -> np.ndarray:
+    """model.py:738-786 -- EpochSpecificModel.grid_search.
+
+    The caller puts ONLY the searched EpochSpecificModel in fit mode (model.fix(); self.fit()),
+    so a column of ``grid`` (N keys x M candidates) is the whole fit vector.  Per column j and row r:
+    Q[r] = loss(grid[:, j], datarow_r, metarow_r, model).sum(); out[k, j] = sum of Q over the rows
+    whose ``which_key`` id is k (the vmap over columns is a plain loop here).
+    """
+    grid = np.asarray(grid, dtype=np.float64)
+    xs, ys, yivar = _t(datablock["xs"]), _t(datablock["ys"]), _t(datablock["yivar"])
+    mask = torch.as_tensor(np.asarray(datablock["mask"]).astype(bool))
+    E = xs.shape[0]
+    keys = np.asarray(metablock[which_key]).astype(np.int64)
+    out = np.zeros(grid.shape)
+    with torch.no_grad():
+        for j in range(grid.shape[1]):
+            p = _t(grid[:, j])
+            Q = np.zeros(E)
+            for r in range(E):
+                meta = {k: int(v[r]) for k, v in metablock.items()}
+                Q[r] = float(chi_square_row(p, xs[r], ys[r], yivar[r], mask[r], meta, model, coefficient).sum())
+            for unq in np.unique(keys):
+                out[unq, j] = Q[np.where(keys == unq)].sum()
+    return out
+
+
+def parabola_fit(p, array1d, loss_grid) -> np.ndarray:
+    """model.py:788-831 -- EpochSpecificModel.parabola_fit after its grid search: for every key
+    whose lowest grid loss is not at an end of the grid, the vertex of the parabola through that
+    point and its two neighbours replaces the parameter.
+
+    Quirk restated as is (model.py:819-830): the parabolas are taken from the FIRST n rows of the
+    grid (``inds_i = arange(n)``, n = number of interior minima) at the column triplets of the
+    interior rows, and written to the interior rows -- equal to the intended row-by-row fit only when
+    no row before an interior one has its minimum at an end.  polyfit of 3 points by a parabola is the
+    interpolating parabola; its derivative's root is the vertex.
+    """
+    p = np.asarray(p, dtype=np.float64).copy()
+    array1d = np.asarray(array1d, dtype=np.float64)
+    loss_grid = np.asarray(loss_grid, dtype=np.float64)
+    grid = p[:, None] + array1d[None, :]
+    minima = np.argmin(loss_grid, axis=1).astype(int)
+    mask_ends = (minima == 0) | (minima == loss_grid.shape[1] - 1)
+    n = int(np.sum(~mask_ends))
+    if n == 0:
+        return p
+    inds_i = np.arange(0, n, dtype=int).repeat(3).reshape(-1, 3)
+    inds_j = (minima[~mask_ends, None] + np.array([-1, 0, 1])[None, :]).reshape(-1, 3)
+    g, l = grid[inds_i, inds_j], loss_grid[inds_i, inds_j]
+    g_min = np.empty(n)
+    for i in range(n):
+        poly = np.polyfit(g[i], l[i], 2)
+        g_min[i] = np.roots(np.polyder(poly))[0].real
+    p[~mask_ends] = g_min
+    return p
+
+
+# --------------------------------------------------------------------------
 # dataset.py:192-237  blockify (host-side layout of the inputs)
 # --------------------------------------------------------------------------
 

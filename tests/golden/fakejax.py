@@ -205,6 +205,9 @@ jnp.ones = _ones
 jnp.arange = _arange
 jnp.where = _where
 jnp.polyval = _polyval
+jnp.polyfit = lambda x, y, deg: _arr(np.polyfit(np.asarray(x), np.asarray(y), deg))
+jnp.polyder = lambda p: _arr(np.polyder(np.asarray(p)))
+jnp.roots = lambda p, strip_zeros=True: _arr(np.roots(np.asarray(p)).astype(np.complex128).real)
 jnp.floor = lambda x: torch.floor(_arr(x)).as_subclass(Arr)
 jnp.exp = lambda x: torch.exp(_arr(x)).as_subclass(Arr)
 jnp.log = lambda x: torch.log(_arr(x)).as_subclass(Arr)
@@ -250,17 +253,23 @@ def _lead(arg):
     return arg.shape[0]
 
 
+def _take(arg, i, axis):
+    if axis == 0:
+        return _index_arg(arg, i)
+    return _arr(arg).select(axis, i).as_subclass(Arr)
+
+
 def _vmap(fun, in_axes=0, out_axes=0):
     def mapped(*args):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
-        if out_axes != 0 or any(a not in (0, None) for a in axes):
-            # the only non-zero axis the reference uses is in grid_search (out of scope)
-            raise NotImplementedError("fakejax.vmap: only axis 0")
-        n = next(_lead(a) for a, ax in zip(args, axes) if ax == 0)
+        n = next(_lead(a) if ax == 0 else _arr(a).shape[ax] for a, ax in zip(args, axes) if ax is not None)
         outs = []
         for i in range(n):
-            outs.append(fun(*[_index_arg(a, i) if ax == 0 else a for a, ax in zip(args, axes)]))
-        return torch.stack([o.as_subclass(torch.Tensor) for o in outs]).as_subclass(Arr)
+            outs.append(fun(*[_take(a, i, ax) if ax is not None else a for a, ax in zip(args, axes)]))
+        if isinstance(outs[0], tuple):     # several outputs (parabola_fit): stack each
+            return tuple(torch.stack([_arr(o[k]).as_subclass(torch.Tensor) for o in outs], dim=out_axes).as_subclass(Arr)
+                         for k in range(len(outs[0])))
+        return torch.stack([o.as_subclass(torch.Tensor) for o in outs], dim=out_axes).as_subclass(Arr)
 
     return mapped
 

@@ -221,6 +221,20 @@ def fixture_wobble(pv, name, ragged=False, descending=False, keyed=False):
     out["coef_loss"] = npy(loss2.loss_all(p, db, mb, model, DEV, 100))
     out["coef_grad"] = npy(fakejax.jax.grad(loss2.loss_all)(p, db, mb, model, DEV, 100))
     model.fix()
+    # EpochSpecificModel.grid_search / parabola_fit (model.py:738-831) around the stored shifts
+    arr1d = npy(jabble.physics.shifts(np.linspace(-6000.0, 6000.0, 13)))
+    for tag, sm in (("gs", model[0][0]), ("gs_tell", model[1][0])):
+        g = np.array(npy(sm.p)[:, None] + arr1d[None, :])
+        out[tag + "_grid"] = g
+        out[tag + "_loss"] = npy(sm.grid_search(g, loss, model, dataset, DEV))
+    out["pf_array1d"] = arr1d
+    mins = np.argmin(out["gs_loss"], axis=1)
+    if np.any((mins > 0) & (mins < len(arr1d) - 1)):     # the reference vmaps over the interior minima: none -> it fails
+        p_keep = npy(model[0][0].p).copy()
+        model[0][0].parabola_fit(arr1d, loss, model, dataset, DEV, DEV)
+        out["pf_p"] = npy(model[0][0].p)
+        model[0][0].p = jnp.array(p_keep)
+    model.fix()
     for k, rows in (("xs", xs), ("ys", ys), ("ivs", ivs), ("ms", ms)):
         ragged_pack(out, k, rows)
     out["block_xs"], out["block_mask"] = npy(db["xs"]), npy(db["mask"])

@@ -77,6 +77,13 @@ def test_golden_wobble(name):
     p = np.asarray(model.get_parameters())
     assert abs(obj.value(p) - float(g["coef_loss"])) <= TOL * abs(float(g["coef_loss"]))
     _check_grad(model, obj.gradient(p), g["coef_grad"])
+    # RV grid search and parabola refinement through the reference-facing API (model.py:738-831)
+    for tag, leaf in (("gs", model[0][0]), ("gs_tell", model[1][0])):
+        L = leaf.grid_search(g[tag + "_grid"], loss, model, data)
+        assert rel_err(L, g[tag + "_loss"]) < TOL, tag
+    if "pf_p" in g:
+        model[0][0].parabola_fit(g["pf_array1d"], loss, model, data)
+        assert np.allclose(model[0][0].p, g["pf_p"], rtol=0, atol=1e-12)
 
 
 def test_golden_stellar():
@@ -332,3 +339,36 @@ def test_stellar_only_specialised_kernel():
         assert abs(vf - vs) <= 1e-12 * abs(vs)
         _check_grad(model, gf, gs, tol=1e-11)
         fast.close(); slow.close()
+
+
+def test_grid_search_vs_oracle_at_size():
+    """500 candidates per epoch (quickplay.train_cycle's parabola stage) against the oracle on a sample
+    of epochs, and the stellar shifts recovered by parabola_fit from a perturbed start."""
+    ch = synth.make_chunk(chunk=7, n_epochs=40, n_pix=1500, p_val=3, n_lines=25)
+    model = ch.model
+    db, mb, dbd, mbd = _blocks(ch.data)
+    loss = jabble.loss.ChiSquare()
+    arr = jabble.physics.shifts(np.linspace(-100, 100, 500))
+    grid = model[0][0].p[:, None] + arr[None, :]
+    L = model[0][0].grid_search(grid, loss, model, ch.data)
+    assert L.shape == grid.shape and np.all(np.isfinite(L))
+    cols = [0, 17, 250, 499]
+    Lo = O.grid_search(grid[:, cols], "index", dbd, mbd, model)
+    assert rel_err(L[:, cols], Lo) < TOL
+    # the loss of the stored shifts is the column of the zero offset
+    model.fix(); model[0][0].fit()
+    p = np.asarray(model.get_parameters())
+    obj = engine.Objective(loss, model, db, mb)
+    zero = np.argmin(np.abs(arr))
+    g2 = model[0][0].p[:, None] + np.array([0.0])[None, :]
+    assert abs(model[0][0].grid_search(g2, loss, model, ch.data).sum() - obj.value(p)) <= 1e-12 * obj.value(p)
+    # a grid wide enough that every epoch has its minimum inside it (with end minima the reference's
+    # row indexing mixes epochs, model.py:819-830): the parabola vertices lower the loss
+    before = obj.value(p)
+    wide = jabble.physics.shifts(np.linspace(-600, 600, 241))
+    Lw = model[0][0].grid_search(model[0][0].p[:, None] + wide[None, :], loss, model, ch.data)
+    mins = np.argmin(Lw, axis=1)
+    assert np.all((mins > 0) & (mins < len(wide) - 1))
+    model[0][0].parabola_fit(wide, loss, model, ch.data)
+    model.fix(); model[0][0].fit()
+    assert engine.Objective(loss, model, db, mb).value(np.asarray(model.get_parameters())) < before

@@ -137,6 +137,13 @@ def test_golden_wobble(name):
     val, grad = O.loss_and_grad(O.get_parameters(model), dbd, mbd, model, coefficient=0.37)
     assert abs(val - float(g["coef_loss"])) <= 1e-12 * abs(val)
     assert rel_err(grad, g["coef_grad"]) < 1e-11
+    # RV grid search and parabola refinement (model.py:738-831)
+    for tag, leaf in (("gs", (0, 0)), ("gs_tell", (1, 0))):
+        set_fit(model, [leaf])
+        L = O.grid_search(g[tag + "_grid"], meta["which_key"], dbd, mbd, model)
+        assert rel_err(L, g[tag + "_loss"]) < 1e-11
+    if "pf_p" in g:
+        assert np.allclose(O.parabola_fit(model[0][0].p, g["pf_array1d"], g["gs_loss"]), g["pf_p"], rtol=0, atol=1e-13)
 
 
 def test_golden_pseudonormal():

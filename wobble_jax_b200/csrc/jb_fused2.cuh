@@ -220,14 +220,15 @@ __device__ __forceinline__ void f2_pixel(const double (&g)[NC], double y, double
 
 // One row of the task walked in direction DIR (+1: pixels 0..3 of the lane, -1: 3..0).
 // px = the lane's column of the staged record (pixel j at [32 * j], x | y | ivar kTile doubles apart).
-template <int NC, int PV, int FL, int DIR>
+template <int NC, int PV, int FL, int DIR, bool ALL>
 __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc, Win2<PV> (&win)[NC],
                                        const uint32_t (&abase)[NC], uint32_t cdelta, double& loss,
                                        double (&sums)[f2_pad(f2_nsums(NC, FL))], bool live, bool resync, int lane,
                                        bool first_row) {
     // live = the lane owns a weighted pixel in this row.  A lane that does not keeps its windows
     // where they are (its filled pixels carry ivar = 0 and an x on its neighbours' knots: every
-    // sum gets exactly zero from them, wherever the window sits).
+    // sum gets exactly zero from them, wherever the window sits).  ALL: every lane of the row is live.
+    if (ALL) live = true;
     double g[NC];
     bool step[NC];
     {
@@ -299,12 +300,11 @@ __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<N
     for (int q = 0; q < NSP; ++q) sums[q] = 0.0;
     if (live_mask != 0) {      // some weighted pixel in this row of the tile
         const double* px = reinterpret_cast<const double*>(cx.wb + L::ring + (size_t)s * kTileBytes) + cx.lane;
-#ifdef JB_F2_ALL_LIVE   // tuning builds: what the frozen-lane logic costs
-        const bool live = true;
-#else
         const bool live = (live_mask >> cx.lane) & 1u;
-#endif
-        f2_row<NC, PV, FL, DIR>(px, rc, win, abase, cdelta, loss, sums, live, !was_live, cx.lane, DIR > 0 && i == 0);
+        if (live_mask == 0xffffffffu)     // the usual row: no lane sits out (the frozen-lane selects fold away)
+            f2_row<NC, PV, FL, DIR, true>(px, rc, win, abase, cdelta, loss, sums, true, !was_live, cx.lane, DIR > 0 && i == 0);
+        else
+            f2_row<NC, PV, FL, DIR, false>(px, rc, win, abase, cdelta, loss, sums, live, !was_live, cx.lane, DIR > 0 && i == 0);
         was_live = live;
     } else was_live = false;
     if (NS > 0) {

@@ -145,6 +145,82 @@ __global__ void k_forward(ForwardParams a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// EpochSpecificModel.grid_search (jabble/model.py:738-786) for the ShiftingModel of one additive
+// component: the chi-square of every row at M candidate values of that row's shift, everything
+// else as stored.  Only the searched component depends on the candidate, so a block first forms
+// y - (all other components) for a tile of pixels, once, and then every thread walks the tile for
+// its own candidate: out[row][j] = sum_pix ivar * (y - m_j)^2.
+struct GridParams {
+    const double* data;            // tile-interleaved x | y | ivar (mask folded: ivar = 0)
+    int64_t n_rows;
+    int n_tiles;
+    int n_comp;
+    CompDev comp[kMaxComp];
+    int search;                    // stored index of the component whose shift is searched
+    const double* grid;            // [n_keys][M] candidate shifts
+    int M;
+    double* out;                   // [n_rows][M]
+    int* status;
+};
+
+template <int PV>
+__global__ void k_grid_search(GridParams a) {
+    __shared__ double sx[kTile], sr[kTile], sw[kTile];
+    const int64_t r = blockIdx.x;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;      // candidate of this thread
+    const CompDev& cs = a.comp[a.search];
+    const double st = cs.stretch ? cs.stretch[cs.stretch_key[r]] : 1.0;
+    const double sh = j < a.M ? a.grid[(int64_t)cs.shift_key[r] * a.M + j] : 0.0;
+    const double* ctrl = cs.ctrl;
+    double acc = 0.0;
+    bool ok = true;
+    for (int t = 0; t < a.n_tiles; ++t) {
+        const double* rec = a.data + (r * a.n_tiles + t) * kTileDoubles;
+        const int p = threadIdx.x;                             // blockDim.x == kTile: one pixel each
+        const int pos = (p % kPixPerLane) * 32 + p / kPixPerLane;
+        const double x = rec[pos], y = rec[kTile + pos], w = rec[2 * kTile + pos];
+        double mo = 0.0;
+        if (w != 0.0) {
+            for (int ci = 0; ci < a.n_comp; ++ci) {
+                if (ci == a.search) continue;
+                const CompDev& c = a.comp[ci];
+                const double shift = c.shift ? c.shift[c.shift_key[r]] : 0.0;
+                const double* cc = c.kind == 1 ? c.ctrl + (int64_t)c.ctrl_key[r] * c.n_knots : c.ctrl;
+                double s;
+                if (c.p_val == 3) s = spline_value<3>(c, cc, x, shift, ok);
+                else if (c.p_val == 2) s = spline_value<2>(c, cc, x, shift, ok);
+                else s = spline_value<1>(c, cc, x, shift, ok);
+                if (c.stretch) s *= c.stretch[c.stretch_key[r]];
+                mo += s;
+            }
+        }
+        __syncthreads();       // the previous tile has been consumed
+        sx[p] = x; sr[p] = y - mo; sw[p] = w;
+        __syncthreads();
+        if (j < a.M) {
+            for (int q = 0; q < kTile; ++q) {
+                const double wq = sw[q];
+                if (wq == 0.0) continue;                       // same for every thread of the block
+                double g; int I;
+                knot_coord<PV>(sx[q], sh, cs.xp0, cs.inv_dx, g, I);
+                const double tt = ((sx[q] - sh) - cs.xp0) * cs.inv_dx;
+                const int klo = knot_lo<PV>(I);
+                if (!(tt > -1.0e9 && tt < 1.0e9) || klo < 0 || klo + PV > cs.n_knots - 1) { ok = false; continue; }
+                double wgt[PV + 1], dw[PV > 0 ? PV : 1];
+                Basis<PV>::eval(g, wgt, dw);
+                double sv = 0.0;
+#pragma unroll
+                for (int k = 0; k <= PV; ++k) sv = __fma_rn(__ldg(ctrl + klo + k), wgt[k], sv);
+                const double res = sr[q] - st * sv;
+                acc = __fma_rn(wq * res, res, acc);
+            }
+        }
+    }
+    if (j < a.M) a.out[r * a.M + j] = acc;
+    if (!ok) atomicOr(a.status, kStatOutOfRange);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused loss + gradient + Fisher.
 //
 // Work item ("task") = one warp, one tile of kTile pixel columns, one group of <= 32 rows.

@@ -103,6 +103,7 @@ struct jb_plan {
     int* d_key_ptr[jb::kMaxComp][3] = {};   // [comp][0 shift, 1 stretch, 2 per-key control points] CSR rowptr
     int* d_key_rows[jb::kMaxComp][3] = {};
     int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
+    std::vector<int> h_shift_key[jb::kMaxComp];   // host copy of the shift keys (jb_plan_grid_search sums rows into keys)
 
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
     int64_t tiles_kind[4] = {0, 0, 0, 0};   // smooth, general, serial, empty
@@ -752,6 +753,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                 if (k[r] < 0 || k[r] >= nkeys[s]) return fail(JB_ERR_BAD_ARG, "component %d: key %d of row %lld outside [0,%lld)", c, k[r], (long long)r, (long long)nkeys[s]);
             }
             if ((rc = dev_upload(pl, &pl->d_keys[c][s], k))) return rc;
+            if (s == 0) pl->h_shift_key[c] = k;
             {   // CSR key -> rows, rows ascending: the fixed order of the per-key sums
                 std::vector<int> ptr(nkeys[s] + 1, 0), rows(E);
                 for (int64_t r = 0; r < E; ++r) ptr[k[r] + 1]++;
@@ -944,6 +946,53 @@ int jb_plan_fisher(jb_plan* pl, int32_t component, double* f_out, int64_t n_shif
     pl->force_der = false; pl->pack_dirty = true;
     if (rc) return rc;
     JB_CUDA(cudaMemcpy(f_out, pl->d_fisher_all + cd.shift_offset, n_shift * sizeof(double), cudaMemcpyDeviceToHost));
+    return JB_OK;
+}
+
+int jb_plan_grid_search(jb_plan* pl, int32_t component, const double* grid, int64_t n_shift, int64_t n_grid,
+                        double* loss_out) {
+    if (!pl || !grid || !loss_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (component < 0 || component >= pl->n_comp) return fail(JB_ERR_BAD_ARG, "component %d", component);
+    if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
+    if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "jb_plan_set_params has not been called");
+    int ci = 0;
+    while (pl->ext_of[ci] != component) ++ci;
+    const jb_component_desc& cd = pl->desc[ci];
+    if (cd.kind != JB_COMP_SPLINE) return fail(JB_ERR_UNSUPPORTED, "grid search over the shift of a NormalizationModel component");
+    if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
+    if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
+    if (n_grid <= 0 || n_grid > (1 << 20)) return fail(JB_ERR_BAD_ARG, "n_grid %lld", (long long)n_grid);
+    JB_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    double *d_grid = nullptr, *d_out = nullptr;
+    JB_CUDA(cudaMallocAsync(&d_grid, (size_t)n_shift * n_grid * sizeof(double), st));
+    JB_CUDA(cudaMallocAsync(&d_out, (size_t)pl->E * n_grid * sizeof(double), st));
+    JB_CUDA(cudaMemcpyAsync(d_grid, grid, (size_t)n_shift * n_grid * sizeof(double), cudaMemcpyHostToDevice, st));
+    jb::GridParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.data = pl->d_data; gp.n_rows = pl->E; gp.n_tiles = pl->n_tiles; gp.n_comp = pl->n_comp;
+    for (int c = 0; c < pl->n_comp; ++c) gp.comp[c] = pl->comp[c];
+    gp.search = ci; gp.grid = d_grid; gp.M = (int)n_grid; gp.out = d_out; gp.status = pl->d_status;
+    const dim3 blocks((unsigned)pl->E, (unsigned)((n_grid + jb::kTile - 1) / jb::kTile));
+    switch (cd.p_val) {
+        case 1: jb::k_grid_search<1><<<blocks, jb::kTile, 0, st>>>(gp); break;
+        case 2: jb::k_grid_search<2><<<blocks, jb::kTile, 0, st>>>(gp); break;
+        default: jb::k_grid_search<3><<<blocks, jb::kTile, 0, st>>>(gp); break;
+    }
+    pl->launches++;
+    JB_CUDA(cudaGetLastError());
+    std::vector<double> rows((size_t)pl->E * n_grid);
+    JB_CUDA(cudaMemcpyAsync(rows.data(), d_out, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaFreeAsync(d_grid, st));
+    JB_CUDA(cudaFreeAsync(d_out, st));
+    int rc = read_status(pl, st, nullptr);     // synchronises the stream
+    if (rc) return rc;
+    // rows -> keys, in row order (model.py:777-781); ChiSquare: coefficient * 0.5 * ivar * res^2
+    std::fill(loss_out, loss_out + n_shift * n_grid, 0.0);
+    const std::vector<int>& key = pl->h_shift_key[ci];
+    for (int64_t r = 0; r < pl->E; ++r)
+        for (int64_t j = 0; j < n_grid; ++j) loss_out[(int64_t)key[r] * n_grid + j] += rows[(size_t)r * n_grid + j];
+    for (int64_t i = 0; i < n_shift * n_grid; ++i) loss_out[i] *= 0.5 * pl->coef;
     return JB_OK;
 }
 

@@ -257,6 +257,17 @@ class Plan:
         _lib.check(self.lib.jb_plan_fisher(self.handle, component, out.ctypes.data_as(_lib.c_f64p), n))
         return out
 
+    def grid_search(self, component, grid):
+        """(n_keys, M) losses of the rows of every shift key of ``component`` at M candidate shifts."""
+        g = np.ascontiguousarray(grid, dtype=np.float64)
+        n = self.spec.leaf_of(self.spec.components[component]["shift"]).size
+        if g.ndim != 2 or g.shape[0] != n:
+            raise ValueError(f"grid must be ({n}, M), got {g.shape}")
+        out = np.empty(g.shape, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_grid_search(self.handle, component, g.ctypes.data_as(_lib.c_f64p), n, g.shape[1],
+                                                out.ctypes.data_as(_lib.c_f64p)))
+        return out
+
     def grad_all(self):
         out = np.empty(self.spec.n_params, dtype=np.float64)
         _lib.check(self.lib.jb_plan_grad_all(self.handle, out.ctypes.data_as(_lib.c_f64p), out.size))
@@ -434,6 +445,24 @@ def evaluate_row(model, p, x, meta):
         if len(p) not in (0, plan.n_fit):
             raise ValueError(f"p has {len(p)} entries, the model has {plan.n_fit} parameters in fit mode")
         return plan.forward(p)[0]
+    finally:
+        plan.close()
+
+
+def grid_search(model, shift_model, datablock, metablock, grid, coefficient=1.0, device=0):
+    """EpochSpecificModel.grid_search (jabble/model.py:738-786) for a ShiftingModel of the tree."""
+    spec = TreeSpec(model)
+    comp = None
+    for i, c in enumerate(spec.components):
+        if c["shift"] is shift_model:
+            comp = i
+    if comp is None:
+        raise NotImplementedError("grid_search runs on the CUDA path for the ShiftingModel of an additive component only")
+    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
+                coefficient=coefficient, device=device)
+    try:
+        plan.sync_from_model()
+        return plan.grid_search(comp, grid)
     finally:
         plan.close()
 

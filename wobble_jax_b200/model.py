@@ -328,11 +328,55 @@ class EpochSpecificModel(Model):
         datablock, metablock = data.blockify(device)
         return engine.fisher_information(model, self, datablock, metablock)
 
-    def grid_search(self, *args, **kwargs):
-        raise NotImplementedError("grid_search is outside the accelerated hot path (SURVEY.md section 8f-3)")
+    def grid_search(self, grid, loss, model, data, device=None, epoches=None):
+        """model.py:738-786 -- the loss of the rows of every epoch at each of M candidate values of
+        this model's parameter: ``grid`` is (N epochs, M), the result too.  Like the reference this
+        puts the whole model in fixed mode and ``self`` in fit mode.  One kernel forms all
+        (row, candidate) sums (``jb_plan_grid_search``); the reference loops rows in Python under a
+        vmap over the M columns.
+        """
+        from . import engine
+        from . import loss as L
 
-    def parabola_fit(self, *args, **kwargs):
-        raise NotImplementedError("parabola_fit is outside the accelerated hot path (SURVEY.md section 8f-3)")
+        if not isinstance(loss, L.ChiSquare):
+            raise NotImplementedError("grid_search runs on the CUDA path for ChiSquare only")
+        if epoches is None:
+            epoches = slice(0, self.n)
+        model.fix()
+        self.fit(epoches=epoches)
+        if isinstance(model, ContainerModel):
+            model.get_parameters()
+        datablock, metablock = data.blockify(device)
+        return engine.grid_search(model, self, datablock, metablock, np.asarray(grid, dtype=np.float64),
+                                  coefficient=loss.coefficient)
+
+    def parabola_fit(self, array1d, loss, model, data, device_1=None, device_2=None):
+        """model.py:788-831 -- grid search around every parameter, then the vertex of the parabola
+        through the lowest grid point and its two neighbours replaces the parameter (epochs whose
+        minimum sits at an end of the grid keep theirs).
+
+        Restated as the reference has it, including its row indexing (model.py:819-830): the
+        parabolas are read from the FIRST n rows of the grid, n = number of interior minima, at the
+        column triplets of the interior rows.
+        """
+        array1d = np.asarray(array1d, dtype=np.float64)
+        grid = np.array(self.p[:, None] + array1d[None, :])
+        lgrid = np.array(self.grid_search(grid, loss, model, data, device_1))
+        minima = np.argmin(lgrid, axis=1).astype(int)
+        mask_ends = ((minima == 0) + (minima == lgrid.shape[1] - 1)).astype(bool)
+        n = int(np.sum(~mask_ends))
+        if n == 0:
+            return
+        inds_i = np.arange(0, n, dtype=int).repeat(3).reshape(-1, 3)
+        inds_j = (minima[~mask_ends, None] + np.array([-1, 0, 1])[None, :]).flatten().reshape(-1, 3)
+        g, l = grid[inds_i, inds_j], lgrid[inds_i, inds_j]
+        g_min = np.empty(n)
+        for i in range(n):
+            poly = np.polyfit(g[i], l[i], deg=2)
+            g_min[i] = np.roots(np.polyder(poly))[0].real
+        p = np.array(self.p, dtype=np.float64)
+        p[~mask_ends] = g_min
+        self.p = p
 
 
 class ShiftingModel(EpochSpecificModel):

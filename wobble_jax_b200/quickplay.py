@@ -61,18 +61,22 @@ def train_cycle(model, dataset, loss, device_store=None, device_op=None, batch_s
                 options={"maxiter": 100_000}, parabola_fit=False):
     """quickplay.py:287-380 -- the staged fit: stellar template; stellar+telluric templates; RVs;
     everything; RVs; everything.  RV is model[0][0], templates model[0][1] and model[1][1]."""
-    if parabola_fit:
-        raise NotImplementedError("parabola_fit is SURVEY.md section 8f-3 (not built yet)")
     stages = [
         [(0, 1)],
         [(0, 1), (1, 1)],
         [(0, 0)],
+        "parabola",
         [(0, 0), (0, 1), (1, 1)],
         [(0, 0)],
         [(0, 0), (0, 1), (1, 1)],
     ]
     for fits in stages:
         model.fix()
+        if fits == "parabola":     # quickplay.py:344-350 -- 500 candidates within +-100 m/s of every RV
+            if parabola_fit:
+                shift_search = physics.shifts(np.linspace(-100, 100, 500))
+                model[0][0].parabola_fit(shift_search, loss, model, dataset, device_op, device_store)
+            continue
         for f in fits:
             model.fit(*f)
         model.display()
