@@ -171,6 +171,14 @@ int jb_plan_fisher(jb_plan *plan, int32_t component, double *f_out, int64_t n_sh
 int jb_plan_grid_search(jb_plan *plan, int32_t component, const double *grid, int64_t n_shift,
                         int64_t n_grid, double *loss_out);
 
+/*
+ * Diagonal of the Hessian of the loss with respect to the shifts of `component`
+ * (quickplay.get_RV_error_2d, jabble/quickplay.py:455-482, which takes jacrev(grad(loss))[key, key]
+ * row by row): h_out[k] = coefficient * sum over the rows of key k and their unmasked pixels of
+ * ivar ((a S')^2 - (y - m) a S'').
+ */
+int jb_plan_curvature(jb_plan *plan, int32_t component, double *h_out, int64_t n_shift);
+
 /* Gradient w.r.t. ALL parameters from the last evaluation (diagnostics / tests).  Entries of
  * parameters that are not in fit mode hold only what the kernel variant of that evaluation formed. */
 int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);

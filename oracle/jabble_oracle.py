@@ -429,6 +429,54 @@ def parabola_fit(p, array1d, loss_grid) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# Hessian-based RV errors                      reference: quickplay.py:405-482
+# --------------------------------------------------------------------------
+
+def rv_curvature(p_shift, which_key, datablock, metablock, model, coefficient=1.0) -> np.ndarray:
+    """quickplay.py:455-477 -- information[k] = sum over the rows of key k of
+    jacrev(grad(loss_row))[k, k]; ONLY the RV ShiftingModel is in fit mode."""
+    xs, ys, yivar = _t(datablock["xs"]), _t(datablock["ys"]), _t(datablock["yivar"])
+    mask = torch.as_tensor(np.asarray(datablock["mask"]).astype(bool))
+    keys = np.asarray(metablock[which_key]).astype(np.int64)
+    info = np.zeros(len(np.asarray(p_shift)))
+    for r in range(xs.shape[0]):
+        p = _t(p_shift).clone().requires_grad_(True)
+        meta = {k: int(v[r]) for k, v in metablock.items()}
+        l = chi_square_row(p, xs[r], ys[r], yivar[r], mask[r], meta, model, coefficient).sum()
+        (g,) = torch.autograd.grad(l, p, create_graph=True)
+        (h,) = torch.autograd.grad(g[keys[r]], p)
+        info[keys[r]] += float(h[keys[r]])
+    return info
+
+
+def rv_curvature_est(p_shift, which_key, datablock, metablock, model, epsilon, coefficient=1.0) -> np.ndarray:
+    """quickplay.py:405-450 -- slope through the origin of the row gradients [key] over 20 common
+    offsets of the whole RV vector in [-epsilon, epsilon], summed by key."""
+    xs, ys, yivar = _t(datablock["xs"]), _t(datablock["ys"]), _t(datablock["yivar"])
+    mask = torch.as_tensor(np.asarray(datablock["mask"]).astype(bool))
+    keys = np.asarray(metablock[which_key]).astype(np.int64)
+    p_space = np.linspace(-epsilon, epsilon, 20)
+    N = len(np.asarray(p_shift))
+    acc = np.zeros((N, 20))
+    for r in range(xs.shape[0]):
+        meta = {k: int(v[r]) for k, v in metablock.items()}
+        for i, e in enumerate(p_space):
+            p = (_t(p_shift) + e).clone().requires_grad_(True)
+            l = chi_square_row(p, xs[r], ys[r], yivar[r], mask[r], meta, model, coefficient).sum()
+            (g,) = torch.autograd.grad(l, p)
+            acc[keys[r], i] += float(g[keys[r]])
+    numerator = acc @ p_space
+    denominator = p_space @ p_space
+    return np.where(np.abs(denominator) > 1e-22 * numerator, numerator / denominator, np.nan)
+
+
+def rv_error_2d(shift_values, information) -> np.ndarray:
+    """quickplay.py:451-453, 479-482 -- 1/sqrt(information) * d velocities/d shift."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return 1.0 / np.sqrt(np.asarray(information)) * dvelocities(shift_values)
+
+
+# --------------------------------------------------------------------------
 # dataset.py:192-237  blockify (host-side layout of the inputs)
 # --------------------------------------------------------------------------
 

@@ -204,6 +204,7 @@ jnp.empty = _zeros
 jnp.ones = _ones
 jnp.arange = _arange
 jnp.where = _where
+jnp.nan = float("nan")
 jnp.polyval = _polyval
 jnp.polyfit = lambda x, y, deg: _arr(np.polyfit(np.asarray(x), np.asarray(y), deg))
 jnp.polyder = lambda p: _arr(np.polyder(np.asarray(p)))
@@ -278,12 +279,29 @@ def _grad(fun, argnums=0):
     assert argnums == 0
 
     def g(p, *args, **kw):
-        pp = _arr(p).detach().clone().as_subclass(torch.Tensor).requires_grad_(True)
+        pt = _arr(p).as_subclass(torch.Tensor)
+        if pt.requires_grad:           # under jacrev: stay on the outer graph, keep the graph of the gradient
+            out = fun(pt.as_subclass(Arr), *args, **kw)
+            (gr,) = torch.autograd.grad(out, pt, create_graph=True)
+            return gr.as_subclass(Arr)
+        pp = pt.detach().clone().requires_grad_(True)
         out = fun(pp.as_subclass(Arr), *args, **kw)
         (gr,) = torch.autograd.grad(out, pp)
         return gr.as_subclass(Arr)
 
     return g
+
+
+def _jacrev(fun, argnums=0):
+    assert argnums == 0
+
+    def j(p, *args, **kw):
+        pp = _arr(p).detach().as_subclass(torch.Tensor)
+        J = torch.autograd.functional.jacobian(
+            lambda q: fun(q.as_subclass(Arr), *args, **kw).as_subclass(torch.Tensor), pp)
+        return J.as_subclass(Arr)
+
+    return j
 
 
 def _jacfwd(fun, argnums=0):
@@ -302,6 +320,7 @@ jax.jit = _jit
 jax.vmap = _vmap
 jax.grad = _grad
 jax.jacfwd = _jacfwd
+jax.jacrev = _jacrev
 jax.device_put = lambda x, device=None: _arr(x)
 jax.devices = lambda kind="cpu": ["cpu:0"]
 jax.device_count = lambda: 1

@@ -227,6 +227,10 @@ def fixture_wobble(pv, name, ragged=False, descending=False, keyed=False):
         g = np.array(npy(sm.p)[:, None] + arr1d[None, :])
         out[tag + "_grid"] = g
         out[tag + "_loss"] = npy(sm.grid_search(g, loss, model, dataset, DEV))
+    # Hessian-based RV errors (quickplay.py:405-482)
+    out["rv_err_2d"] = npy(jabble.quickplay.get_RV_error_2d(model, dataset, loss, [0, 0], DEV))
+    out["rv_err_2d_est"] = npy(jabble.quickplay.get_RV_error_2d_est(model, dataset, loss, [0, 0], DEV))
+    model.fix()
     out["pf_array1d"] = arr1d
     mins = np.argmin(out["gs_loss"], axis=1)
     if np.any((mins > 0) & (mins < len(arr1d) - 1)):     # the reference vmaps over the interior minima: none -> it fails

@@ -81,6 +81,11 @@ def test_golden_wobble(name):
     for tag, leaf in (("gs", model[0][0]), ("gs_tell", model[1][0])):
         L = leaf.grid_search(g[tag + "_grid"], loss, model, data)
         assert rel_err(L, g[tag + "_loss"]) < TOL, tag
+    # Hessian-based RV errors (quickplay.py:405-482); NaN where the curvature is negative
+    assert np.allclose(jabble.quickplay.get_RV_error_2d(model, data, loss, [0, 0]), g["rv_err_2d"],
+                       rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(jabble.quickplay.get_RV_error_2d_est(model, data, loss, [0, 0]), g["rv_err_2d_est"],
+                       rtol=1e-7, atol=0, equal_nan=True)
     if "pf_p" in g:
         model[0][0].parabola_fit(g["pf_array1d"], loss, model, data)
         assert np.allclose(model[0][0].p, g["pf_p"], rtol=0, atol=1e-12)

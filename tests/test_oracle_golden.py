@@ -142,6 +142,12 @@ def test_golden_wobble(name):
         set_fit(model, [leaf])
         L = O.grid_search(g[tag + "_grid"], meta["which_key"], dbd, mbd, model)
         assert rel_err(L, g[tag + "_loss"]) < 1e-11
+    # Hessian-based RV errors (quickplay.py:405-482); NaN where the curvature is negative
+    set_fit(model, [(0, 0)])
+    H = O.rv_curvature(model[0][0].p, meta["which_key"], dbd, mbd, model)
+    assert np.allclose(O.rv_error_2d(model[0][0].p, H), g["rv_err_2d"], rtol=1e-10, atol=0, equal_nan=True)
+    He = O.rv_curvature_est(model[0][0].p, meta["which_key"], dbd, mbd, model, O.shifts(10))
+    assert np.allclose(O.rv_error_2d(model[0][0].p, He), g["rv_err_2d_est"], rtol=1e-8, atol=0, equal_nan=True)
     if "pf_p" in g:
         assert np.allclose(O.parabola_fit(model[0][0].p, g["pf_array1d"], g["gs_loss"]), g["pf_p"], rtol=0, atol=1e-13)
 

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("jb_plan_forward", C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p]),
     ("jb_plan_fisher", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64]),
     ("jb_plan_grad_all", C.c_int, [C.c_void_p, c_f64p, C.c_int64]),
+    ("jb_plan_curvature", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64]),
     ("jb_plan_grid_search", C.c_int, [C.c_void_p, C.c_int32, c_f64p, C.c_int64, C.c_int64, c_f64p]),
     ("jb_batch_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
     ("jb_batch_destroy", None, [C.c_void_p]),

@@ -221,6 +221,72 @@ __global__ void k_grid_search(GridParams a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Diagonal of the Hessian of the chi-square with respect to the shift of one component
+// (quickplay.get_RV_error_2d, jabble/quickplay.py:455-482: jacrev(grad(loss)) [key, key] per row):
+//   d^2/d shift^2 of 0.5 ivar (y - m)^2 = ivar ((a S')^2 - (y - m) a S''),   m = a S(x - shift) + others
+// S' and S'' are the derivatives of the piecewise polynomial (what differentiating the reference's
+// floor / mod arithmetic gives).  One block per row; out[row] = the row's sum.
+template <int PV>
+__global__ void k_row_curvature(GridParams a) {
+    __shared__ double red[kTile];
+    const int64_t r = blockIdx.x;
+    const CompDev& cs = a.comp[a.search];
+    const double st = cs.stretch ? cs.stretch[cs.stretch_key[r]] : 1.0;
+    const double sh = cs.shift[cs.shift_key[r]];
+    double acc = 0.0;
+    bool ok = true;
+    for (int t = 0; t < a.n_tiles; ++t) {
+        const double* rec = a.data + (r * a.n_tiles + t) * kTileDoubles;
+        const int p = threadIdx.x;
+        const int pos = (p % kPixPerLane) * 32 + p / kPixPerLane;
+        const double x = rec[pos], y = rec[kTile + pos], w = rec[2 * kTile + pos];
+        if (w == 0.0) continue;
+        double mo = 0.0;
+        for (int ci = 0; ci < a.n_comp; ++ci) {
+            if (ci == a.search) continue;
+            const CompDev& c = a.comp[ci];
+            const double shift = c.shift ? c.shift[c.shift_key[r]] : 0.0;
+            const double* cc = c.kind == 1 ? c.ctrl + (int64_t)c.ctrl_key[r] * c.n_knots : c.ctrl;
+            double s;
+            if (c.p_val == 3) s = spline_value<3>(c, cc, x, shift, ok);
+            else if (c.p_val == 2) s = spline_value<2>(c, cc, x, shift, ok);
+            else s = spline_value<1>(c, cc, x, shift, ok);
+            if (c.stretch) s *= c.stretch[c.stretch_key[r]];
+            mo += s;
+        }
+        double g; int I;
+        knot_coord<PV>(x, sh, cs.xp0, cs.inv_dx, g, I);
+        const double tt = ((x - sh) - cs.xp0) * cs.inv_dx;
+        const int klo = knot_lo<PV>(I);
+        if (!(tt > -1.0e9 && tt < 1.0e9) || klo < 0 || klo + PV > cs.n_knots - 1) { ok = false; continue; }
+        double cv[PV + 1], wgt[PV + 1], dw[PV > 0 ? PV : 1];
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) cv[k] = __ldg(cs.ctrl + klo + k);
+        Basis<PV>::eval(g, wgt, dw);
+        double S = 0.0, dS = 0.0, d2S = 0.0;
+#pragma unroll
+        for (int k = 0; k <= PV; ++k) S = __fma_rn(cv[k], wgt[k], S);
+#pragma unroll
+        for (int k = 0; k < PV; ++k) dS = __fma_rn(cv[k + 1] - cv[k], dw[k], dS);
+        // second derivative: PV (PV-1) sum_j (c[j+2] - 2 c[j+1] + c[j]) * [(PV-2)!-scaled B-spline of degree PV-2]
+        if (PV == 3) d2S = ((cv[2] - 2.0 * cv[1]) + cv[0]) * (0.5 - g) + ((cv[3] - 2.0 * cv[2]) + cv[1]) * (0.5 + g);
+        else if (PV == 2) d2S = (cv[2] - 2.0 * cv[1]) + cv[0];
+        const double s1 = PV * cs.inv_dx * dS * st;                          // a S'
+        const double s2 = PV * (PV - 1) * cs.inv_dx * cs.inv_dx * d2S * st;  // a S''
+        const double res = y - (mo + st * S);
+        acc += w * (s1 * s1 - res * s2);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kTile / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.out[r] = red[0];
+    if (!ok) atomicOr(a.status, kStatOutOfRange);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused loss + gradient + Fisher.
 //
 // Work item ("task") = one warp, one tile of kTile pixel columns, one group of <= 32 rows.

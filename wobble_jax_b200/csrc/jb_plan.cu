@@ -996,6 +996,45 @@ int jb_plan_grid_search(jb_plan* pl, int32_t component, const double* grid, int6
     return JB_OK;
 }
 
+int jb_plan_curvature(jb_plan* pl, int32_t component, double* h_out, int64_t n_shift) {
+    if (!pl || !h_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (component < 0 || component >= pl->n_comp) return fail(JB_ERR_BAD_ARG, "component %d", component);
+    if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
+    if (!pl->params_set) return fail(JB_ERR_BAD_ARG, "jb_plan_set_params has not been called");
+    int ci = 0;
+    while (pl->ext_of[ci] != component) ++ci;
+    const jb_component_desc& cd = pl->desc[ci];
+    if (cd.kind != JB_COMP_SPLINE) return fail(JB_ERR_UNSUPPORTED, "curvature of the shift of a NormalizationModel component");
+    if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
+    if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
+    JB_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    double* d_out = nullptr;
+    JB_CUDA(cudaMallocAsync(&d_out, (size_t)pl->E * sizeof(double), st));
+    jb::GridParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.data = pl->d_data; gp.n_rows = pl->E; gp.n_tiles = pl->n_tiles; gp.n_comp = pl->n_comp;
+    for (int c = 0; c < pl->n_comp; ++c) gp.comp[c] = pl->comp[c];
+    gp.search = ci; gp.out = d_out; gp.status = pl->d_status;
+    switch (cd.p_val) {
+        case 1: jb::k_row_curvature<1><<<(unsigned)pl->E, jb::kTile, 0, st>>>(gp); break;
+        case 2: jb::k_row_curvature<2><<<(unsigned)pl->E, jb::kTile, 0, st>>>(gp); break;
+        default: jb::k_row_curvature<3><<<(unsigned)pl->E, jb::kTile, 0, st>>>(gp); break;
+    }
+    pl->launches++;
+    JB_CUDA(cudaGetLastError());
+    std::vector<double> rows((size_t)pl->E);
+    JB_CUDA(cudaMemcpyAsync(rows.data(), d_out, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaFreeAsync(d_out, st));
+    int rc = read_status(pl, st, nullptr);     // synchronises the stream
+    if (rc) return rc;
+    std::fill(h_out, h_out + n_shift, 0.0);
+    const std::vector<int>& key = pl->h_shift_key[ci];
+    for (int64_t r = 0; r < pl->E; ++r) h_out[key[r]] += rows[(size_t)r];
+    for (int64_t i = 0; i < n_shift; ++i) h_out[i] *= pl->coef;
+    return JB_OK;
+}
+
 int jb_plan_stream(jb_plan* pl, void** stream_out) {
     if (!pl || !stream_out) return fail(JB_ERR_BAD_ARG, "null argument");
     *stream_out = (void*)pl->stream;

@@ -257,6 +257,13 @@ class Plan:
         _lib.check(self.lib.jb_plan_fisher(self.handle, component, out.ctypes.data_as(_lib.c_f64p), n))
         return out
 
+    def curvature(self, component):
+        """d^2 loss / d shift_k^2 for every shift key of ``component`` (jb_plan_curvature)."""
+        n = self.spec.leaf_of(self.spec.components[component]["shift"]).size
+        out = np.empty(n, dtype=np.float64)
+        _lib.check(self.lib.jb_plan_curvature(self.handle, component, out.ctypes.data_as(_lib.c_f64p), n))
+        return out
+
     def grid_search(self, component, grid):
         """(n_keys, M) losses of the rows of every shift key of ``component`` at M candidate shifts."""
         g = np.ascontiguousarray(grid, dtype=np.float64)
@@ -445,6 +452,24 @@ def evaluate_row(model, p, x, meta):
         if len(p) not in (0, plan.n_fit):
             raise ValueError(f"p has {len(p)} entries, the model has {plan.n_fit} parameters in fit mode")
         return plan.forward(p)[0]
+    finally:
+        plan.close()
+
+
+def shift_curvature(model, shift_model, datablock, metablock, coefficient=1.0, device=0):
+    """Hessian diagonal of the loss w.r.t. a ShiftingModel of the tree (quickplay.get_RV_error_2d)."""
+    spec = TreeSpec(model)
+    comp = None
+    for i, c in enumerate(spec.components):
+        if c["shift"] is shift_model:
+            comp = i
+    if comp is None:
+        raise NotImplementedError("the curvature runs on the CUDA path for the ShiftingModel of an additive component only")
+    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
+                coefficient=coefficient, device=device)
+    try:
+        plan.sync_from_model()
+        return plan.curvature(comp)
     finally:
         plan.close()
 

@@ -92,3 +92,55 @@ def get_RV_error_fisher(model, dataset, device=None, rv_ind=[0, 0]):
         rv_model = rv_model[xx]
     f_info = rv_model.f_info(model, dataset, device)
     return np.sqrt(1 / f_info) * physics.dvelocities(rv_model.p)
+
+
+def _rv_model(model, rv_ind):
+    rv_model = model
+    for ind in rv_ind:
+        rv_model = rv_model[ind]
+    return rv_model
+
+
+def get_RV_error_2d(model, dataset, loss, rv_ind, device=None):
+    """quickplay.py:455-482 -- per-epoch RV error bar from the curvature of the loss,
+    1/sqrt(d^2 loss / d shift_k^2) * dv/d(shift).  The reference takes ``jacrev(grad(loss))`` of every
+    row (an N x N Hessian per row) and keeps [key, key]; here one kernel forms the diagonal
+    analytically (``jb_plan_curvature``).  NaN where the curvature is negative, as in the reference.
+    """
+    from . import engine
+    from . import loss as L
+
+    if not isinstance(loss, L.ChiSquare):
+        raise NotImplementedError("get_RV_error_2d runs on the CUDA path for ChiSquare only")
+    model.fix()
+    model.fit(*rv_ind)
+    rv_model = _rv_model(model, rv_ind)
+    data, meta = dataset.blockify(device)
+    information = engine.shift_curvature(model, rv_model, data, meta, coefficient=loss.coefficient)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.array(1 / np.sqrt(information) * physics.dvelocities(model[0][0].p))
+
+
+def get_RV_error_2d_est(model, dataset, loss, rv_ind, device=None, epsilon=None):
+    """quickplay.py:405-453 -- the same curvature estimated as the slope (least squares through
+    the origin) of the RV gradient over 20 common offsets of all RVs in [-epsilon, epsilon].
+    Every row depends on its own epoch's RV only, so the reference's per-row gradients summed by
+    key are the gradient of the whole loss: 20 fused evaluations.
+    """
+    from . import engine
+
+    epsilon = physics.shifts(10) if epsilon is None else epsilon
+    model.fix()
+    model.fit(*rv_ind)
+    rv_model = _rv_model(model, rv_ind)
+    data, meta = dataset.blockify(device)
+    p_space = np.linspace(-epsilon, epsilon, 20)
+    p0 = np.asarray(model.get_parameters(), dtype=np.float64)
+    obj = engine.Objective(loss, model, data, meta)
+    G = np.stack([obj.gradient(p0 + e) for e in p_space], axis=1)       # (N, 20)
+    numerator = G @ p_space
+    denominator = p_space @ p_space
+    safe = np.abs(denominator) > 1e-22 * numerator
+    information = np.where(safe, numerator / denominator, np.nan)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.array(1 / np.sqrt(information) * physics.dvelocities(model[0][0].p))
