@@ -377,3 +377,22 @@ def test_grid_search_vs_oracle_at_size():
     model[0][0].parabola_fit(wide, loss, model, ch.data)
     model.fix(); model[0][0].fit()
     assert engine.Objective(loss, model, db, mb).value(np.asarray(model.get_parameters())) < before
+
+
+def test_save_rvs(tmp_path):
+    """model.save_rvs (model.py:73-82): velocities, times and the three RV error bars in one file."""
+    from wobble_jax_b200 import store
+    ch = synth.make_chunk(chunk=8, n_epochs=12, n_pix=700, p_val=3, n_lines=12)
+    loss = jabble.loss.ChiSquare()
+    path = str(tmp_path / "rvs.h5")
+    times = np.arange(12.0)
+    jabble.model.save_rvs(path, [0, 0], ch.model, ch.data, loss, times)
+    with store.File(path, "r") as hf:
+        assert set(hf.keys()) == {"rvs", "time", "rv_error_fisher", "rv_error_2d_est", "rv_error_2d_full"}
+        assert np.allclose(hf["rvs"][:], jabble.physics.velocities(ch.model[0][0].p))
+        assert np.array_equal(hf["time"][:], times)
+        ef, e2 = hf["rv_error_fisher"][:], hf["rv_error_2d_full"][:]
+    assert np.all(np.isfinite(ef)) and ef.shape == (12,)
+    # on data drawn from the model the curvature is dominated by the Fisher term
+    ok = np.isfinite(e2)
+    assert ok.sum() >= 10 and np.allclose(e2[ok], ef[ok], rtol=0.2)

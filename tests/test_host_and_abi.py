@@ -100,3 +100,48 @@ def test_blockify_padding_and_keys():
     assert db["xs"].shape == (3, 5) and db["mask"][1, 3:].all() and not db["mask"][0].any()
     assert np.array_equal(mb["index"], [0, 1, 2]) and np.array_equal(mb["times"], [1, 0, 1])
     assert len(db) == 3 and db.ele(1)["xs"].shape == (5,)
+
+
+def test_save_load_round_trip(tmp_path):
+    """jabble.model.save / load and Data.save / load (model.py:35-71, dataset.py:239-277): the tree,
+    every leaf's parameters, the metadata and the group / dataset names of the reference's HDF5 layout
+    (written as the .npz mirror when h5py is not installed)."""
+    import wobble_jax_b200 as jabble
+    from wobble_jax_b200 import store, synth
+
+    ch = synth.make_chunk(chunk=1, n_epochs=5, n_pix=200, p_val=3, n_lines=4)
+    model = ch.model + jabble.quickplay.get_normalization_model(ch.data, 2, 4)
+    model.metadata = {"times": np.arange(5.0), "names": np.array(["a", "b", "c", "d", "e"])}
+    model[0][0].p = model[0][0].p + 1e-6
+    path = str(tmp_path / "model.h5")
+    jabble.model.save(path, model, header={"star": "51 Peg"})
+    with store.File(path, "r") as hf:
+        assert list(hf.keys()) == ["AdditiveModel", "metadata"]
+        top = hf["AdditiveModel"]
+        assert list(top.keys()) == ["CompositeModel_0", "CompositeModel_1", "CompositeModel_2"]
+        assert list(top["CompositeModel_1"].keys()) == ["ShiftingModel_0", "CardinalSplineMixture_0", "StretchingModel_0"]
+        assert set(top["CompositeModel_0"]["CardinalSplineMixture_0"].keys()) == {"p", "xs", "p_val", "alpha"}
+        assert set(top["CompositeModel_2"]["NormalizationModel_0"].keys()) == {"model_CardinalSplineMixture", "p", "which_key", "size"}
+    back = jabble.model.load(path)
+    assert type(back).__name__ == "AdditiveModel" and len(back.models) == 3
+    for i in range(3):
+        for a, b in zip(model[i].models, back[i].models):
+            assert type(a) is type(b) and np.array_equal(a.p, b.p)
+    assert back[1][0].which_key == model[1][0].which_key and back[0][1].p_val == 3
+    assert np.array_equal(back[0][1].xs, model[0][1].xs)
+    assert back[2][1].size == model[2][1].size and np.array_equal(back[2][1].model.xs, model[2][1].model.xs)
+    assert np.array_equal(back.metadata["times"], model.metadata["times"])
+    assert list(back.metadata["names"]) == ["a", "b", "c", "d", "e"]
+    # a model fixed before saving comes back with the same parameter vector order
+    model.fix(); model.fit(0, 0); model.fit(1, 1); back.fix(); back.fit(0, 0); back.fit(1, 1)
+    assert np.array_equal(model.get_parameters(), back.get_parameters())
+
+    ch.data.metadata["times"] = np.arange(5.0)
+    dpath = str(tmp_path / "data.h5")
+    ch.data.save(dpath)
+    d2 = jabble.dataset.Data.load(dpath)
+    assert len(d2) == len(ch.data)
+    for a, b in zip(ch.data.dataframes, d2.dataframes):
+        for k in ("xs", "ys", "yivar", "mask"):
+            assert np.array_equal(getattr(a, k), getattr(b, k))
+    assert np.array_equal(d2.metadata["times"], np.arange(5.0))

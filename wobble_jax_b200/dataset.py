@@ -62,6 +62,46 @@ class Data:
         self.metadata = {}
         self.metakeys = {}
 
+    def save(self, filename):
+        """dataset.py:239-254 -- group ``data`` with one ``dataframe_<i>`` per row, group ``metadata``
+        (HDF5 when h5py is installed, else the .npz mirror of the same tree)."""
+        from . import store
+        with store.File(filename, "w") as hf:
+            group = hf.create_group("data")
+            for i, dataframe in enumerate(self.dataframes):
+                subgroup = group.create_group(f"dataframe_{i}", track_order=True)
+                subgroup.create_dataset("xs", data=dataframe.xs)
+                subgroup.create_dataset("ys", data=dataframe.ys)
+                subgroup.create_dataset("yivar", data=dataframe.yivar)
+                subgroup.create_dataset("mask", data=dataframe.mask)
+            metagroup = hf.create_group("metadata")
+            for key in self.metadata.keys():
+                value = np.asarray(self.metadata[key])
+                if value.dtype.kind in {"U", "S"}:
+                    metagroup.create_dataset(key, data=np.char.encode(value, "utf-8"))
+                else:
+                    metagroup.create_dataset(key, data=value)
+
+    @staticmethod
+    def load(filename):
+        """dataset.py:256-277."""
+        from . import store
+        with store.File(filename, "r") as hf:
+            group = hf["data"]
+            dataframes = []
+            for key in group.keys():
+                if key.startswith("dataframe_"):
+                    dataframes.append(DataFrame(group[key]["xs"][:], group[key]["ys"][:], group[key]["yivar"][:],
+                                                group[key]["mask"][:]))
+            data = Data(dataframes)
+            metagroup = hf["metadata"]
+            for key in metagroup.keys():
+                if store.is_string_dtype(metagroup[key].dtype):
+                    data.metadata[key] = np.array(metagroup[key].asstr()[:], dtype=str)
+                else:
+                    data.metadata[key] = np.array(metagroup[key][:])
+        return data
+
     def __getitem__(self, i):
         return self.dataframes[i]
 

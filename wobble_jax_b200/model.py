@@ -47,6 +47,71 @@ def create_x_grid(xs, vel_padding, resolution):
     return np.linspace(x_min - x_padding, x_max + x_padding, size)
 
 
+def spline_alphas(n):
+    """cardinalspline.py:6-42 -- alphas[j, k] = coefficient of s^j on piece k of the n!-scaled
+    Irwin-Hall B-spline of degree n (s = t + (n+1)/2 in [k, k+1)); stored beside a saved spline.
+    Closed form of the reference's recursion: n! * density of a sum of n+1 uniforms is
+    sum_{i <= k} (-1)^i C(n+1, i) (s - i)^n on piece k."""
+    return np.array([[sum((-1) ** i * math.comb(n + 1, i) * math.comb(n, j) * float(-i) ** (n - j)
+                          for i in range(k + 1)) for k in range(n + 1)] for j in range(n + 1)], dtype=np.float64)
+
+
+def load(filename):
+    """model.py:35-54 -- rebuild a saved model tree (and its metadata)."""
+    from . import store
+    model, metadata = None, {}
+    with store.File(filename, "r") as hf:
+        for key in hf.keys():
+            if key == "metadata":
+                metagroup = hf["metadata"]
+                for mkey in metagroup.keys():
+                    if store.is_string_dtype(metagroup[mkey].dtype):
+                        metadata[mkey] = np.array(metagroup[mkey].asstr()[:], dtype=str)
+                    else:
+                        metadata[mkey] = np.array(metagroup[mkey][:])
+                continue
+            obj_name = key.split("/")[-1].split("_")[0]
+            if obj_name in _SAVED_CLASSES:
+                model = _SAVED_CLASSES[obj_name].load(hf[key])
+    model.metadata = metadata
+    return model
+
+
+def save(filename, model, header={}):
+    """model.py:56-71 -- group <Class> holding the tree, group ``metadata``, attribute
+    ``date_created`` (+ ``header``).  HDF5 when h5py is installed, else the .npz mirror of the same
+    tree (wobble_jax_b200/store.py)."""
+    from datetime import datetime
+    from . import store
+    with store.File(filename, "w") as hf:
+        group = hf.create_group(model.__class__.__name__)
+        model.save(group)
+        hf.attrs["date_created"] = datetime.now().isoformat()
+        for key in header.keys():
+            hf.attrs[key] = header[key]
+        metagroup = hf.create_group("metadata")
+        for key in model.metadata.keys():
+            value = np.asarray(model.metadata[key])
+            if value.dtype.kind in {"U", "S"}:
+                metagroup.create_dataset(key, data=np.char.encode(value, "utf-8"))
+            else:
+                metagroup.create_dataset(key, data=value)
+
+
+def save_rvs(filename, rv_inds, model, dataset, loss, time, device=None):
+    """model.py:73-82 -- RVs, times and the three RV error bars of a fitted model."""
+    from . import quickplay, store
+    with store.File(filename, "w") as hf:
+        rvs_model = model
+        for ind in rv_inds:
+            rvs_model = rvs_model[ind]
+        hf.create_dataset("rvs", data=physics.velocities(rvs_model.p))
+        hf.create_dataset("time", data=np.asarray(time))
+        hf.create_dataset("rv_error_fisher", data=quickplay.get_RV_error_fisher(model, dataset, device, rv_inds))
+        hf.create_dataset("rv_error_2d_est", data=quickplay.get_RV_error_2d_est(model, dataset, loss, rv_inds, device))
+        hf.create_dataset("rv_error_2d_full", data=quickplay.get_RV_error_2d(model, dataset, loss, rv_inds, device))
+
+
 def _as_param(p):
     return np.array(p, dtype=np.float64).reshape(-1)
 
@@ -212,6 +277,25 @@ class ContainerModel(Model):
     def split_p(self, p):
         return [p[self.get_indices(k)] for k in range(len(self._parameters_per_model))]
 
+    def save(self, hf):
+        """model.py:576-583 -- one sub-group <Class>_<n> per child, in order."""
+        iteration = 0
+        for model in self.models:
+            while model.__class__.__name__ + f"_{iteration}" in hf.keys():
+                iteration += 1
+            subgroup = hf.create_group(model.__class__.__name__ + f"_{iteration}", track_order=True)
+            model.save(subgroup)
+
+    @staticmethod
+    def load(hf):
+        """model.py:585-593."""
+        models = []
+        for group_key in hf.keys():
+            obj_name = hf[group_key].name.split("/")[-1].split("_")[0]
+            models.append(_SAVED_CLASSES[obj_name].load(hf[group_key]))
+        obj_name = hf.name.split("/")[-1].split("_")[0]
+        return _SAVED_CLASSES[obj_name](models)
+
     def fit(self, i=None, *args):
         """model.py:512-532 -- ``fit()`` everything, or ``fit(i, j, ...)`` one sub-model by path."""
         if i is None:
@@ -328,6 +412,20 @@ class EpochSpecificModel(Model):
         datablock, metablock = data.blockify(device)
         return engine.fisher_information(model, self, datablock, metablock)
 
+    def save(self, group):
+        """model.py:903-905."""
+        from . import store
+        group.create_dataset("p", data=np.asarray(self.p))
+        store.string_dataset(group, "which_key", self.which_key)
+
+    @staticmethod
+    def load(hf):
+        """model.py:907-909."""
+        obj_name = hf.name.split("/")[-1].split("_")[0]
+        which_key = hf["which_key"][()]
+        which_key = which_key.decode("utf-8") if isinstance(which_key, bytes) else str(which_key)
+        return _SAVED_CLASSES[obj_name](p=np.array(hf["p"]), which_key=which_key)
+
     def grid_search(self, grid, loss, model, data, device=None, epoches=None):
         """model.py:738-786 -- the loss of the rows of every epoch at each of M candidate values of
         this model's parameter: ``grid`` is (N epochs, M), the result too.  Like the reference this
@@ -405,6 +503,18 @@ class CardinalSplineMixture(Model):
         else:
             self.p = np.zeros(self.xs.shape)
 
+    def save(self, group):
+        """model.py:1030-1034."""
+        group.create_dataset("p", data=np.asarray(self.p))
+        group.create_dataset("xs", data=np.asarray(self.xs))
+        group.create_dataset("p_val", data=self.p_val)
+        group.create_dataset("alpha", data=spline_alphas(self.p_val))
+
+    @staticmethod
+    def load(group):
+        """model.py:1036-1037."""
+        return CardinalSplineMixture(p=np.array(group["p"]), p_val=int(group["p_val"][()]), xs=np.array(group["xs"]))
+
 
 class NormalizationModel(Model):
     """model.py:1110-1157 -- f(p, x, i) = inner(p.reshape(size, K)[meta[which_key]], x): a private
@@ -417,3 +527,28 @@ class NormalizationModel(Model):
         self.which_key = which_key
         self.model_p_size = len(model.p)
         self.size = int(size)
+
+    def save(self, group):
+        """model.py:1145-1150."""
+        from . import store
+        modelgroup = group.create_group("model_" + self.model.__class__.__name__)
+        self.model.save(modelgroup)
+        group.create_dataset("p", data=np.asarray(self.p))
+        store.string_dataset(group, "which_key", self.which_key)
+        group.create_dataset("size", data=self.size)
+
+    @staticmethod
+    def load(group):
+        """model.py:1152-1157."""
+        model = None
+        for key in group.keys():
+            if key.startswith("model_"):
+                model = _SAVED_CLASSES[key.split("_")[-1]].load(group[key])
+        which_key = group["which_key"][()]
+        which_key = which_key.decode("utf-8") if isinstance(which_key, bytes) else str(which_key)
+        return NormalizationModel(p=np.array(group["p"][:]), model=model, which_key=which_key, size=int(group["size"][()]))
+
+
+#: classes ``load`` may rebuild (the reference evals the class name found in the file, model.py:50-52)
+_SAVED_CLASSES = {c.__name__: c for c in (ContainerModel, CompositeModel, AdditiveModel, ShiftingModel, StretchingModel,
+                                          CardinalSplineMixture, NormalizationModel)}
