@@ -197,6 +197,14 @@ int jb_batch_create(jb_plan *const *plans, int32_t n_plans, jb_batch **out);
 void jb_batch_destroy(jb_batch *batch);
 int jb_batch_bind(jb_batch *batch, const double *const *d_p_fit, double *const *d_out);
 int jb_batch_eval_device(jb_batch *batch, void *stream);
+/*
+ * The same evaluation with HOST buffers (what scipy's func / fprime hand over for every chunk of a
+ * Pool of fits): p_fit_host[i] is the fit vector of plan i, out_host[i] receives [loss, gradient]
+ * (1 + n_fit doubles).  One host->device copy of all fit vectors from pinned staging, one launch per
+ * kernel for all plans, one device->host copy, one synchronisation; errors as jb_plan_eval.
+ * Replaces any binding made by jb_batch_bind.
+ */
+int jb_batch_eval_host(jb_batch *batch, const double *const *p_fit_host, double *const *out_host);
 int jb_batch_check(jb_batch *batch);
 int64_t jb_batch_launches(const jb_batch *batch);
 

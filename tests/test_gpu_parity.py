@@ -196,6 +196,33 @@ def test_epoch_sharding_sums_to_the_unsharded_result():
     _check_grad(model, gs, g, tol=1e-12)
 
 
+def test_batch_eval_host_equals_per_plan_results():
+    """jb_batch_eval_host: host buffers in and out for several chunks, bit-identical to jb_plan_eval."""
+    chunks = [synth.make_chunk(chunk=c, n_epochs=18 + 5 * c, n_pix=600 + 128 * c, p_val=3, n_lines=10) for c in range(3)]
+    plans, ps, refs = [], [], []
+    for ch in chunks:
+        model = synth.fit_all(ch.model)
+        db, mb = ch.data.blockify()
+        plan = engine.build_plan(model, db, mb)
+        p = np.asarray(model.get_parameters())
+        refs.append(plan.eval(p))
+        plans.append(plan); ps.append(p)
+    batch = engine.Batch(plans)
+    for rep in range(2):
+        outs = batch.eval_host(ps)
+        for (f, g), o in zip(refs, outs):
+            assert o[0] == f and np.array_equal(o[1:], g)
+    # an out-of-range shift in one chunk is reported, not swallowed
+    bad = [p.copy() for p in ps]
+    bad[1][0] += 1.0
+    with pytest.raises(ValueError, match="outside the knot grid"):
+        batch.eval_host(bad)
+    assert batch.eval_host(ps)[2][0] == refs[2][0]
+    batch.close()
+    for pl in plans:
+        pl.close()
+
+
 def test_batched_launch_equals_per_plan_results():
     """jb_batch: several chunks evaluated by one launch per kernel give bit-identical results to the
     per-plan path (same kernels, same fixed summation order)."""

@@ -1062,4 +1062,10 @@ __global__ void k_finish(const ReduceParams* __restrict__ arr, const int* __rest
     }
 }
 
+// status words of the plans of a batch -> one flat array (one copy instead of one per plan)
+__global__ void k_gather_status(int* const* __restrict__ ptrs, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[2 * i] = ptrs[i][0]; out[2 * i + 1] = ptrs[i][1]; }
+}
+
 }  // namespace jb

@@ -135,6 +135,11 @@ struct jb_batch {
     int total[6] = {0, 0, 0, 0, 0, 0};
     bool scatter = true, dirty = true;
     int64_t launches = 0;
+    // jb_batch_eval_host: flat device buffers + pinned staging for all plans
+    double *d_flat_p = nullptr, *d_flat_out = nullptr, *h_flat_p = nullptr, *h_flat_out = nullptr;
+    std::vector<int64_t> off_p, off_out;
+    int** d_stat_ptrs = nullptr; int* d_stat_flat = nullptr; int* h_stat_flat = nullptr;
+    bool host_bound = false;
 };
 
 namespace {
@@ -1093,6 +1098,13 @@ void jb_batch_destroy(jb_batch* b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (void* q : b->dev) cudaFree(q);
+    if (b->d_flat_p) cudaFree(b->d_flat_p);
+    if (b->d_flat_out) cudaFree(b->d_flat_out);
+    if (b->h_flat_p) cudaFreeHost(b->h_flat_p);
+    if (b->h_flat_out) cudaFreeHost(b->h_flat_out);
+    if (b->d_stat_ptrs) cudaFree(b->d_stat_ptrs);
+    if (b->d_stat_flat) cudaFree(b->d_stat_flat);
+    if (b->h_stat_flat) cudaFreeHost(b->h_stat_flat);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -1103,6 +1115,61 @@ int jb_batch_bind(jb_batch* b, const double* const* d_p_fit, double* const* d_ou
     if (d_p_fit) b->p_fit.assign(d_p_fit, d_p_fit + b->plans.size());
     b->out.assign(d_out, d_out + b->plans.size());
     b->dirty = true;
+    b->host_bound = false;
+    return JB_OK;
+}
+
+int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* const* out_host) {
+    if (!b || !p_fit_host || !out_host) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t n = b->plans.size();
+    if (!b->host_bound) {     // (re)build the flat buffers for the plans' current fit sizes
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        if (b->d_flat_p) { cudaFree(b->d_flat_p); cudaFree(b->d_flat_out); cudaFreeHost(b->h_flat_p); cudaFreeHost(b->h_flat_out); }
+        if (!b->d_stat_ptrs) {
+            std::vector<int*> ptrs;
+            for (jb_plan* pl : b->plans) ptrs.push_back(pl->d_status);
+            JB_CUDA(cudaMalloc(&b->d_stat_ptrs, n * sizeof(int*)));
+            JB_CUDA(cudaMemcpy(b->d_stat_ptrs, ptrs.data(), n * sizeof(int*), cudaMemcpyHostToDevice));
+            JB_CUDA(cudaMalloc(&b->d_stat_flat, 2 * n * sizeof(int)));
+            JB_CUDA(cudaMallocHost(&b->h_stat_flat, 2 * n * sizeof(int)));
+        }
+        b->off_p.assign(n + 1, 0); b->off_out.assign(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) {
+            b->off_p[i + 1] = b->off_p[i] + b->plans[i]->n_fit;
+            b->off_out[i + 1] = b->off_out[i] + b->plans[i]->n_fit + 1;
+        }
+        const size_t np = (size_t)std::max<int64_t>(b->off_p[n], 1), no = (size_t)b->off_out[n];
+        JB_CUDA(cudaMalloc(&b->d_flat_p, np * sizeof(double)));
+        JB_CUDA(cudaMalloc(&b->d_flat_out, no * sizeof(double)));
+        JB_CUDA(cudaMallocHost(&b->h_flat_p, np * sizeof(double)));
+        JB_CUDA(cudaMallocHost(&b->h_flat_out, no * sizeof(double)));
+        b->p_fit.resize(n); b->out.resize(n);
+        for (size_t i = 0; i < n; ++i) { b->p_fit[i] = b->d_flat_p + b->off_p[i]; b->out[i] = b->d_flat_out + b->off_out[i]; }
+        b->dirty = true;
+        b->host_bound = true;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit) { b->host_bound = false; return fail(JB_ERR_BAD_ARG, "plan %zu changed its fit vector: call again", i); }
+        if (b->plans[i]->n_fit && !p_fit_host[i]) return fail(JB_ERR_BAD_ARG, "null p_fit for plan %zu", i);
+        if (b->plans[i]->n_fit) memcpy(b->h_flat_p + b->off_p[i], p_fit_host[i], b->plans[i]->n_fit * sizeof(double));
+    }
+    cudaStream_t st = b->stream;
+    if (b->off_p[n]) JB_CUDA(cudaMemcpyAsync(b->d_flat_p, b->h_flat_p, b->off_p[n] * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = jb_batch_eval_device(b, st);
+    if (rc) return rc;
+    JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
+    JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; ++i)
+        if (b->h_stat_flat[2 * i] || b->h_stat_flat[2 * i + 1])
+            if ((rc = read_status(b->plans[i], st, nullptr))) return rc;
+    for (size_t i = 0; i < n; ++i) {
+        if (!out_host[i]) return fail(JB_ERR_BAD_ARG, "null output for plan %zu", i);
+        memcpy(out_host[i], b->h_flat_out + b->off_out[i], (b->plans[i]->n_fit + 1) * sizeof(double));
+        if (!std::isfinite(out_host[i][0])) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
+    }
     return JB_OK;
 }
 

@@ -329,6 +329,18 @@ class Batch:
     def eval_device(self, stream_ptr=0):
         _lib.check(self.lib.jb_batch_eval_device(self.handle, C.c_void_p(stream_ptr)))
 
+    def eval_host(self, p_list, out_list=None):
+        """All chunks with HOST buffers: ``p_list[i]`` the fit vector of plan i; returns (or fills)
+        ``out_list[i]`` = [loss, gradient] arrays.  One H2D copy, one launch per kernel, one D2H copy."""
+        n = len(self.plans)
+        ps = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1) for p in p_list]
+        if out_list is None:
+            out_list = [np.empty(p.size + 1, dtype=np.float64) for p in ps]
+        pf = (C.c_void_p * n)(*[p.ctypes.data for p in ps])
+        po = (C.c_void_p * n)(*[o.ctypes.data for o in out_list])
+        _lib.check(self.lib.jb_batch_eval_host(self.handle, pf, po))
+        return out_list
+
     def check(self):
         _lib.check(self.lib.jb_batch_check(self.handle))
 
