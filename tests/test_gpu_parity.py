@@ -355,6 +355,23 @@ def test_specialised_kernel_agrees_with_general_kernel_for_every_fit_state(p_val
     plan.close(); ref.close()
 
 
+@pytest.mark.parametrize("G", [1, 3, 7])
+def test_specialised_kernel_rows_per_group_and_ragged_rows(G):
+    """k_fused2 with short row groups (odd counts: the up / down row pairs end on an up row), ragged
+    and descending rows (lanes without a weighted pixel keep their windows) against the oracle."""
+    ch = synth.make_chunk(chunk=9, n_epochs=23, n_pix=1000, p_val=3, n_lines=12, ragged=True, descending=True)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    plan = engine.build_plan(model, db, mb, rows_per_group=G)
+    val, grad = plan.eval(p)
+    assert plan.info()["fused_variant"] >= 0 and plan.info()["rows_per_group"] == G
+    oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    plan.close()
+
+
 def test_stellar_only_specialised_kernel():
     g = load_golden("stellar.npz")
     data = dataset_from_golden(g)

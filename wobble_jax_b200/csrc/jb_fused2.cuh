@@ -159,6 +159,11 @@ __device__ __forceinline__ bool win_step(Win2<PV>& w, int In, uint32_t abase, ui
     return step;
 }
 
+#ifdef JB_F2_SAMEGRID   // tuning builds: every component on the knot grid of component 0
+#define JB_F2_GRID(c) 0
+#else
+#define JB_F2_GRID(c) (c)
+#endif
 template <int NC> struct RowConst { double sh[NC], st[NC], xp0[NC], inv_dx[NC]; };
 
 // One pixel, windows already in place.  SLIDE = 0: the windows did not move (first pixel of a row);
@@ -237,7 +242,7 @@ __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc,
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             int In;
-            knot_coord<PV>(x, rc.sh[c], rc.xp0[c], rc.inv_dx[c], g[c], In);
+            knot_coord<PV>(x, rc.sh[c], rc.xp0[JB_F2_GRID(c)], rc.inv_dx[JB_F2_GRID(c)], g[c], In);
             In = live ? In : win[c].I;
             win_turn<PV>(win[c], In, abase[c], cdelta, resync, lane, first_row);
             step[c] = false;
@@ -255,7 +260,7 @@ __device__ __forceinline__ void f2_row(const double* px, const RowConst<NC>& rc,
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             int In;
-            knot_coord<PV>(x, rc.sh[c], rc.xp0[c], rc.inv_dx[c], g[c], In);
+            knot_coord<PV>(x, rc.sh[c], rc.xp0[JB_F2_GRID(c)], rc.inv_dx[JB_F2_GRID(c)], g[c], In);
             In = live ? In : win[c].I;
             step[c] = win_step<PV, DIR>(win[c], In, abase[c], cdelta);
         }
