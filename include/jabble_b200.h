@@ -203,8 +203,13 @@ int jb_batch_eval_device(jb_batch *batch, void *stream);
  * (1 + n_fit doubles).  One host->device copy of all fit vectors from pinned staging, one launch per
  * kernel for all plans, one device->host copy, one synchronisation; errors as jb_plan_eval.
  * Replaces any binding made by jb_batch_bind.
+ * A window overflow (JB_ERR_WINDOW) is reported, not retried as jb_plan_eval does.
+ * _begin / _end split the call so that a caller can keep several batches (each on its own stream)
+ * in flight: begin copies and enqueues and returns; end waits and hands the results over.
  */
 int jb_batch_eval_host(jb_batch *batch, const double *const *p_fit_host, double *const *out_host);
+int jb_batch_eval_host_begin(jb_batch *batch, const double *const *p_fit_host);
+int jb_batch_eval_host_end(jb_batch *batch, double *const *out_host);
 int jb_batch_check(jb_batch *batch);
 int64_t jb_batch_launches(const jb_batch *batch);
 

@@ -139,7 +139,7 @@ struct jb_batch {
     double *d_flat_p = nullptr, *d_flat_out = nullptr, *h_flat_p = nullptr, *h_flat_out = nullptr;
     std::vector<int64_t> off_p, off_out;
     int** d_stat_ptrs = nullptr; int* d_stat_flat = nullptr; int* h_stat_flat = nullptr;
-    bool host_bound = false;
+    bool host_bound = false, host_pending = false;
 };
 
 namespace {
@@ -1119,10 +1119,15 @@ int jb_batch_bind(jb_batch* b, const double* const* d_p_fit, double* const* d_ou
     return JB_OK;
 }
 
-int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* const* out_host) {
-    if (!b || !p_fit_host || !out_host) return fail(JB_ERR_BAD_ARG, "null argument");
+int jb_batch_eval_device(jb_batch* b, void* stream);
+
+int jb_batch_eval_host_begin(jb_batch* b, const double* const* p_fit_host) {
+    if (!b || !p_fit_host) return fail(JB_ERR_BAD_ARG, "null argument");
     JB_CUDA(cudaSetDevice(b->device));
     const size_t n = b->plans.size();
+    if (b->host_bound)
+        for (size_t i = 0; i < n; ++i)
+            if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit) b->host_bound = false;   // a fit vector changed size
     if (!b->host_bound) {     // (re)build the flat buffers for the plans' current fit sizes
         JB_CUDA(cudaStreamSynchronize(b->stream));
         if (b->d_flat_p) { cudaFree(b->d_flat_p); cudaFree(b->d_flat_out); cudaFreeHost(b->h_flat_p); cudaFreeHost(b->h_flat_out); }
@@ -1150,7 +1155,6 @@ int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* con
         b->host_bound = true;
     }
     for (size_t i = 0; i < n; ++i) {
-        if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit) { b->host_bound = false; return fail(JB_ERR_BAD_ARG, "plan %zu changed its fit vector: call again", i); }
         if (b->plans[i]->n_fit && !p_fit_host[i]) return fail(JB_ERR_BAD_ARG, "null p_fit for plan %zu", i);
         if (b->plans[i]->n_fit) memcpy(b->h_flat_p + b->off_p[i], p_fit_host[i], b->plans[i]->n_fit * sizeof(double));
     }
@@ -1161,7 +1165,19 @@ int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* con
     JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
     jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
     JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    b->host_pending = true;
+    return JB_OK;
+}
+
+int jb_batch_eval_host_end(jb_batch* b, double* const* out_host) {
+    if (!b || !out_host) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (!b->host_pending) return fail(JB_ERR_BAD_ARG, "jb_batch_eval_host_begin has not been called");
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t n = b->plans.size();
+    cudaStream_t st = b->stream;
     JB_CUDA(cudaStreamSynchronize(st));
+    b->host_pending = false;
+    int rc;
     for (size_t i = 0; i < n; ++i)
         if (b->h_stat_flat[2 * i] || b->h_stat_flat[2 * i + 1])
             if ((rc = read_status(b->plans[i], st, nullptr))) return rc;
@@ -1171,6 +1187,13 @@ int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* con
         if (!std::isfinite(out_host[i][0])) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
     }
     return JB_OK;
+}
+
+int jb_batch_eval_host(jb_batch* b, const double* const* p_fit_host, double* const* out_host) {
+    if (!out_host) return fail(JB_ERR_BAD_ARG, "null argument");
+    int rc = jb_batch_eval_host_begin(b, p_fit_host);
+    if (rc) return rc;
+    return jb_batch_eval_host_end(b, out_host);
 }
 
 int jb_batch_eval_device(jb_batch* b, void* stream) {

@@ -341,6 +341,22 @@ class Batch:
         _lib.check(self.lib.jb_batch_eval_host(self.handle, pf, po))
         return out_list
 
+    def eval_host_begin(self, p_list):
+        """Copy the fit vectors and enqueue the evaluation on the batch's own stream; returns at once."""
+        n = len(self.plans)
+        self._ps = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1) for p in p_list]
+        pf = (C.c_void_p * n)(*[p.ctypes.data for p in self._ps])
+        _lib.check(self.lib.jb_batch_eval_host_begin(self.handle, pf))
+
+    def eval_host_end(self, out_list=None):
+        """Wait for ``eval_host_begin`` and return (or fill) the [loss, gradient] arrays."""
+        n = len(self.plans)
+        if out_list is None:
+            out_list = [np.empty(p.size + 1, dtype=np.float64) for p in self._ps]
+        po = (C.c_void_p * n)(*[o.ctypes.data for o in out_list])
+        _lib.check(self.lib.jb_batch_eval_host_end(self.handle, po))
+        return out_list
+
     def check(self):
         _lib.check(self.lib.jb_batch_check(self.handle))
 
