@@ -203,7 +203,8 @@ int jb_batch_eval_device(jb_batch *batch, void *stream);
  * (1 + n_fit doubles).  One host->device copy of all fit vectors from pinned staging, one launch per
  * kernel for all plans, one device->host copy, one synchronisation; errors as jb_plan_eval.
  * Replaces any binding made by jb_batch_bind.
- * A window overflow (JB_ERR_WINDOW) is reported, not retried as jb_plan_eval does.
+ * A knot-window overflow is handled as in jb_plan_eval (re-sort, wider window, shorter row groups,
+ * the batch evaluated again).
  * _begin / _end split the call so that a caller can keep several batches (each on its own stream)
  * in flight: begin copies and enqueues and returns; end waits and hands the results over.
  */

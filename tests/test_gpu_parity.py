@@ -440,3 +440,25 @@ def test_save_rvs(tmp_path):
     # on data drawn from the model the curvature is dominated by the Fisher term
     ok = np.isfinite(e2)
     assert ok.sum() >= 10 and np.allclose(e2[ok], ef[ok], rtol=0.2)
+
+
+def test_optimize_many_equals_optimize_chunk_by_chunk():
+    """optimize_many: every chunk keeps its own scipy L-BFGS-B, evaluations batched on the GPU -- the
+    same iterates, results and parameters as Model.optimize run one chunk after the other."""
+    import copy
+    chunks = [synth.make_chunk(chunk=c, n_epochs=16 + 4 * c, n_pix=640 + 128 * c, p_val=3, n_lines=10) for c in range(3)]
+    loss = jabble.loss.ChiSquare()
+    opts = {"maxiter": 6 }
+    solo, many = [copy.deepcopy(ch.model) for ch in chunks], [copy.deepcopy(ch.model) for ch in chunks]
+    ref = []
+    for m, ch, it in zip(solo, chunks, (6, 3, 9)):
+        m.fix(); m.fit(0, 1); m.fit(1, 1)
+        ref.append(m.optimize(loss, ch.data, options={"maxiter": 6}))
+    for m in many:
+        m.fix(); m.fit(0, 1); m.fit(1, 1)
+    res = jabble.model.optimize_many(many, loss, [ch.data for ch in chunks], options=opts)
+    for (x0, f0, d0), (x1, f1, d1), a, b in zip(ref, res, solo, many):
+        assert np.array_equal(x0, x1) and f0 == f1
+        assert d0["funcalls"] == d1["funcalls"] and d0["nit"] == d1["nit"]
+        assert np.array_equal(np.asarray(a.get_parameters()), np.asarray(b.get_parameters()))
+        assert len(b.results) == 1 and b.results["funcalls"][0] == d1["funcalls"]

@@ -1175,12 +1175,37 @@ int jb_batch_eval_host_end(jb_batch* b, double* const* out_host) {
     JB_CUDA(cudaSetDevice(b->device));
     const size_t n = b->plans.size();
     cudaStream_t st = b->stream;
-    JB_CUDA(cudaStreamSynchronize(st));
     b->host_pending = false;
     int rc;
-    for (size_t i = 0; i < n; ++i)
-        if (b->h_stat_flat[2 * i] || b->h_stat_flat[2 * i + 1])
-            if ((rc = read_status(b->plans[i], st, nullptr))) return rc;
+    for (int attempt = 0;; ++attempt) {
+        JB_CUDA(cudaStreamSynchronize(st));
+        // plans whose knot window overflowed get what jb_plan_eval gives them (eval_sync): first a
+        // re-sort of their rows with the current parameters, then a wider window / shorter row
+        // groups; then the whole batch is evaluated again (the fit vectors are still on the device)
+        bool again = false;
+        for (size_t i = 0; i < n; ++i) {
+            if (!b->h_stat_flat[2 * i] && !b->h_stat_flat[2 * i + 1]) continue;
+            jb_plan* pl = b->plans[i];
+            bool window = false;
+            rc = read_status(pl, st, &window);
+            if (rc == JB_OK) continue;
+            if (!window || attempt >= 12) return rc;
+            JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
+            if (attempt > 0) {
+                if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
+                else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
+                else return rc;
+                if ((rc = alloc_scratch(pl))) return rc;
+            }
+            if ((rc = resort_rows(pl))) return rc;
+            again = true;
+        }
+        if (!again) break;
+        if ((rc = jb_batch_eval_device(b, st))) return rc;
+        JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
+        jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
+        JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     for (size_t i = 0; i < n; ++i) {
         if (!out_host[i]) return fail(JB_ERR_BAD_ARG, "null output for plan %zu", i);
         memcpy(out_host[i], b->h_flat_out + b->off_out[i], (b->plans[i]->n_fit + 1) * sizeof(double));

@@ -411,6 +411,7 @@ class Objective:
         self._p = None
         self._f = None
         self._g = None
+        self._data_eval = self.plan.eval      # (loss, gradient) of the data term; LockstepEvaluator reroutes it
 
     @classmethod
     def cached(cls, loss, model, datablock, metablock):
@@ -433,7 +434,7 @@ class Objective:
     def _eval(self, p):
         p = np.asarray(p, dtype=np.float64).reshape(-1)
         if self._p is None or p.shape != self._p.shape or not np.array_equal(p, self._p):
-            self._f, self._g = self.plan.eval(p)
+            self._f, self._g = self._data_eval(p)
             for r in self.regs:
                 # the reference's loss_all evaluates a regulariser inside the vmap over rows
                 # (loss.py:61-74): its value and gradient are counted once per row of the block
@@ -449,6 +450,69 @@ class Objective:
 
     def gradient(self, p):
         return self._eval(p)[1].copy()
+
+
+class LockstepEvaluator:
+    """Evaluations of several independent objectives (chunks / orders, each driven by its own scipy
+    L-BFGS-B in its own thread) sent to the GPU together: a thread that asks for (loss, gradient)
+    waits until every thread still optimising has asked, then ONE batched launch per kernel serves
+    them all (``jb_batch_eval_host``).  Every optimiser sees exactly the numbers ``jb_plan_eval``
+    would have given it (the batched kernels are bit-identical to the per-plan ones), so the
+    iterates are those of ``Model.optimize`` run chunk by chunk.
+    """
+
+    def __init__(self, objectives):
+        import threading
+        self.objs = list(objectives)
+        self.cv = threading.Condition()
+        self.pending, self.results = {}, {}
+        self.active = set(range(len(self.objs)))
+        self.batches = {}
+        self.n_flushes = 0
+        for i, o in enumerate(self.objs):
+            o._data_eval = (lambda p, i=i: self.request(i, p))
+
+    def request(self, i, p):
+        with self.cv:
+            self.pending[i] = np.ascontiguousarray(p, dtype=np.float64).reshape(-1).copy()
+            if set(self.pending) >= self.active:
+                self._flush()
+            else:
+                self.cv.wait_for(lambda: i in self.results)
+            res = self.results.pop(i)
+        if isinstance(res, BaseException):
+            raise res
+        return res
+
+    def done(self, i):
+        """Thread i has stopped optimising: the others no longer wait for it."""
+        with self.cv:
+            self.active.discard(i)
+            if self.pending and set(self.pending) >= self.active:
+                self._flush()
+
+    def _flush(self):          # called with the lock held, by the thread whose request completed the set
+        idx = tuple(sorted(self.pending))
+        try:
+            batch = self.batches.get(idx)
+            if batch is None:
+                batch = self.batches[idx] = Batch([self.objs[i].plan for i in idx])
+            outs = batch.eval_host([self.pending[i] for i in idx])
+            for i, o in zip(idx, outs):
+                self.results[i] = (float(o[0]), o[1:].copy())
+        except BaseException as exc:       # every waiting optimiser gets the error, nobody is left waiting
+            for i in idx:
+                self.results[i] = exc
+        self.pending.clear()
+        self.n_flushes += 1
+        self.cv.notify_all()
+
+    def close(self):
+        for b in self.batches.values():
+            b.close()
+        self.batches.clear()
+        for o in self.objs:
+            o._data_eval = o.plan.eval
 
 
 def _meta_value(meta, key):

@@ -112,6 +112,57 @@ def save_rvs(filename, rv_inds, model, dataset, loss, time, device=None):
         hf.create_dataset("rv_error_2d_full", data=quickplay.get_RV_error_2d(model, dataset, loss, rv_inds, device))
 
 
+def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_size=None, options={}):
+    """``Model.optimize`` (model.py:195-238) for many independent models at once -- the echelle orders /
+    chunks the reference fits in a ``multiprocessing.Pool(jax.device_count())``
+    (notebooks/02-51peg.py:66-78).  Every model keeps its own scipy L-BFGS-B (same ``options``, same
+    iterates, same ``results`` record and ``_unpack`` as ``optimize``); the optimisers run in threads
+    and their evaluations go to the GPU together, one launch per kernel for all models that are still
+    iterating (``engine.LockstepEvaluator``).  ``loss`` is one loss for all models (copied per model:
+    regularisers keep per-model index sets) or one per model.  Returns the list of ``(x, f, d)``.
+    """
+    import threading
+    from . import engine
+
+    models, datas = list(models), list(datas)
+    losses = list(loss) if isinstance(loss, (list, tuple)) else [copy.deepcopy(loss) for _ in models]
+    if not (len(models) == len(datas) == len(losses)):
+        raise ValueError("optimize_many: one dataset (and one loss) per model")
+    objectives, x0s = [], []
+    for model, data, ls in zip(models, datas, losses):
+        datablock, metablock = data.blockify(device_store)
+        ls.ready_indices(model)
+        x0s.append(np.asarray(model.get_parameters(), dtype=np.float64))
+        objectives.append(engine.Objective(ls, model, datablock, metablock))
+    evaluator = engine.LockstepEvaluator(objectives)
+    out, errors = [None] * len(models), [None] * len(models)
+
+    def run(i):
+        try:
+            out[i] = scipy.optimize.fmin_l_bfgs_b(func=objectives[i].value, fprime=objectives[i].gradient,
+                                                  x0=x0s[i], **options)
+        except BaseException as exc:
+            errors[i] = exc
+        finally:
+            evaluator.done(i)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(models))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    evaluator.close()
+    for exc in errors:
+        if exc is not None:
+            raise exc
+    for model, ls, (x, f, d) in zip(models, losses, out):
+        model.results = np.append(
+            model.results,
+            np.array([(d["task"], d["funcalls"], d["nit"], d["warnflag"], f, repr(ls))], dtype=_RESULTS_DTYPE), axis=0)
+        model._unpack(np.asarray(x, dtype=np.float64))
+    return out
+
+
 def _as_param(p):
     return np.array(p, dtype=np.float64).reshape(-1)
 
