@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=64, help="chunks per GPU")
+    ap.add_argument("--float32", action="store_true",
+                    help="the float32 tier (JB_PLAN_FLOAT32: float records, k_fused32; 13 B/pixel) instead of float64")
     ap.add_argument("--epochs", type=int, default=2000)
     ap.add_argument("--pixels", type=int, default=4096)
     ap.add_argument("--p-val", type=int, default=3)
@@ -159,7 +161,7 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.float32 else "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,7 +205,7 @@ def run_b200(args, rank, world, local_rank):
             spec = engine.TreeSpec(model)
             plan = engine.Plan(spec, ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
                                ch.datablock["mask"], ch.metablock, device=local_rank,
-                               rows_per_group=args.rows_per_group)
+                               rows_per_group=args.rows_per_group, float32=args.float32)
             plan.sync_from_model()
             plans.append(plan)
             p_host.append(np.asarray(model.get_parameters()).copy())
@@ -312,14 +314,14 @@ def run_b200(args, rank, world, local_rank):
     achieved = bytes_per_launch / (fused_batch_avg_ms * 1e-3) / 1e9
     traffic = None     # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and (args.epochs, args.pixels, args.p_val) == (2000, 4096, 3):
+    if os.path.exists(tpath) and (args.epochs, args.pixels, args.p_val) == (2000, 4096, 3) and not args.float32:
         with open(tpath) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.float32 else "f64", "data": "synthetic",
         "config": workload_config(args),
         "evals_per_s": args.chunks * world * args.steps / (dev_ms * 1e-3),
         "hbm_frac_whole_step": (info["algorithmic_bytes"] * args.chunks * args.steps / (dev_ms * 1e-3) / 1e9) / peak,
@@ -332,7 +334,8 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic * args.chunks if traffic else None,
-                     "kernel": f"k_fused2<2,{args.p_val},{info['fused_variant']}>" if info["fused_variant"] >= 0 else f"k_fused<2,{args.p_val}>",
+                     "kernel": (f"k_fused32<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 64 else
+                                f"k_fused2<2,{args.p_val},{info['fused_variant']}>" if info["fused_variant"] >= 0 else f"k_fused<2,{args.p_val}>"),
                      "kernel_ms": fused_batch_avg_ms, "launches_timed": int(fused_batch_n),
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": peak_src,
                      "timed": "CUDA events around the kernel on the launch stream inside the timed steps (one launch = all chunks of the GPU)",

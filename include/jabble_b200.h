@@ -95,6 +95,11 @@ typedef struct {
 } jb_plan_desc;
 
 /* jb_plan_desc.flags */
+#define JB_PLAN_FLOAT32 2          /* float32 tier: the data block is kept as float (x relative to its
+                                      tile, 13 B/pixel) and the fused kernel computes in float; results
+                                      within 1e-5 of the float64 ones.  Needs smooth tiles and no
+                                      NormalizationModel component; jb_plan_grid_search and _curvature are
+                                      float64 paths and not available on such a plan                  */
 #define JB_PLAN_GENERAL_KERNEL 1   /* always evaluate with the general fused kernel (k_fused), never the
                                       specialised one (k_fused2): cross-checks and A/B measurements   */
 

@@ -462,3 +462,49 @@ def test_optimize_many_equals_optimize_chunk_by_chunk():
         assert d0["funcalls"] == d1["funcalls"] and d0["nit"] == d1["nit"]
         assert np.array_equal(np.asarray(a.get_parameters()), np.asarray(b.get_parameters()))
         assert len(b.results) == 1 and b.results["funcalls"][0] == d1["funcalls"]
+
+
+TOL32 = 1e-5       # BASELINE.json north_star: relative 1e-5 in float32
+
+
+@pytest.mark.parametrize("p_val,E,P,kw", [
+    (3, 40, 1500, {}),
+    (2, 33, 700, {"ragged": True}),
+    (1, 17, 300, {"descending": True}),
+    (3, 70, 4096, {"ragged": True, "descending": True}),
+])
+def test_float32_tier_vs_oracle(p_val, E, P, kw):
+    """JB_PLAN_FLOAT32: float records (x relative to its tile) and float arithmetic in k_fused32, against
+    the float64 oracle, and against the float64 kernel for the Fisher information."""
+    ch = synth.make_chunk(chunk=3, n_epochs=E, n_pix=P, p_val=p_val, n_lines=20, **kw)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    plan = engine.build_plan(model, db, mb, float32=True)
+    val, grad = plan.eval(p)
+    assert plan.info()["fused_variant"] >= 64
+    assert plan.info()["algorithmic_bytes"] < 14 * E * P + 10 ** 6
+    oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+    assert abs(val - oval) <= TOL32 * abs(oval)
+    _check_grad(model, grad, ograd, tol=TOL32)
+    val2, grad2 = plan.eval(p)
+    assert val2 == val and np.array_equal(grad, grad2)          # still no atomics: bit-reproducible
+    ref = engine.build_plan(model, db, mb)
+    assert rel_err(plan.fisher(0), ref.fisher(0)) < TOL32
+    with pytest.raises(ValueError, match="float64 path"):
+        plan.grid_search(0, model[0][0].p[:, None] + np.zeros((1, 3)))
+    plan.close(); ref.close()
+
+
+def test_float32_tier_limits():
+    """What the float32 tier does not take is refused loudly: tiles with pixels a knot or more apart
+    (the golden fixtures), and there is no silent float64 fallback."""
+    g = load_golden("wobble_p3.npz")
+    data = dataset_from_golden(g)
+    model, meta = wobble_from_golden(g)
+    db, mb, dbd, mbd = _blocks(data)
+    set_fit(model, [(0, 0), (0, 1), (1, 1)])
+    plan = engine.build_plan(model, db, mb, float32=True)
+    with pytest.raises(ValueError, match="float32 plan needs smooth tiles"):
+        plan.eval(np.asarray(model.get_parameters()))
+    plan.close()

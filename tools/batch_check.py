@@ -3,11 +3,12 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wobble_jax_b200 import engine, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+f32 = len(sys.argv) > 2 and sys.argv[2] == "f32"
 plans, ps, refs = [], [], []
 for c in range(n):
     ch = synth.make_chunk(c, as_block=True)
     model = synth.fit_all(ch.model)
-    plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"], ch.datablock["mask"], ch.metablock)
+    plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"], ch.datablock["mask"], ch.metablock, float32=f32)
     plan.sync_from_model()
     p = np.asarray(model.get_parameters()); ps.append(p); plans.append(plan)
     refs.append(plan.eval(p))

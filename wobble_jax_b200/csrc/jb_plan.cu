@@ -18,6 +18,7 @@
 #include "../../include/jabble_b200.h"
 #include "jb_kernels.cuh"
 #include "jb_fused2.cuh"
+#include "jb_fused32.cuh"
 
 namespace {
 
@@ -86,6 +87,8 @@ struct jb_plan {
     bool force_der = false;    // jb_plan_fisher: derivative sums whatever the fit flags say
     bool f2_ok = true;         // every tile suits k_fused2: live lanes smooth, lanes sharing a window copy never on one knot
     bool general_only = false; // JB_PLAN_GENERAL_KERNEL
+    bool f32 = false;          // JB_PLAN_FLOAT32: float records, k_fused32
+    float* d_data32 = nullptr; // tile-interleaved x_rel | y | ivar as floats (f32 plans only)
     bool force_v1 = false;     // a batch whose plans disagree on the kernel variant falls back to k_fused
     int variant = -1;          // fused kernel of this plan: -1 k_fused (general), else the FL flags of k_fused2
     int64_t* d_fit_map = nullptr;
@@ -230,6 +233,8 @@ enum { K_SCATTER = 0, K_PREPARE, K_FUSED, K_STAGE1, K_STAGE2, K_FINISH, K_COUNT 
 
 int check_supported_for_eval(const jb_plan* pl) {
     if (!pl->has_data) return fail(JB_ERR_BAD_ARG, "plan was created without ys/yivar (forward only)");
+    if (pl->f32 && (pl->has_norm || pl->n_glob > 2 || !pl->f2_ok))
+        return fail(JB_ERR_UNSUPPORTED, "a float32 plan needs smooth tiles (consecutive pixels less than a knot apart) and no NormalizationModel component");
     if (pl->n_glob < 1 || pl->n_glob > 2)
         return fail(JB_ERR_UNSUPPORTED, "%d CardinalSplineMixture components (the fused kernel takes 1 or 2)", pl->n_glob);
     if (pl->n_comp - pl->n_glob > 1) return fail(JB_ERR_UNSUPPORTED, "more than one NormalizationModel component");
@@ -250,12 +255,15 @@ int check_supported_for_eval(const jb_plan* pl) {
 // the environment keeps the general kernel (A/B measurements).
 int plan_variant(const jb_plan* pl) {
     static const bool env_v1 = getenv("JB_FUSED_V1") != nullptr;
-    if (env_v1 || pl->general_only || pl->force_v1 || !pl->f2_ok || pl->has_norm || pl->n_glob > 2) return -1;
+    if ((env_v1 && !pl->f32) || pl->general_only || pl->force_v1 || !pl->f2_ok || pl->has_norm || pl->n_glob > 2) return -1;
     int fl = 0;
     for (int c = 0; c < pl->n_glob; ++c) {
         if (pl->desc[c].shift_offset >= 0 && (pl->fit_shift[c] || pl->force_der)) fl |= 1 << c;
         if (pl->desc[c].stretch_offset >= 0) fl |= 4 << c;
     }
+    // float32 tier (bit 6): cubic splines get the kernel of their fit state, the other degrees one
+    // kernel per shape that forms every sum
+    if (pl->f32) return 64 | (pl->desc[0].p_val == 3 ? fl : (pl->n_glob == 1 ? 5 : 15));
     return fl;
 }
 
@@ -269,7 +277,8 @@ int refresh_pack(jb_plan* pl) {
     k.sc.p_fit = pl->d_pfit; k.sc.fit_map = pl->d_fit_map; k.sc.params = pl->d_params; k.sc.n_fit = pl->n_fit;
     k.pr.row_perm = pl->d_row_perm; k.pr.grouprec = pl->d_grouprec; k.pr.n_rows = pl->E; k.pr.n_comp = pl->n_comp;
     jb::FusedParams& fp = k.fu;
-    fp.data = pl->d_data; fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
+    fp.data = pl->f32 ? reinterpret_cast<const double*>(pl->d_data32) : pl->d_data;
+    fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
     fp.n_rows = pl->E; fp.n_tiles = pl->n_tiles;
     fp.rows_per_group = pl->G; fp.n_groups = pl->n_groups; fp.n_tasks = pl->n_tasks; fp.wincap = pl->wincap;
     fp.n_comp = pl->n_glob;
@@ -311,9 +320,10 @@ int refresh_pack(jb_plan* pl) {
             for (int q = 0; q < 3; ++q) rp.rq[c][q] = c * jb::kRowQ + q;
         if (pl->has_norm) { rp.rq[pl->n_glob][0] = pl->n_glob * jb::kRowQ; rp.rq[pl->n_glob][1] = pl->n_glob * jb::kRowQ + 1; }
     } else {
-        NQ = jb::f2_pad(jb::f2_nsums(pl->n_glob, pl->variant));
+        const int fl = pl->variant & 15;       // bit 6 marks the float32 tier
+        NQ = jb::f2_pad(jb::f2_nsums(pl->n_glob, fl));
         for (int c = 0; c < pl->n_glob; ++c)
-            for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, pl->variant, c, q);
+            for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, fl, c, q);
     }
     rp.nq = NQ;
     rp.nb_ctrl = pl->n_groups * pl->n_glob;
@@ -377,8 +387,36 @@ int launch_fused2_t(const LaunchSet& L, cudaStream_t st) {
     return JB_OK;
 }
 
+template <int NC, int PV, int FL>
+int launch_fused32_t(const LaunchSet& L, cudaStream_t st) {
+    const size_t smem = (size_t)jb::kWarpsPerBlock * jb::fused32_warp_smem<NC>(L.wincap);
+    JB_CUDA(cudaFuncSetAttribute(jb::k_fused32<NC, PV, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jb::k_fused32<NC, PV, FL><<<(unsigned)L.total[K_FUSED], jb::kWarpsPerBlock * 32, smem, st>>>(L.fu, L.off[K_FUSED], L.n);
+    JB_CUDA(cudaGetLastError());
+    return JB_OK;
+}
+
+template <int NC, int PV>
+int launch_fused32_f(const LaunchSet& L, cudaStream_t st) {
+    if constexpr (PV != 3) return launch_fused32_t<NC, PV, (NC == 1 ? 5 : 15)>(L, st);
+    else {
+#define JB_F32(f) case f: return launch_fused32_t<NC, PV, f>(L, st);
+        if constexpr (NC == 1) {
+            switch (L.variant & 15) { JB_F32(0) JB_F32(1) JB_F32(4) JB_F32(5) }
+        } else {
+            switch (L.variant & 15) {
+                JB_F32(0) JB_F32(1) JB_F32(2) JB_F32(3) JB_F32(4) JB_F32(5) JB_F32(6) JB_F32(7)
+                JB_F32(8) JB_F32(9) JB_F32(10) JB_F32(11) JB_F32(12) JB_F32(13) JB_F32(14) JB_F32(15)
+            }
+        }
+#undef JB_F32
+        return fail(JB_ERR_UNSUPPORTED, "no k_fused32 for flags %d", L.variant & 15);
+    }
+}
+
 template <int NC, int PV>
 int launch_fused2_f(const LaunchSet& L, cudaStream_t st) {
+    if (L.variant & 64) return launch_fused32_f<NC, PV>(L, st);
 #define JB_F2(f) case f: return launch_fused2_t<NC, PV, f>(L, st);
 #ifdef JB_F2_FAST_BUILD   // kernel-tuning builds: only the benchmark's variant
     if constexpr (NC == 2 && PV == 3) { switch (L.variant) { JB_F2(9) } }
@@ -584,6 +622,8 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->has_data = d->ys != nullptr;
     pl->coef = d->coefficient;
     pl->general_only = (d->flags & JB_PLAN_GENERAL_KERNEL) != 0;
+    pl->f32 = (d->flags & JB_PLAN_FLOAT32) != 0;
+    if (pl->f32 && (pl->general_only || !d->ys)) return fail(JB_ERR_BAD_ARG, "a float32 plan needs ys / yivar and cannot ask for the general kernel");
     pl->n_comp = d->n_components;
     // store the components globals first, the per-key (normalisation) ones last
     std::vector<jb_component_desc> comps;
@@ -720,7 +760,37 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
         if ((rc = dev_alloc(pl, &rec, (size_t)E * sizeof(jb::RowRec<2, 1>)))) return rc;
         pl->d_grouprec = rec;
     }
-    if ((rc = dev_upload(pl, &pl->d_data, hdata))) return rc;
+    if (pl->f32) {
+        // float records: (x - x_ref) / dx, x_ref = the first x of the (row, tile) -- TileInfo.xmin, what
+        // the kernel adds back in double -- split into a knot count (a byte) and a fraction (a float),
+        // then y and ivar; same lane interleave
+        for (int c = 1; c < pl->n_glob; ++c)
+            if (comps[c].dx != comps[0].dx) return fail(JB_ERR_UNSUPPORTED, "a float32 plan needs one knot spacing for all spline components");
+        const double inv_dx0 = 1.0 / comps[0].dx;
+        std::vector<unsigned char> h32((size_t)E * NT * jb::kTileBytes32, 0);
+        for (int64_t r = 0; r < E; ++r)
+            for (int t = 0; t < NT; ++t) {
+                const size_t ti = (size_t)r * NT + t;
+                const double* rec = hdata.data() + ti * jb::kTileDoubles;
+                float* out = reinterpret_cast<float*>(h32.data() + ti * jb::kTileBytes32);
+                unsigned char* kout = h32.data() + ti * jb::kTileBytes32 + jb::kTileFloats * 4;
+                for (int q = 0; q < jb::kTile; ++q) {
+                    double off = std::isfinite(txmin[ti]) ? (rec[q] - txmin[ti]) * inv_dx0 : 0.0;
+                    if (!(off >= 0.0)) off = 0.0;
+                    if (off > 255.0) return fail(JB_ERR_UNSUPPORTED, "a float32 plan needs tiles narrower than 255 knots");
+                    const double k = std::floor(off);
+                    kout[q] = (unsigned char)k;
+                    out[q] = (float)(off - k);
+                    out[jb::kTile + q] = (float)rec[jb::kTile + q];
+                    out[2 * jb::kTile + q] = (float)rec[2 * jb::kTile + q];
+                }
+            }
+        {
+            unsigned char* dptr = nullptr;
+            if ((rc = dev_upload(pl, &dptr, h32))) return rc;
+            pl->d_data32 = reinterpret_cast<float*>(dptr);
+        }
+    } else if ((rc = dev_upload(pl, &pl->d_data, hdata))) return rc;
     if ((rc = dev_upload(pl, &pl->d_x, hx))) return rc;
     if ((rc = dev_upload(pl, &pl->d_row_rev, pl->h_row_rev))) return rc;
     std::vector<int> perm(E);
@@ -823,7 +893,7 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     int64_t knots = 0;
     for (int c = 0; c < pl->n_comp; ++c)
         knots += pl->desc[c].kind == JB_COMP_SPLINE ? pl->desc[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys;
-    info->algorithmic_bytes = pl->E * pl->P * 25 + 2 * knots * 8 + pl->E * 7 * 8;
+    info->algorithmic_bytes = pl->E * pl->P * (pl->f32 ? 13 : 25) + 2 * knots * 8 + pl->E * 7 * 8;
     info->kernel_launches = pl->launches; info->evaluations = pl->evaluations;
     info->serial_rows = pl->serial_rows;
     info->tiles_smooth = pl->tiles_kind[0]; info->tiles_general = pl->tiles_kind[1];
@@ -963,6 +1033,7 @@ int jb_plan_grid_search(jb_plan* pl, int32_t component, const double* grid, int6
     int ci = 0;
     while (pl->ext_of[ci] != component) ++ci;
     const jb_component_desc& cd = pl->desc[ci];
+    if (pl->f32) return fail(JB_ERR_UNSUPPORTED, "grid search is a float64 path: not available on a float32 plan");
     if (cd.kind != JB_COMP_SPLINE) return fail(JB_ERR_UNSUPPORTED, "grid search over the shift of a NormalizationModel component");
     if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
     if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
@@ -1009,6 +1080,7 @@ int jb_plan_curvature(jb_plan* pl, int32_t component, double* h_out, int64_t n_s
     int ci = 0;
     while (pl->ext_of[ci] != component) ++ci;
     const jb_component_desc& cd = pl->desc[ci];
+    if (pl->f32) return fail(JB_ERR_UNSUPPORTED, "the curvature is a float64 path: not available on a float32 plan");
     if (cd.kind != JB_COMP_SPLINE) return fail(JB_ERR_UNSUPPORTED, "curvature of the shift of a NormalizationModel component");
     if (cd.shift_offset < 0) return fail(JB_ERR_BAD_ARG, "component %d has no ShiftingModel", component);
     if (n_shift != cd.n_shift) return fail(JB_ERR_BAD_ARG, "n_shift %lld, component has %lld", (long long)n_shift, (long long)cd.n_shift);
@@ -1078,6 +1150,7 @@ int jb_batch_create(jb_plan* const* plans, int32_t n, jb_batch** out) {
         int rc = check_supported_for_eval(pl);
         if (rc) return rc;
         if (pl->device != p0->device) return fail(JB_ERR_BAD_ARG, "plans of a batch must live on one device");
+        if (pl->f32 != p0->f32) return fail(JB_ERR_UNSUPPORTED, "float32 and float64 plans cannot share a batch");
         if (pl->n_glob != p0->n_glob || pl->has_norm != p0->has_norm || pl->desc[0].p_val != p0->desc[0].p_val ||
             (pl->has_norm && pl->desc[pl->n_glob].p_val != p0->desc[p0->n_glob].p_val))
             return fail(JB_ERR_UNSUPPORTED, "plans of a batch must share the model shape (components, spline degree)");
