@@ -508,3 +508,23 @@ def test_float32_tier_limits():
     with pytest.raises(ValueError, match="float32 plan needs smooth tiles"):
         plan.eval(np.asarray(model.get_parameters()))
     plan.close()
+
+
+def test_train_norm_sigma_clips_outliers():
+    """quickplay.train_norm (quickplay.py:238-285): fit the normalisation, mask what sticks out."""
+    ch = synth.make_chunk(chunk=10, n_epochs=8, n_pix=1024, p_val=3, n_lines=12)
+    rng = np.random.default_rng(5)
+    spikes = []
+    for r in range(len(ch.data)):
+        idx = rng.choice(1024, size=3, replace=False)
+        ch.data[r].ys[idx] += 1.5           # cosmic rays
+        spikes.append(idx)
+    before = sum(int(f.mask.sum()) for f in ch.data.dataframes)
+    model = ch.model + jabble.quickplay.get_normalization_model(ch.data, 2, 4)
+    jabble.quickplay.train_norm(model, ch.data, jabble.loss.ChiSquare(), maxiter=2, options={"maxiter": 8},
+                                nsigma=[6.0, 6.0])
+    for r, idx in enumerate(spikes):
+        assert ch.data[r].mask[idx].all()
+    after = sum(int(f.mask.sum()) for f in ch.data.dataframes)
+    assert before + 24 <= after < before + 24 + 0.05 * 8 * 1024       # the spikes, and little else
+    assert len(model.results) == 2

@@ -85,6 +85,39 @@ def train_cycle(model, dataset, loss, device_store=None, device_op=None, batch_s
     return model
 
 
+def train_norm(model, dataset, loss, device_store=None, device_op=None, batch_size=None,
+               nsigma=[0.5, 2], maxiter=3, options={"maxiter": 64}, norm_model_index=[2, 1]):
+    """quickplay.py:238-285 -- fit the normalisation model with sigma clipping: optimise it, then
+    mask every pixel whose residual lies below -nsigma[0] or above nsigma[1] times the row's
+    sqrt(median(resid^2)); ``maxiter`` rounds.  The reference evaluates the model row by row; here one
+    forward launch gives every row's model values (``jb_plan_forward``), the clipping is the same.
+    """
+    from . import engine
+
+    for _ in range(maxiter):
+        model.fix()
+        model.fit(*norm_model_index)
+        res1 = model.optimize(loss, dataset, device_store, device_op, batch_size, options=options)
+        print(res1)
+        model.fix()
+        datablock, metablock = dataset.blockify(device_op)
+        plan = engine.build_plan(model, datablock, metablock)
+        try:
+            fwd = plan.forward()
+        finally:
+            plan.close()
+        for data_epoch in range(len(dataset)):
+            frame = dataset[data_epoch]
+            mask = np.asarray(frame.mask, dtype=bool)
+            n = len(frame.xs)
+            with np.errstate(invalid="ignore"):
+                resid = np.asarray(frame.ys, dtype=np.float64) - fwd[data_epoch, :n]
+                sigma = np.sqrt(np.nanmedian(resid ** 2))
+                m_new = (resid < -nsigma[0] * sigma) | (resid > nsigma[1] * sigma)
+            frame.mask = mask | m_new[:len(mask)]
+    return model
+
+
 def get_RV_error_fisher(model, dataset, device=None, rv_ind=[0, 0]):
     """quickplay.py:382-403 -- per-epoch RV error bar sqrt(1/F) * dv/d(shift), in m/s."""
     rv_model = model
