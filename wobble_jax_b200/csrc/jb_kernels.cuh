@@ -3,9 +3,13 @@
 //   k_scatter_params   p_fit -> params_all[fit_map]
 //   k_prepare_rows     per-row shift/stretch records in sorted-row order
 //   k_forward          model(p, x, meta) per pixel                       (Model.__call__)
-//   k_fused<NC,PV>     warp->knot, basis weights, gather, residual, chi-square, adjoints of the
+//   k_fused<NC,PV,PVN> warp->knot, basis weights, gather, residual, chi-square, adjoints of the
 //                      control points (deterministic, no float atomics), of shift/stretch, and the
-//                      per-row Fisher sums -- ONE pass over x, y, ivar, mask
+//                      per-row Fisher sums -- ONE pass over x, y, ivar, mask.  The general kernel:
+//                      any pixel spacing, NormalizationModel component.  Smooth plans run on
+//                      k_fused2 (jb_fused2.cuh), their float32 tier on k_fused32 (jb_fused32.cuh)
+//   k_grid_search<PV>  chi-square of every row at M candidate shifts    (EpochSpecificModel.grid_search)
+//   k_row_curvature<PV> d^2 chi-square / d shift^2 per row              (quickplay.get_RV_error_2d)
 //   k_reduce_stage1/2  fixed-order reduction of the per-task partial windows and per-row sums
 //   k_finish           loss, gather of the fit-mode gradient
 #pragma once

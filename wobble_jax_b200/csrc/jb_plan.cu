@@ -3,7 +3,9 @@
 // A plan owns: the data block in HBM (canonicalised: every row ascending in x, padded to a
 // multiple of the 128-pixel warp tile), the flat parameter vector, the fit map, the scratch for
 // per-task partials, one CUDA stream.  An evaluation is six launches on that stream:
-//   k_scatter_params -> k_prepare_rows -> k_fused -> k_reduce_stage1 -> k_reduce_stage2 -> k_finish
+//   k_scatter_params -> k_prepare_rows -> k_fused2 | k_fused32 | k_fused -> k_reduce_stage1 ->
+//   k_reduce_stage2 -> k_finish
+// (plan_variant picks the fused kernel from the plan's tiles, components, fit state and flags).
 #include <algorithm>
 #include <climits>
 #include <cmath>
