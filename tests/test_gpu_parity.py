@@ -70,6 +70,11 @@ def test_golden_wobble(name):
     assert rel_err(F, g["f_info"]) < TOL
     assert rel_err(jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0, 0]), g["rv_err"]) < TOL
     assert rel_err(model[1][0].f_info(model, data), g["f_info_tell"]) < TOL
+    # per-pixel loss array (quickplay.get_loss_array): its sum is loss_all
+    set_fit(model, [(0, 0), (0, 1), (1, 1)])
+    p_all = np.asarray(model.get_parameters())
+    la = jabble.quickplay.get_loss_array(model, db, mb, loss)
+    assert la.shape == db["xs"].shape and abs(la.sum() - loss.loss_all(p_all, db, mb, model, None, 3)) <= 1e-11 * la.sum()
     # coefficient (LossFunc.__mul__)
     set_fit(model, [(0, 0), (1, 1)])
     loss2 = jabble.loss.ChiSquare() * 0.37

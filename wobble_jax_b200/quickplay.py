@@ -177,3 +177,24 @@ def get_RV_error_2d_est(model, dataset, loss, rv_ind, device=None, epsilon=None)
     information = np.where(safe, numerator / denominator, np.nan)
     with np.errstate(invalid="ignore", divide="ignore"):
         return np.array(1 / np.sqrt(information) * physics.dvelocities(model[0][0].p))
+
+
+def get_loss_array(model, datablock, metablock, loss, device=None):
+    """quickplay.py:484-491 -- the per-pixel loss of every row, (E, P): for ChiSquare
+    coefficient * where(~mask, 0.5 * yivar * (ys - model)^2, 0) (loss.py:164-173), from one forward
+    launch instead of a Python loop over rows."""
+    from . import engine
+    from . import loss as L
+
+    if not isinstance(loss, L.ChiSquare):
+        raise NotImplementedError("get_loss_array runs on the CUDA path for ChiSquare only")
+    loss.ready_indices(model)
+    plan = engine.build_plan(model, datablock, metablock)
+    try:
+        fwd = plan.forward(np.asarray(model.get_parameters(), dtype=np.float64))
+    finally:
+        plan.close()
+    mask = np.asarray(datablock["mask"], dtype=bool)
+    with np.errstate(invalid="ignore"):
+        arr = 0.5 * np.asarray(datablock["yivar"]) * (np.asarray(datablock["ys"]) - fwd) ** 2
+    return loss.coefficient * np.where(~mask, arr, 0.0)
