@@ -39,6 +39,7 @@ constexpr int kMaxGroup = 32;     // rows per group: lane i keeps the parameters
 // status bits written by kernels into plan->d_status[0]
 constexpr int kStatOutOfRange = 1;
 constexpr int kStatWindow = 2;
+constexpr int kStatBounds = 4;      // raised only by JB_DEBUG_BOUNDS builds: a window address left its class copy
 
 struct CompDev {
     int kind;                 // jb_comp_kind

@@ -76,7 +76,18 @@ struct Win2 {
     double a[PV + 1];   // adjoint sums of those knots
     int I;              // interval the window sits on
     uint32_t pa;        // shared-memory address of the class copy's entry for knot klo
+#ifdef JB_DEBUG_BOUNDS  // self-check builds (compute-sanitizer is not available on the GPU pool): the
+    uint32_t dbg_lo, dbg_hi;   // first / last legal value of pa; violations raise kStatWindow
+    int* dbg_status;
+#endif
 };
+
+template <int PV>
+__device__ __forceinline__ void win_check(const Win2<PV>& w, uint32_t pa) {
+#ifdef JB_DEBUG_BOUNDS
+    if (pa < w.dbg_lo || pa > w.dbg_hi) atomicOr(w.dbg_status, kStatBounds);
+#endif
+}
 
 // predicated shared-memory helpers (no branch, no memory clobber: the windows are only touched
 // through these between the __syncwarp()s that fence the prologue and the epilogue)
@@ -131,6 +142,7 @@ __device__ __forceinline__ void win_turn(Win2<PV>& w, int In, uint32_t abase, ui
     for (int k = PV; k > 0; --k) w.a[k] = sd ? w.a[k - 1] : w.a[k];
     w.a[0] = sd ? 0.0 : w.a[0];
     const uint32_t pa = abase + 8u * (uint32_t)In;
+    win_check<PV>(w, pa);
     const int iold = resync ? In + 1 : w.I;      // after sitting out (and at the first row): always re-read
 #pragma unroll
     for (int k = 0; k <= PV; ++k) lds_if_ne(w.c[k], pa + cdelta + 8u * k, In, iold);
@@ -143,6 +155,7 @@ __device__ __forceinline__ void win_turn(Win2<PV>& w, int In, uint32_t abase, ui
 template <int PV, int DIR>
 __device__ __forceinline__ bool win_step(Win2<PV>& w, int In, uint32_t abase, uint32_t cdelta) {
     const uint32_t pa = abase + 8u * (uint32_t)In;
+    win_check<PV>(w, pa);
     const bool step = In != w.I;
     const double rv = DIR > 0 ? w.a[0] : w.a[PV];
     if (DIR > 0) {
@@ -460,6 +473,9 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
         asm volatile("" : "+r"(abase[c]));   // one register, not base + offset
         win[c].I = lo[c] - KOFF;             // a valid (empty) window until the first pixel moves it
         win[c].pa = A;
+#ifdef JB_DEBUG_BOUNDS
+        win[c].dbg_lo = A; win[c].dbg_hi = A + 8u * (uint32_t)(W - PV - 1); win[c].dbg_status = a.status;
+#endif
 #pragma unroll
         for (int k = 0; k <= PV; ++k) { win[c].a[k] = 0.0; win[c].c[k] = 0.0; }
         rc.xp0[c] = a.comp[c].xp0; rc.inv_dx[c] = a.comp[c].inv_dx;

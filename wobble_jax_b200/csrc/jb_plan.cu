@@ -524,6 +524,8 @@ int read_status(jb_plan* pl, cudaStream_t st, bool* window) {
     pl->serial_rows = pl->h_status[1];
     if (window) *window = false;
     if (bits || pl->h_status[1]) JB_CUDA(cudaMemsetAsync(pl->d_status, 0, 2 * sizeof(int), st));
+    if (bits & jb::kStatBounds)
+        return fail(JB_ERR_CUDA, "JB_DEBUG_BOUNDS: a window address left its shared-memory copy (kernel bug)");
     if (bits & jb::kStatOutOfRange)
         return fail(JB_ERR_OUT_OF_RANGE, "an unmasked warped pixel lies outside the knot grid of a spline component");
     if (bits & jb::kStatWindow) {
