@@ -450,6 +450,12 @@ class Objective:
     def value(self, p):
         return self._eval(p)[0]
 
+    def value_and_gradient(self, p):
+        """(f, g) in one call: what scipy's ``fmin_l_bfgs_b(func, x0)`` takes when ``fprime`` is None --
+        one Python callback per evaluation instead of two (same numbers, same iterates)."""
+        f, g = self._eval(p)
+        return f, g.copy()
+
     def gradient(self, p):
         return self._eval(p)[1].copy()
 

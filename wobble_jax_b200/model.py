@@ -139,8 +139,7 @@ def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_
 
     def run(i):
         try:
-            out[i] = scipy.optimize.fmin_l_bfgs_b(func=objectives[i].value, fprime=objectives[i].gradient,
-                                                  x0=x0s[i], **options)
+            out[i] = scipy.optimize.fmin_l_bfgs_b(func=objectives[i].value_and_gradient, x0=x0s[i], **options)
         except BaseException as exc:
             errors[i] = exc
         finally:
@@ -211,8 +210,9 @@ class Model:
         loss.ready_indices(self)
         x0 = np.asarray(self.get_parameters(), dtype=np.float64)
         objective = engine.Objective(loss, self, datablock, metablock)
-        x, f, d = scipy.optimize.fmin_l_bfgs_b(
-            func=objective.value, fprime=objective.gradient, x0=x0, **options)
+        # func returns (loss, gradient): the pair the reference hands scipy as func / fprime
+        # (model.py:226-229), from one fused evaluation and one callback
+        x, f, d = scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)
         self.results = np.append(
             self.results,
             np.array([(d["task"], d["funcalls"], d["nit"], d["warnflag"], f, repr(loss))],
