@@ -202,6 +202,10 @@ int jb_batch_create(jb_plan *const *plans, int32_t n_plans, jb_batch **out);
 void jb_batch_destroy(jb_batch *batch);
 int jb_batch_bind(jb_batch *batch, const double *const *d_p_fit, double *const *d_out);
 int jb_batch_eval_device(jb_batch *batch, void *stream);
+/* The same, then waits and handles knot-window overflows as jb_plan_eval does (re-sort, wider window,
+ * shorter row groups, evaluate again); out-of-range pixels are reported.  For device-side drivers
+ * before they start iterating. */
+int jb_batch_eval_device_checked(jb_batch *batch, void *stream);
 /*
  * The same evaluation with HOST buffers (what scipy's func / fprime hand over for every chunk of a
  * Pool of fits): p_fit_host[i] is the fit vector of plan i, out_host[i] receives [loss, gradient]
@@ -216,6 +220,11 @@ int jb_batch_eval_device(jb_batch *batch, void *stream);
 int jb_batch_eval_host(jb_batch *batch, const double *const *p_fit_host, double *const *out_host);
 int jb_batch_eval_host_begin(jb_batch *batch, const double *const *p_fit_host);
 int jb_batch_eval_host_end(jb_batch *batch, double *const *out_host);
+/* enable != 0: a plan whose trial point puts an unmasked pixel outside a knot grid does not fail the
+ * batched host call; its loss comes back NaN (gradient undefined) and the caller decides -- an
+ * optimiser's line search treats it as a rejected step (the reference's clamped gather, model.py:985,
+ * gives a large finite loss there). */
+int jb_batch_soft_range(jb_batch *batch, int enable);
 int jb_batch_check(jb_batch *batch);
 int64_t jb_batch_launches(const jb_batch *batch);
 

@@ -533,3 +533,28 @@ def test_train_norm_sigma_clips_outliers():
     after = sum(int(f.mask.sum()) for f in ch.data.dataframes)
     assert before + 24 <= after < before + 24 + 0.05 * 8 * 1024       # the spikes, and little else
     assert len(model.results) == 2
+
+
+def test_rv_fit_survives_line_search_excursions_and_train_cycle_runs():
+    """With the RVs in fit mode scipy's first L-BFGS step has unit length (metres per second would be
+    fine; log-wavelength shifts are 1e-4): the trial point leaves the knot grid.  The reference's
+    clamped gather returns a large finite loss there and scipy shortens the step; so must we."""
+    ch = synth.make_chunk(chunk=11, n_epochs=20, n_pix=768, p_val=3, n_lines=12)
+    model = ch.model
+    loss = jabble.loss.ChiSquare()
+    model.fix(); model.fit(0, 0)
+    db, mb = ch.data.blockify()
+    p0 = np.asarray(model.get_parameters())
+    f0 = loss.loss_all(p0, db, mb, model, None, None)
+    x, f, d = model.optimize(loss, ch.data, options={"maxiter": 30})
+    assert f < f0 and d["warnflag"] in (0, 1)
+    assert np.max(np.abs(x - p0)) < 1e-4            # the RVs moved by metres per second, not off the grid
+    # the staged fit of quickplay.train_cycle (templates, RVs, parabola refinement, everything)
+    ch2 = synth.make_chunk(chunk=12, n_epochs=16, n_pix=640, p_val=3, n_lines=10)
+    m2 = ch2.model
+    m2.fix(); m2.fit(0, 0); m2.fit(0, 1); m2.fit(1, 1)
+    f_start = loss.loss_all(np.asarray(m2.get_parameters()), *ch2.data.blockify(), m2, None, None)
+    jabble.quickplay.train_cycle(m2, ch2.data, loss, options={"maxiter": 8}, parabola_fit=True)
+    m2.fix(); m2.fit(0, 0); m2.fit(0, 1); m2.fit(1, 1)
+    f_end = loss.loss_all(np.asarray(m2.get_parameters()), *ch2.data.blockify(), m2, None, None)
+    assert f_end < f_start and len(m2.results) == 6

@@ -77,9 +77,11 @@ SYMBOLS = [
     ("jb_batch_destroy", None, [C.c_void_p]),
     ("jb_batch_bind", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("jb_batch_eval_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("jb_batch_eval_device_checked", C.c_int, [C.c_void_p, C.c_void_p]),
     ("jb_batch_eval_host", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("jb_batch_eval_host_begin", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("jb_batch_eval_host_end", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("jb_batch_soft_range", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_batch_check", C.c_int, [C.c_void_p]),
     ("jb_batch_launches", C.c_int64, [C.c_void_p]),
     ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

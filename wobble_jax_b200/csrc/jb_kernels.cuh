@@ -62,6 +62,7 @@ struct PrepareParams {
     int64_t n_rows;
     int n_comp;
     CompDev comp[kMaxComp];
+    int* status;      // cleared here, at the start of every evaluation: what it holds afterwards is this evaluation's
 };
 
 template <int NC, int HN>
@@ -69,6 +70,7 @@ __global__ void k_prepare_rows(const PrepareParams* __restrict__ arr, const int*
     const int pi = find_plan(off, n, blockIdx.x);
     const PrepareParams& a = arr[pi];
     const int64_t pos = (int64_t)(blockIdx.x - off[pi]) * blockDim.x + threadIdx.x;
+    if (pos == 0 && a.status) { a.status[0] = 0; a.status[1] = 0; }
     if (pos >= a.n_rows) return;
     const int r = a.row_perm[pos];
     RowRec<NC, HN> rec;
@@ -1059,7 +1061,9 @@ __global__ void k_finish(const ReduceParams* __restrict__ arr, const int* __rest
             if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) out[0] = 0.5 * a.coef * sh[0];
+        // an evaluation that ran off the knot grid or out of its window has no value: NaN, so that a
+        // device-side line search rejects the trial (host callers read the status word and get the error)
+        if (threadIdx.x == 0) out[0] = a.status[0] ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * a.coef * sh[0];
     } else {
         const int64_t i = (int64_t)(blk - 1) * blockDim.x + threadIdx.x;
         if (i < a.n_fit) out[1 + i] = a.grad_all[a.fit_map[i]];

@@ -145,6 +145,7 @@ struct jb_batch {
     std::vector<int64_t> off_p, off_out;
     int** d_stat_ptrs = nullptr; int* d_stat_flat = nullptr; int* h_stat_flat = nullptr;
     bool host_bound = false, host_pending = false;
+    bool soft_range = false;   // jb_batch_soft_range: an out-of-range plan yields a NaN loss instead of an error
 };
 
 namespace {
@@ -278,6 +279,7 @@ int refresh_pack(jb_plan* pl) {
     memset(&k, 0, sizeof k);
     k.sc.p_fit = pl->d_pfit; k.sc.fit_map = pl->d_fit_map; k.sc.params = pl->d_params; k.sc.n_fit = pl->n_fit;
     k.pr.row_perm = pl->d_row_perm; k.pr.grouprec = pl->d_grouprec; k.pr.n_rows = pl->E; k.pr.n_comp = pl->n_comp;
+    k.pr.status = pl->d_status;
     jb::FusedParams& fp = k.fu;
     fp.data = pl->f32 ? reinterpret_cast<const double*>(pl->d_data32) : pl->d_data;
     fp.grouprec = pl->d_grouprec; fp.tinfo = pl->d_tinfo;
@@ -1198,24 +1200,77 @@ int jb_batch_bind(jb_batch* b, const double* const* d_p_fit, double* const* d_ou
 
 int jb_batch_eval_device(jb_batch* b, void* stream);
 
+static int batch_status_buffers(jb_batch* b) {
+    if (b->d_stat_ptrs) return JB_OK;
+    const size_t n = b->plans.size();
+    std::vector<int*> ptrs;
+    for (jb_plan* pl : b->plans) ptrs.push_back(pl->d_status);
+    JB_CUDA(cudaMalloc(&b->d_stat_ptrs, n * sizeof(int*)));
+    JB_CUDA(cudaMemcpy(b->d_stat_ptrs, ptrs.data(), n * sizeof(int*), cudaMemcpyHostToDevice));
+    JB_CUDA(cudaMalloc(&b->d_stat_flat, 2 * n * sizeof(int)));
+    JB_CUDA(cudaMallocHost(&b->h_stat_flat, 2 * n * sizeof(int)));
+    return JB_OK;
+}
+
+// After an evaluation was enqueued on st: wait, and give every plan whose knot window overflowed
+// what jb_plan_eval gives it (eval_sync: first a re-sort of its rows with the current parameters,
+// then a wider window / shorter row groups) and evaluate the whole batch again, until it fits.
+// copy_out: re-enqueue the device->host copy of the flat output buffer behind each evaluation.
+static int batch_settle(jb_batch* b, cudaStream_t st, bool copy_out) {
+    const size_t n = b->plans.size();
+    int rc;
+    for (int attempt = 0;; ++attempt) {
+        jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
+        JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        JB_CUDA(cudaStreamSynchronize(st));
+        bool again = false;
+        for (size_t i = 0; i < n; ++i) {
+            if (!b->h_stat_flat[2 * i] && !b->h_stat_flat[2 * i + 1]) continue;
+            jb_plan* pl = b->plans[i];
+            bool window = false;
+            rc = read_status(pl, st, &window);
+            if (rc == JB_OK) continue;
+            if (rc == JB_ERR_OUT_OF_RANGE && b->soft_range) continue;     // its loss came back NaN (k_finish)
+            if (!window || attempt >= 12) return rc;
+            JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
+            if (attempt > 0) {
+                if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
+                else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
+                else return rc;
+                if ((rc = alloc_scratch(pl))) return rc;
+            }
+            if ((rc = resort_rows(pl))) return rc;
+            again = true;
+        }
+        if (!again) return JB_OK;
+        if ((rc = jb_batch_eval_device(b, st))) return rc;
+        if (copy_out)
+            JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+}
+
+int jb_batch_eval_device_checked(jb_batch* b, void* stream) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    JB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    int rc = batch_status_buffers(b);
+    if (rc) return rc;
+    if ((rc = jb_batch_eval_device(b, st))) return rc;
+    return batch_settle(b, st, false);
+}
+
 int jb_batch_eval_host_begin(jb_batch* b, const double* const* p_fit_host) {
     if (!b || !p_fit_host) return fail(JB_ERR_BAD_ARG, "null argument");
     JB_CUDA(cudaSetDevice(b->device));
     const size_t n = b->plans.size();
+    int rc0;
     if (b->host_bound)
         for (size_t i = 0; i < n; ++i)
             if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit) b->host_bound = false;   // a fit vector changed size
     if (!b->host_bound) {     // (re)build the flat buffers for the plans' current fit sizes
         JB_CUDA(cudaStreamSynchronize(b->stream));
         if (b->d_flat_p) { cudaFree(b->d_flat_p); cudaFree(b->d_flat_out); cudaFreeHost(b->h_flat_p); cudaFreeHost(b->h_flat_out); }
-        if (!b->d_stat_ptrs) {
-            std::vector<int*> ptrs;
-            for (jb_plan* pl : b->plans) ptrs.push_back(pl->d_status);
-            JB_CUDA(cudaMalloc(&b->d_stat_ptrs, n * sizeof(int*)));
-            JB_CUDA(cudaMemcpy(b->d_stat_ptrs, ptrs.data(), n * sizeof(int*), cudaMemcpyHostToDevice));
-            JB_CUDA(cudaMalloc(&b->d_stat_flat, 2 * n * sizeof(int)));
-            JB_CUDA(cudaMallocHost(&b->h_stat_flat, 2 * n * sizeof(int)));
-        }
+        if ((rc0 = batch_status_buffers(b))) return rc0;
         b->off_p.assign(n + 1, 0); b->off_out.assign(n + 1, 0);
         for (size_t i = 0; i < n; ++i) {
             b->off_p[i + 1] = b->off_p[i] + b->plans[i]->n_fit;
@@ -1240,8 +1295,6 @@ int jb_batch_eval_host_begin(jb_batch* b, const double* const* p_fit_host) {
     int rc = jb_batch_eval_device(b, st);
     if (rc) return rc;
     JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
-    jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
-    JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
     b->host_pending = true;
     return JB_OK;
 }
@@ -1253,41 +1306,19 @@ int jb_batch_eval_host_end(jb_batch* b, double* const* out_host) {
     const size_t n = b->plans.size();
     cudaStream_t st = b->stream;
     b->host_pending = false;
-    int rc;
-    for (int attempt = 0;; ++attempt) {
-        JB_CUDA(cudaStreamSynchronize(st));
-        // plans whose knot window overflowed get what jb_plan_eval gives them (eval_sync): first a
-        // re-sort of their rows with the current parameters, then a wider window / shorter row
-        // groups; then the whole batch is evaluated again (the fit vectors are still on the device)
-        bool again = false;
-        for (size_t i = 0; i < n; ++i) {
-            if (!b->h_stat_flat[2 * i] && !b->h_stat_flat[2 * i + 1]) continue;
-            jb_plan* pl = b->plans[i];
-            bool window = false;
-            rc = read_status(pl, st, &window);
-            if (rc == JB_OK) continue;
-            if (!window || attempt >= 12) return rc;
-            JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
-            if (attempt > 0) {
-                if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
-                else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
-                else return rc;
-                if ((rc = alloc_scratch(pl))) return rc;
-            }
-            if ((rc = resort_rows(pl))) return rc;
-            again = true;
-        }
-        if (!again) break;
-        if ((rc = jb_batch_eval_device(b, st))) return rc;
-        JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
-        jb::k_gather_status<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->d_stat_ptrs, (int)n, b->d_stat_flat);
-        JB_CUDA(cudaMemcpyAsync(b->h_stat_flat, b->d_stat_flat, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    }
+    int rc = batch_settle(b, st, true);
+    if (rc) return rc;
     for (size_t i = 0; i < n; ++i) {
         if (!out_host[i]) return fail(JB_ERR_BAD_ARG, "null output for plan %zu", i);
         memcpy(out_host[i], b->h_flat_out + b->off_out[i], (b->plans[i]->n_fit + 1) * sizeof(double));
-        if (!std::isfinite(out_host[i][0])) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
+        if (!std::isfinite(out_host[i][0]) && !b->soft_range) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
     }
+    return JB_OK;
+}
+
+int jb_batch_soft_range(jb_batch* b, int enable) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    b->soft_range = enable != 0;
     return JB_OK;
 }
 

@@ -341,6 +341,14 @@ class Batch:
         _lib.check(self.lib.jb_batch_eval_host(self.handle, pf, po))
         return out_list
 
+    def soft_range(self, enable=True):
+        """Out-of-range plans give a NaN loss in ``eval_host`` instead of failing the whole call."""
+        _lib.check(self.lib.jb_batch_soft_range(self.handle, int(bool(enable))))
+
+    def eval_device_checked(self, stream_ptr=0):
+        """eval_device, then wait and settle knot-window overflows the way jb_plan_eval does."""
+        _lib.check(self.lib.jb_batch_eval_device_checked(self.handle, C.c_void_p(stream_ptr)))
+
     def eval_host_begin(self, p_list):
         """Copy the fit vectors and enqueue the evaluation on the batch's own stream; returns at once."""
         n = len(self.plans)
@@ -410,9 +418,11 @@ class Objective:
             if r.indices is None:
                 r.ready_indices(model)
         self.n_evals = 0
+        self.n_out_of_range = 0
         self._p = None
         self._f = None
         self._g = None
+        self._f_inside = None                 # loss of the last evaluation that stayed inside the knot grids
         self._data_eval = self.plan.eval      # (loss, gradient) of the data term; LockstepEvaluator reroutes it
 
     @classmethod
@@ -436,7 +446,19 @@ class Objective:
     def _eval(self, p):
         p = np.asarray(p, dtype=np.float64).reshape(-1)
         if self._p is None or p.shape != self._p.shape or not np.array_equal(p, self._p):
-            self._f, self._g = self._data_eval(p)
+            try:
+                self._f, self._g = self._data_eval(p)
+                self._f_inside = self._f
+            except ValueError as exc:
+                # A trial point of a line search that carries an unmasked pixel off a knot grid (a first
+                # L-BFGS step has unit length: metres per second for an RV).  The reference's gather
+                # clamps there (model.py:985) and scipy sees a large finite loss and shortens the step;
+                # here the kernel refuses the point, so the line search is told the same thing: a loss
+                # far above the last valid one, no slope.  The first evaluation of a fit still raises.
+                if "outside the knot grid" not in str(exc) or self._f_inside is None:
+                    raise
+                self.n_out_of_range += 1
+                self._f, self._g = 1e8 * max(abs(self._f_inside), 1.0), np.zeros_like(p)
             for r in self.regs:
                 # the reference's loss_all evaluates a regulariser inside the vmap over rows
                 # (loss.py:61-74): its value and gradient are counted once per row of the block
@@ -505,9 +527,13 @@ class LockstepEvaluator:
             batch = self.batches.get(idx)
             if batch is None:
                 batch = self.batches[idx] = Batch([self.objs[i].plan for i in idx])
+                batch.soft_range(True)
             outs = batch.eval_host([self.pending[i] for i in idx])
             for i, o in zip(idx, outs):
-                self.results[i] = (float(o[0]), o[1:].copy())
+                if np.isfinite(o[0]):
+                    self.results[i] = (float(o[0]), o[1:].copy())
+                else:      # this chunk's trial left a knot grid: its optimiser hears what jb_plan_eval would say
+                    self.results[i] = ValueError("an unmasked warped pixel lies outside the knot grid of a spline component")
         except BaseException as exc:       # every waiting optimiser gets the error, nobody is left waiting
             for i in idx:
                 self.results[i] = exc
