@@ -98,6 +98,7 @@ class EpochShardedObjective:
         self._p = None
         self._f = None
         self._g = None
+        self._f_inside = None
 
     def _eval(self, p):
         torch = self.torch
@@ -108,7 +109,23 @@ class EpochShardedObjective:
                 self.plan.eval_device(self.d_p.data_ptr(), self.d_out.data_ptr(), self.stream.cuda_stream)
                 all_reduce_sum(self.d_out, self.group)
                 out = self.d_out.cpu().numpy()
-            self.plan.check()
+            # A shard whose trial point leaves a knot grid writes a NaN loss (k_finish), so after the
+            # all-reduce EVERY rank sees NaN and takes the same branch: the first evaluation raises, a
+            # later one (a line-search excursion) gets the penalty engine.Objective gives it.
+            try:
+                self.plan.check()
+                err = None
+            except ValueError as exc:
+                err = exc
+            if not np.isfinite(out[0]):
+                if self._f_inside is None:
+                    raise err if err is not None else ValueError(
+                        "an unmasked warped pixel lies outside the knot grid of a spline component (on another rank)")
+                out = np.concatenate([[1e8 * max(abs(self._f_inside), 1.0)], np.zeros(self.n_fit)])
+            else:
+                if err is not None:
+                    raise err
+                self._f_inside = float(out[0])
             self._f, self._g, self._p = float(out[0]), out[1:].copy(), p.copy()
         return self._f, self._g
 
