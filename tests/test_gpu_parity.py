@@ -558,3 +558,51 @@ def test_rv_fit_survives_line_search_excursions_and_train_cycle_runs():
     m2.fix(); m2.fit(0, 0); m2.fit(0, 1); m2.fit(1, 1)
     f_end = loss.loss_all(np.asarray(m2.get_parameters()), *ch2.data.blockify(), m2, None, None)
     assert f_end < f_start and len(m2.results) == 6
+
+
+def test_end_to_end_workflow_recovers_injected_rvs(tmp_path):
+    """The reference's notebook flow on a synthetic star (notebooks/01-testdata.ipynb, 05-simulateddata):
+    build the wobble model from rough RVs, train_cycle with the parabola stage, RV error bars three
+    ways, save / load -- and the recovered RVs must agree with the injected ones within a few sigma."""
+    ch = synth.make_chunk(chunk=13, n_epochs=24, n_pix=1536, p_val=3, n_lines=40, snr=200.0)
+    data, truth = ch.data, ch.truth
+    rng = np.random.default_rng(3)
+    init_v = truth["vel"] + rng.normal(0.0, 300.0, len(truth["vel"]))       # rough starting RVs
+    model = jabble.quickplay.get_wobble_model(init_v, truth["airmass"], ch.grid, 3)
+    loss = jabble.loss.ChiSquare()
+    jabble.quickplay.train_cycle(model, data, loss, options={"maxiter": 60}, parabola_fit=True)
+    rv = jabble.physics.velocities(model[0][0].p)
+    err_f = jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0, 0])
+    err_2 = jabble.quickplay.get_RV_error_2d(model, data, loss, [0, 0])
+    assert np.all(np.isfinite(err_f)) and np.all(err_f > 0) and np.all(err_f < 50.0)
+    ok = np.isfinite(err_2)
+    assert ok.sum() >= 20 and np.allclose(err_2[ok], err_f[ok], rtol=0.3)
+    # RVs are recovered up to a common offset (the template absorbs a constant shift)
+    d = (rv - truth["vel"]) - np.median(rv - truth["vel"])
+    assert np.std(d) < 0.2 * np.std(init_v - truth["vel"]) and np.std(d) < 6.0 * np.median(err_f)
+    path = str(tmp_path / "fit.h5")
+    jabble.model.save(path, model)
+    back = jabble.model.load(path)
+    assert np.array_equal(back[0][0].p, model[0][0].p) and np.array_equal(back[1][1].p, model[1][1].p)
+    jabble.model.save_rvs(str(tmp_path / "rvs.h5"), [0, 0], back, data, loss, np.arange(24.0))
+
+
+def test_pseudonormal_workflow_runs():
+    """PseudoNormalModel flow (README.md:13; notebooks/04-HD4307.ipynb, 07-apogee-cframes.ipynb): the
+    wobble model plus a per-row normalisation spline, train_norm then train_cycle (general kernel)."""
+    ch = synth.make_chunk(chunk=14, n_epochs=10, n_pix=1024, p_val=3, n_lines=20, ragged=True)
+    data, truth = ch.data, ch.truth
+    for r in range(len(data)):                       # a slow continuum trend per row for the normalisation to take out
+        x = data[r].xs
+        data[r].ys = data[r].ys + 0.05 * (x - x.mean()) / (x.max() - x.min())
+    model = jabble.quickplay.get_wobble_model(truth["vel"] + 100.0, truth["airmass"], ch.grid, 3) + \
+        jabble.quickplay.get_normalization_model(data, 2, 4)
+    loss = jabble.loss.ChiSquare()
+    model.fix(); model.fit(0, 1); model.fit(1, 1); model.fit(2, 1)
+    f0 = loss.loss_all(np.asarray(model.get_parameters()), *data.blockify(), model, None, None)
+    jabble.quickplay.train_norm(model, data, loss, maxiter=1, options={"maxiter": 20}, nsigma=[8.0, 8.0])
+    jabble.quickplay.train_cycle(model, data, loss, options={"maxiter": 25})
+    model.fix(); model.fit(0, 1); model.fit(1, 1); model.fit(2, 1)
+    f1 = loss.loss_all(np.asarray(model.get_parameters()), *data.blockify(), model, None, None)
+    assert f1 < 0.5 * f0
+    assert np.all(np.isfinite(jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0, 0])))
