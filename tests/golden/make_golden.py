@@ -324,8 +324,39 @@ def fixture_regularised():
     print("regularised.npz", len(out))
 
 
+def fixture_combine():
+    """quickplay.combine_rvs (quickplay.py:15-44): per-chunk RVs -> one RV per time."""
+    rng = np.random.default_rng(77)
+    n_chunks, n_t = 5, 12
+    times = np.sort(rng.uniform(2455000.0, 2455100.0, n_t))
+    truth = 50.0 * np.sin(times / 7.0)
+    rv_list, err_list, time_list = [], [], []
+    for c in range(n_chunks):
+        order = rng.permutation(n_t)                      # chunks list their epochs in different orders
+        err = rng.uniform(2.0, 30.0, n_t)
+        rv = truth[order] + err * rng.normal(size=n_t)
+        if c == 1:
+            err[3] = np.nan                               # dropped: information is NaN
+        if c == 2:
+            err[5] = 0.0                                  # dropped: information is inf
+        if c == 3:
+            err[0] = 1e-3                                 # dropped by max_info = 1e4
+        rv_list.append(rv), err_list.append(err), time_list.append(times[order])
+    out = {"n_chunks": n_chunks}
+    for c in range(n_chunks):
+        out[f"rv_{c}"], out[f"err_{c}"], out[f"time_{c}"] = rv_list[c], err_list[c], time_list[c]
+    with np.errstate(divide="ignore"):
+        out["rv_a"], out["err_a"], out["time_a"] = jabble.quickplay.combine_rvs(rv_list, err_list, time_list)
+        out["rv_b"], out["err_b"], out["time_b"] = jabble.quickplay.combine_rvs(
+            rv_list, err_list, time_list, max_info=1e4, min_info=1.5e-3)
+    np.savez(os.path.join(HERE, "combine_rvs.npz"), **out)
+    print("combine_rvs.npz", len(out))
+
+
 if __name__ == "__main__":
-    todo = sys.argv[1:] or ["basis", "stellar", "wobble", "pseudonormal", "regularised"]
+    todo = sys.argv[1:] or ["basis", "stellar", "wobble", "pseudonormal", "regularised", "combine"]
+    if "combine" in todo:
+        fixture_combine()
     if "basis" in todo:
         fixture_basis()
     if "stellar" in todo:

@@ -145,3 +145,60 @@ def test_save_load_round_trip(tmp_path):
         for k in ("xs", "ys", "yivar", "mask"):
             assert np.array_equal(getattr(a, k), getattr(b, k))
     assert np.array_equal(d2.metadata["times"], np.arange(5.0))
+
+
+def test_combine_rvs_matches_reference_golden():
+    """quickplay.combine_rvs (quickplay.py:15-44) against the outputs of the reference's own function
+    (tests/golden/make_golden.py fixture_combine): NaN / infinite / out-of-window information dropped."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "combine_rvs.npz"))
+    n = int(g["n_chunks"])
+    rv, err, tm = ([g[f"{k}_{c}"] for c in range(n)] for k in ("rv", "err", "time"))
+    for tag, kw in (("a", {}), ("b", dict(max_info=1e4, min_info=1.5e-3))):
+        out_rv, out_err, out_time = jabble.quickplay.combine_rvs(rv, err, tm, **kw)
+        assert np.array_equal(out_time, g["time_" + tag])
+        np.testing.assert_allclose(out_rv, g["rv_" + tag], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(out_err, g["err_" + tag], rtol=1e-9, atol=0)
+    assert not np.array_equal(g["rv_a"], g["rv_b"])
+
+
+def test_summary_files_and_load_model_dir(tmp_path):
+    """create_summary_hdf / load_summary_hdf / load_model_dir (quickplay.py:46-129) over three chunk
+    files: combined RVs, the links group, the per-chunk table ordered by wavelength, cached re-read."""
+    from wobble_jax_b200 import store
+    qp = jabble.quickplay
+    rng = np.random.default_rng(5)
+    times = np.array([3.0, 1.0, 2.0, 5.0, 4.0])
+    files, rvs, errs = [], [], []
+    for c in (2, 0, 1):                                    # written out of wavelength order
+        ch = synth.make_chunk(chunk=c, n_epochs=5, n_pix=120, p_val=3, n_lines=3)
+        ch.data.metadata["times"] = times
+        mfile, dfile = str(tmp_path / f"model_{c}.h5"), str(tmp_path / f"data_{c}.h5")
+        jabble.model.save(mfile, ch.model)
+        ch.data.save(dfile)
+        rv, err = rng.normal(0, 30, 5), rng.uniform(1, 5, 5)
+        loss = rng.uniform(0, 1, (5, 120))
+        f = str(tmp_path / f"chunk_{c}.h5")
+        qp.save_chunk_summary(f, rv, err, times, loss, mfile, dfile)
+        files.append(f), rvs.append(rv), errs.append(err)
+    rv_array, models, table, datas = qp.load_model_dir(str(tmp_path), files)
+    comb_rv, comb_err, comb_time = qp.combine_rvs(rvs, errs, [times] * 3)
+    assert np.array_equal(rv_array["Time_comb"], np.sort(times))
+    np.testing.assert_allclose(rv_array["RV_comb"], comb_rv, rtol=1e-14)
+    np.testing.assert_allclose(rv_array["RV_err_comb"], comb_err, rtol=1e-12)
+    # chunks come back ordered by their smallest wavelength: chunk 0, 1, 2 = files[1], files[2], files[0]
+    lo = [np.min(np.concatenate(d.xs)) for d in datas]
+    assert lo == sorted(lo) and len(models) == 3 and type(models[0]).__name__ == "AdditiveModel"
+    np.testing.assert_array_equal(table["RV_all"], np.stack([rvs[1], rvs[2], rvs[0]]))
+    rank = np.argsort(np.argsort(times))
+    np.testing.assert_allclose(table["RV_difference"][0], rvs[1] - comb_rv[rank], rtol=1e-12, atol=1e-12)
+    assert table["Loss_Avg"].shape == (3, 5)
+    summary = str(tmp_path / "RV_Summary.hdf")
+    with store.File(summary, "r") as hf:
+        assert list(hf.keys()) == ["RVs", "links"]
+        assert sorted(hf["links"].keys()) == ["chunk_0.h5", "chunk_1.h5", "chunk_2.h5"]
+    again = qp.load_summary_hdf(summary)
+    assert np.array_equal(again["RV_comb"], rv_array["RV_comb"]) and again.dtype == rv_array.dtype
+    # second call reads the cached summaries
+    rv_array2, _, table2, _ = qp.load_model_dir(str(tmp_path), files)
+    assert np.array_equal(rv_array2["RV_comb"], rv_array["RV_comb"])
+    assert np.array_equal(table2["Loss_Avg"], table["Loss_Avg"])

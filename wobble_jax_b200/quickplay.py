@@ -2,8 +2,10 @@
 
 These are callers of the hot path with no arithmetic of their own:
 they assemble the model trees the CUDA plan compiler recognises and drive ``Model.optimize``.
-RV post-processing / HDF summaries (quickplay.py:15-129, 405-553) are out of scope.
+RV combination over chunks and the summary files (quickplay.py:15-129) are host-side numpy.
 """
+
+import os
 
 import numpy as np
 
@@ -14,6 +16,139 @@ from . import physics
 def _magnitudes(v):
     """Accept plain arrays or astropy quantities (the reference multiplies by ``u.m/u.s``)."""
     return np.asarray(getattr(v, "value", v), dtype=np.float64)
+
+
+_RV_SUMMARY_DTYPE = [("RV_comb", np.double), ("RV_err_comb", np.double), ("Time_comb", np.double)]
+
+
+def combine_rvs(rv_list, err_list, time_list, max_info=1e30, min_info=0.0):
+    """quickplay.py:15-44 -- one RV per distinct time from the per-chunk (per-order) RVs: the
+    information-weighted mean (information = 1 / err^2) over the chunks whose information lies in
+    ``(min_info, max_info)`` and is finite, and the weighted scatter about it as the error.  A time
+    whose chunks are all filtered out raises ZeroDivisionError like ``np.average`` does in the reference.
+    """
+    all_rvs = np.concatenate([np.asarray(r, dtype=float) for r in rv_list])
+    all_err = np.concatenate([np.asarray(e, dtype=float) for e in err_list])
+    all_times = np.concatenate([np.asarray(t) for t in time_list])
+    with np.errstate(divide="ignore"):
+        all_info = 1 / all_err ** 2
+    out_time = np.unique(all_times)
+    out_rv = np.zeros(out_time.shape)
+    out_err = np.zeros(out_time.shape)
+    keep = (all_info < max_info) & (all_info > min_info) & np.isfinite(all_info)
+    for ii, this_time in enumerate(out_time):
+        sel = keep & (all_times == this_time)
+        rv, info = all_rvs[sel], all_info[sel]
+        out_rv[ii] = np.average(rv, weights=info)
+        out_err[ii] = np.sqrt(np.average(rv ** 2, weights=info) - out_rv[ii] ** 2)
+    return out_rv, out_err, out_time
+
+
+def create_summary_hdf(filename, rv_array, dir_files, dir):
+    """quickplay.py:46-59 -- group ``RVs`` with the combined RVs and group ``links`` with one entry
+    per chunk file.  With h5py the entries are external links like the reference's; the .npz mirror
+    holds the linked path as a string dataset under the same name."""
+    from . import store
+    with store.File(filename, "w") as file:
+        group = file.create_group("RVs")
+        group.create_dataset("RV_comb", data=np.asarray(rv_array["RV_comb"]))
+        group.create_dataset("RV_err_comb", data=np.asarray(rv_array["RV_err_comb"]))
+        group.create_dataset("Time_comb", data=np.asarray(rv_array["Time_comb"]))
+        link_group = file.create_group("links")
+        for dir_file in dir_files:
+            tail = os.path.split(dir_file)[1]
+            target = os.path.join(dir, dir_file)
+            if store.h5py is not None and not isinstance(link_group, store.Group):
+                link_group[tail] = store.h5py.ExternalLink(target, "/")
+            else:
+                store.string_dataset(link_group, tail, target)
+
+
+def load_summary_hdf(filename):
+    """quickplay.py:61-66 -- the structured array ``(RV_comb, RV_err_comb, Time_comb)``."""
+    from . import store
+    with store.File(filename, "r") as file:
+        cols = [np.asarray(file["RVs"][k][:], dtype=np.double) for k in ("RV_comb", "RV_err_comb", "Time_comb")]
+    return np.array([*zip(*cols)], dtype=_RV_SUMMARY_DTYPE)
+
+
+def save_chunk_summary(filename, rvs, rv_err, times, loss_array, model_file, dataset_file):
+    """Writes the per-chunk file ``load_model_dir`` reads (quickplay.py:68-95): datasets ``RVs``,
+    ``RV_err``, ``Times``, ``Loss`` (rows x pixels, ``get_loss_array``) and the attributes ``model`` /
+    ``dataset`` naming the saved model and data.  The reference writes these from its notebooks."""
+    from . import store
+    with store.File(filename, "w") as file:
+        file.create_dataset("RVs", data=np.asarray(rvs, dtype=float))
+        file.create_dataset("RV_err", data=np.asarray(rv_err, dtype=float))
+        file.create_dataset("Times", data=np.asarray(times, dtype=float))
+        file.create_dataset("Loss", data=np.asarray(loss_array, dtype=float))
+        file.attrs["model"] = str(model_file)
+        file.attrs["dataset"] = str(dataset_file)
+
+
+def load_model_dir(path, dir_files, device=None, force_run=False, max_info=1e30, min_info=0.0):
+    """quickplay.py:68-129 -- read every chunk file of a run, combine the RVs (``RV_Summary.hdf``,
+    rebuilt when missing or ``force_run``) and tabulate per chunk the RVs, errors, times, mean loss per
+    time and the difference to the combined RV (``RV_all_Summary.npy``).  Returns ``(rv_array, models,
+    all_rv_array, datasets)`` ordered by the smallest wavelength of each chunk.
+
+    The reference reads the per-time ids through ``datablock.meta_keys`` / ``datablock.datablock``,
+    attributes its ``blockify`` result does not have (``dataset.py:192-237`` returns a tuple); here
+    they come from the ``times`` key of the metablock and ``Data.metakeys``, which is what that code
+    reaches for.  ``model`` / ``dataset`` attributes are loaded with ``model.load`` / ``Data.load``.
+    """
+    from . import dataset as jdataset
+    from . import store
+    all_models, all_data = [], []
+    rv_list, err_list, time_list, loss_rows = [], [], [], []
+    for filename in dir_files:
+        with store.File(filename, "r") as file:
+            rv_list.append(np.array(file["RVs"][:]))
+            err_list.append(np.array(file["RV_err"][:]))
+            time_list.append(np.array(file["Times"][:]))
+            loss_temp = np.array(file["Loss"][:]).mean(axis=1)
+            model_file, data_file = str(file.attrs["model"]), str(file.attrs["dataset"])
+        model = jmodel.load(model_file)
+        data = jdataset.Data.load(data_file)
+        all_models.append(model)
+        all_data.append(data)
+        _, metablock = data.blockify(device)
+        if "times" in metablock.keys():
+            ids = np.asarray(metablock["times"])
+            n_times = len(data.metakeys["times"])
+        else:
+            ids, n_times = np.asarray(metablock["index"]), len(loss_temp)
+        loss_rows.append(np.array([loss_temp[ids == j].mean() for j in range(n_times)]))
+    loss_array = np.stack(loss_rows)
+
+    summary = os.path.join(path, "RV_Summary.hdf")
+    if not os.path.isfile(summary) or force_run:
+        comb_rv, comb_err, comb_time = combine_rvs(rv_list, err_list, time_list, max_info=max_info, min_info=min_info)
+        rv_array = np.array([*zip(comb_rv, comb_err, comb_time)], dtype=_RV_SUMMARY_DTYPE)
+        create_summary_hdf(summary, rv_array, dir_files, path)
+    else:
+        rv_array = load_summary_hdf(summary)
+
+    min_wavelength_of_chunk = np.array([np.min(np.concatenate(d.xs)) for d in all_data])
+    all_summary = os.path.join(path, "RV_all_Summary.npy")
+    if not os.path.isfile(all_summary) or force_run:
+        n_t = loss_array.shape[1]
+        rv_difference = np.zeros((len(rv_list), rv_array["RV_comb"].shape[0]))
+        comb_sorted = rv_array["RV_comb"][np.argsort(rv_array["Time_comb"])]
+        for iii, (rv_sub, time_sub) in enumerate(zip(rv_list, time_list)):
+            rank = np.argsort(np.argsort(time_sub))
+            rv_difference[iii, :] = rv_sub - comb_sorted[rank]
+        all_rv_array = np.array(
+            [*zip(np.stack(rv_list), np.stack(err_list), np.stack(time_list), loss_array, rv_difference,
+                  min_wavelength_of_chunk)],
+            dtype=[("RV_all", np.double, (n_t,)), ("RV_err_all", np.double, (n_t,)), ("Time_all", np.double, (n_t,)),
+                   ("Loss_Avg", np.double, (n_t,)), ("RV_difference", np.double, (n_t,)), ("min_order", int)])
+        np.save(all_summary, all_rv_array)
+    else:
+        all_rv_array = np.load(all_summary)
+
+    order = np.argsort(min_wavelength_of_chunk)
+    return rv_array, [all_models[i] for i in order], all_rv_array[order], [all_data[i] for i in order]
 
 
 def get_stellar_model(init_rvs, model_grid, p_val, which_key="index"):
