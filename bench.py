@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--pixels", type=int, default=4096)
     ap.add_argument("--p-val", type=int, default=3)
     ap.add_argument("--rows-per-group", type=int, default=0)
+    ap.add_argument("--e2e", default="pinned", choices=["pinned", "batch", "threads"],
+                    help="host-buffer path of the end-to-end leg (chunks workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget")
     ap.add_argument("--workload", default="chunks", choices=["chunks", "epochs"],
@@ -288,7 +290,7 @@ def run_b200(args, rank, world, local_rank):
     # one thread hands all chunks over in one call (jb_batch_eval_host).
     grads = [np.empty(n_fit) for _ in plans]
     cores_per_rank = max(1, len(os.sched_getaffinity(0)) // max(world, 1))
-    threaded = cores_per_rank >= 16
+    e2e_path = args.e2e
 
     def eval_host(i):
         p_host[i] += 1e-13
@@ -304,9 +306,24 @@ def run_b200(args, rank, world, local_rank):
         batch.eval_host(p_host, outs)
         return [float(o[0]) for o in outs]
 
+    if e2e_path == "pinned":
+        # the batch's own page-locked host buffers: the fit vectors are written there (as the optimiser
+        # threads of model.optimize_many do), one H2D copy, the evaluation, one D2H copy, read in place
+        pin_p, pin_out = batch.host_buffers()
+        for v, p in zip(pin_p, p_host):
+            v[:] = p
+
+    def eval_host_pinned():
+        for v in pin_p:
+            v += 1e-13
+        batch.eval_pinned()
+        return [float(o[0]) for o in pin_out]
+
     with ThreadPoolExecutor(min(16, args.chunks)) as pool:
         def e2e_step():
-            return list(pool.map(eval_host, range(len(plans)))) if threaded else eval_host_batch()
+            if e2e_path == "threads":
+                return list(pool.map(eval_host, range(len(plans))))
+            return eval_host_pinned() if e2e_path == "pinned" else eval_host_batch()
         for _ in range(min(args.warmup, 2)):
             e2e_step()
         barrier()
@@ -344,8 +361,10 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_fit * args.chunks * world),
                 "d2h_bytes_per_step": int(8 * (n_fit + 1) * args.chunks * world),
                 "ms_per_step": e2e_ms / args.steps,
-                "api": ("jb_plan_eval (host p_fit in, host loss+gradient out), 16 host threads over the chunks" if threaded else
-                        "jb_batch_eval_host (host fit vectors in, host loss+gradient out, all chunks of the rank in one call, one host thread)"),
+                "api": {"threads": "jb_plan_eval (host p_fit in, host loss+gradient out), 16 host threads over the chunks",
+                        "batch": "jb_batch_eval_host (host fit vectors in, host loss+gradient out, all chunks of the rank in one call, one host thread)",
+                        "pinned": "jb_batch_host_buffers + jb_batch_eval_pinned (fit vectors written into / [loss, gradient] read from the "
+                                  "batch's page-locked host buffers; one H2D copy, 6 launches, one D2H copy, one sync per step)"}[e2e_path],
                 "host_cores_per_rank": cores_per_rank},
         "device_api": "jb_batch_eval_device: 6 launches per step for all chunks of the GPU",
         "gpu_launches": int(launches),

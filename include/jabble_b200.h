@@ -220,6 +220,19 @@ int jb_batch_eval_device_checked(jb_batch *batch, void *stream);
 int jb_batch_eval_host(jb_batch *batch, const double *const *p_fit_host, double *const *out_host);
 int jb_batch_eval_host_begin(jb_batch *batch, const double *const *p_fit_host);
 int jb_batch_eval_host_end(jb_batch *batch, double *const *out_host);
+/*
+ * The same without the staging copies: jb_batch_host_buffers hands out the batch's own page-locked
+ * host buffers -- every plan's fit vector back to back in *p_fit_pinned (plan i at off_p[i] ..
+ * off_p[i+1]) and every plan's [loss, gradient] in *out_pinned (plan i at off_out[i] .. off_out[i+1]);
+ * off_p and off_out have n_plans + 1 entries.  The caller (one optimiser thread per chunk, the Pool of
+ * notebooks/02-51peg.py:66-78) writes its fit vector in place; jb_batch_eval_pinned copies
+ * host->device, evaluates every plan, copies device->host and synchronises; the results are read in
+ * place.  The buffers stay valid until a plan's fit vector changes size (jb_plan_set_fit), then
+ * jb_batch_host_buffers must be called again.  Replaces any binding made by jb_batch_bind.
+ */
+int jb_batch_host_buffers(jb_batch *batch, double **p_fit_pinned, double **out_pinned,
+                          int64_t *off_p, int64_t *off_out);
+int jb_batch_eval_pinned(jb_batch *batch);
 /* enable != 0: a plan whose trial point puts an unmasked pixel outside a knot grid does not fail the
  * batched host call; its loss comes back NaN (gradient undefined) and the caller decides -- an
  * optimiser's line search treats it as a rejected step (the reference's clamped gather, model.py:985,

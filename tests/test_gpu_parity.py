@@ -223,6 +223,35 @@ def test_batch_eval_host_equals_per_plan_results():
     with pytest.raises(ValueError, match="outside the knot grid"):
         batch.eval_host(bad)
     assert batch.eval_host(ps)[2][0] == refs[2][0]
+    # the same through the batch's own page-locked buffers (no staging copy): jb_batch_eval_pinned
+    p_views, out_views = batch.host_buffers()
+    assert [v.size for v in p_views] == [p.size for p in ps] and [v.size for v in out_views] == [p.size + 1 for p in ps]
+    for rep in range(2):
+        for v, p in zip(p_views, ps):
+            v[:] = p
+        batch.eval_pinned()
+        for (f, g), o in zip(refs, out_views):
+            assert o[0] == f and np.array_equal(o[1:], g)
+    p_views[1][0] += 1.0
+    with pytest.raises(ValueError, match="outside the knot grid"):
+        batch.eval_pinned()
+    p_views[1][0] -= 1.0
+    # eval_host and eval_pinned share the buffers and can alternate
+    assert batch.eval_host(ps)[0][0] == refs[0][0]
+    batch.eval_pinned()
+    assert out_views[2][0] == refs[2][0]
+    # a fit vector that changes size invalidates the views: the call says so, new views work
+    plans[0].spec.root.fix(); plans[0].spec.root.fit(0, 1)
+    plans[0].sync_from_model()
+    with pytest.raises(ValueError, match="changed size"):
+        batch.eval_pinned()
+    p_views, out_views = batch.host_buffers()
+    p0 = np.asarray(plans[0].spec.root.get_parameters())
+    for v, p in zip(p_views, [p0] + ps[1:]):
+        v[:] = p
+    batch.eval_pinned()
+    f0, g0 = plans[0].eval(p0)
+    assert out_views[0][0] == f0 and np.array_equal(out_views[0][1:], g0) and out_views[1][0] == refs[1][0]
     batch.close()
     for pl in plans:
         pl.close()
@@ -606,3 +635,41 @@ def test_pseudonormal_workflow_runs():
     f1 = loss.loss_all(np.asarray(model.get_parameters()), *data.blockify(), model, None, None)
     assert f1 < 0.5 * f0
     assert np.all(np.isfinite(jabble.quickplay.get_RV_error_fisher(model, data, rv_ind=[0, 0])))
+
+
+@pytest.mark.parametrize("E,P,chunk", [(2000, 4096, 0), (2000, 4096, 63), (3072, 8192, 0)])
+def test_full_size_chunk_vs_c_oracle(E, P, chunk):
+    """BASELINE.json's sizes, not a reduced case: one whole chunk of configs[3] (2000 epochs x 4096
+    pixels, first and last chunk of the 64) and a 3072-epoch slab of configs[4] (8192 pixels per row)
+    against the C oracle (itself pinned to the Python oracle and the golden vectors in
+    tests/test_oracle_c.py) -- loss, every gradient block and the RV Fisher information at 1e-10;
+    the float32 tier on the same chunk at 1e-5; the batched launch bit-identical to the single one."""
+    import os, subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")])
+    from oracle import c_oracle
+    ch = synth.make_chunk(chunk=chunk, n_epochs=E, n_pix=P, p_val=3)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, ofisher, _ = c_oracle.evaluate(p, dbd, mbd, model)
+    plan = engine.build_plan(model, db, mb)
+    val, grad = plan.eval(p)
+    assert plan.info()["fused_variant"] >= 0                   # the specialised kernel, as in the bench
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    assert rel_err(plan.fisher(0), ofisher[:E]) < TOL          # stellar shift is the first leaf
+    # size-independent property: the chunk is the sum of its epoch shards (configs[4]'s exchange step)
+    from wobble_jax_b200 import multigpu
+    loss = jabble.loss.ChiSquare()
+    fs, gs = 0.0, np.zeros_like(grad)
+    for rank in range(2):
+        shard = multigpu.EpochShardedObjective(loss, model, db, mb, rank, 2)
+        fs += shard.value(p); gs += shard.gradient(p)
+    assert abs(fs - val) <= 1e-12 * abs(val)
+    _check_grad(model, gs, grad, tol=1e-12)
+    # float32 tier at full size
+    p32 = engine.build_plan(model, db, mb, float32=True)
+    v32, g32 = p32.eval(p)
+    assert abs(v32 - oval) <= TOL32 * abs(oval)
+    _check_grad(model, g32, ograd, tol=TOL32)
+    p32.close(); plan.close()

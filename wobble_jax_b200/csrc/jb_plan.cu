@@ -1259,43 +1259,90 @@ int jb_batch_eval_device_checked(jb_batch* b, void* stream) {
     return batch_settle(b, st, false);
 }
 
-int jb_batch_eval_host_begin(jb_batch* b, const double* const* p_fit_host) {
-    if (!b || !p_fit_host) return fail(JB_ERR_BAD_ARG, "null argument");
-    JB_CUDA(cudaSetDevice(b->device));
+namespace {
+// (re)build the flat device buffers and their pinned host staging for the plans' current fit sizes
+int batch_host_bind(jb_batch* b) {
     const size_t n = b->plans.size();
     int rc0;
     if (b->host_bound)
         for (size_t i = 0; i < n; ++i)
             if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit) b->host_bound = false;   // a fit vector changed size
-    if (!b->host_bound) {     // (re)build the flat buffers for the plans' current fit sizes
-        JB_CUDA(cudaStreamSynchronize(b->stream));
-        if (b->d_flat_p) { cudaFree(b->d_flat_p); cudaFree(b->d_flat_out); cudaFreeHost(b->h_flat_p); cudaFreeHost(b->h_flat_out); }
-        if ((rc0 = batch_status_buffers(b))) return rc0;
-        b->off_p.assign(n + 1, 0); b->off_out.assign(n + 1, 0);
-        for (size_t i = 0; i < n; ++i) {
-            b->off_p[i + 1] = b->off_p[i] + b->plans[i]->n_fit;
-            b->off_out[i + 1] = b->off_out[i] + b->plans[i]->n_fit + 1;
-        }
-        const size_t np = (size_t)std::max<int64_t>(b->off_p[n], 1), no = (size_t)b->off_out[n];
-        JB_CUDA(cudaMalloc(&b->d_flat_p, np * sizeof(double)));
-        JB_CUDA(cudaMalloc(&b->d_flat_out, no * sizeof(double)));
-        JB_CUDA(cudaMallocHost(&b->h_flat_p, np * sizeof(double)));
-        JB_CUDA(cudaMallocHost(&b->h_flat_out, no * sizeof(double)));
-        b->p_fit.resize(n); b->out.resize(n);
-        for (size_t i = 0; i < n; ++i) { b->p_fit[i] = b->d_flat_p + b->off_p[i]; b->out[i] = b->d_flat_out + b->off_out[i]; }
-        b->dirty = true;
-        b->host_bound = true;
-    }
+    if (b->host_bound) return JB_OK;
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    if (b->d_flat_p) { cudaFree(b->d_flat_p); cudaFree(b->d_flat_out); cudaFreeHost(b->h_flat_p); cudaFreeHost(b->h_flat_out); }
+    b->d_flat_p = b->d_flat_out = b->h_flat_p = b->h_flat_out = nullptr;
+    if ((rc0 = batch_status_buffers(b))) return rc0;
+    b->off_p.assign(n + 1, 0); b->off_out.assign(n + 1, 0);
     for (size_t i = 0; i < n; ++i) {
-        if (b->plans[i]->n_fit && !p_fit_host[i]) return fail(JB_ERR_BAD_ARG, "null p_fit for plan %zu", i);
-        if (b->plans[i]->n_fit) memcpy(b->h_flat_p + b->off_p[i], p_fit_host[i], b->plans[i]->n_fit * sizeof(double));
+        b->off_p[i + 1] = b->off_p[i] + b->plans[i]->n_fit;
+        b->off_out[i + 1] = b->off_out[i] + b->plans[i]->n_fit + 1;
     }
+    const size_t np = (size_t)std::max<int64_t>(b->off_p[n], 1), no = (size_t)b->off_out[n];
+    JB_CUDA(cudaMalloc(&b->d_flat_p, np * sizeof(double)));
+    JB_CUDA(cudaMalloc(&b->d_flat_out, no * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&b->h_flat_p, np * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&b->h_flat_out, no * sizeof(double)));
+    b->p_fit.resize(n); b->out.resize(n);
+    for (size_t i = 0; i < n; ++i) { b->p_fit[i] = b->d_flat_p + b->off_p[i]; b->out[i] = b->d_flat_out + b->off_out[i]; }
+    b->dirty = true;
+    b->host_bound = true;
+    return JB_OK;
+}
+
+// pinned fit vectors -> device, one evaluation of every plan, [loss, gradient] -> pinned (all asynchronous)
+int batch_host_launch(jb_batch* b) {
+    const size_t n = b->plans.size();
     cudaStream_t st = b->stream;
     if (b->off_p[n]) JB_CUDA(cudaMemcpyAsync(b->d_flat_p, b->h_flat_p, b->off_p[n] * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = jb_batch_eval_device(b, st);
     if (rc) return rc;
     JB_CUDA(cudaMemcpyAsync(b->h_flat_out, b->d_flat_out, b->off_out[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return JB_OK;
+}
+}  // namespace
+
+int jb_batch_eval_host_begin(jb_batch* b, const double* const* p_fit_host) {
+    if (!b || !p_fit_host) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t n = b->plans.size();
+    int rc = batch_host_bind(b);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; ++i) {
+        if (b->plans[i]->n_fit && !p_fit_host[i]) return fail(JB_ERR_BAD_ARG, "null p_fit for plan %zu", i);
+        if (b->plans[i]->n_fit) memcpy(b->h_flat_p + b->off_p[i], p_fit_host[i], b->plans[i]->n_fit * sizeof(double));
+    }
+    if ((rc = batch_host_launch(b))) return rc;
     b->host_pending = true;
+    return JB_OK;
+}
+
+int jb_batch_host_buffers(jb_batch* b, double** p_fit_pinned, double** out_pinned, int64_t* off_p, int64_t* off_out) {
+    if (!b || !p_fit_pinned || !out_pinned || !off_p || !off_out) return fail(JB_ERR_BAD_ARG, "null argument");
+    if (b->host_pending) return fail(JB_ERR_BAD_ARG, "an evaluation is pending (jb_batch_eval_host_end)");
+    JB_CUDA(cudaSetDevice(b->device));
+    int rc = batch_host_bind(b);
+    if (rc) return rc;
+    const size_t n = b->plans.size();
+    *p_fit_pinned = b->h_flat_p; *out_pinned = b->h_flat_out;
+    for (size_t i = 0; i <= n; ++i) { off_p[i] = b->off_p[i]; off_out[i] = b->off_out[i]; }
+    return JB_OK;
+}
+
+int jb_batch_eval_pinned(jb_batch* b) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    if (b->host_pending) return fail(JB_ERR_BAD_ARG, "an evaluation is pending (jb_batch_eval_host_end)");
+    if (!b->host_bound || !b->h_flat_p) return fail(JB_ERR_BAD_ARG, "jb_batch_host_buffers has not been called");
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t n = b->plans.size();
+    for (size_t i = 0; i < n; ++i)
+        if (b->off_p[i + 1] - b->off_p[i] != b->plans[i]->n_fit)
+            return fail(JB_ERR_BAD_ARG, "the fit vector of plan %zu changed size: call jb_batch_host_buffers again", i);
+    int rc = batch_host_launch(b);
+    if (rc) return rc;
+    if ((rc = batch_settle(b, b->stream, true))) return rc;
+    if (!b->soft_range)
+        for (size_t i = 0; i < n; ++i)
+            if (!std::isfinite(b->h_flat_out[b->off_out[i]])) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
     return JB_OK;
 }
 

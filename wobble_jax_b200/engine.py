@@ -341,6 +341,26 @@ class Batch:
         _lib.check(self.lib.jb_batch_eval_host(self.handle, pf, po))
         return out_list
 
+    def host_buffers(self):
+        """The batch's page-locked host buffers as numpy views: ``(p_views, out_views)`` with
+        ``p_views[i]`` the fit vector of plan i (write it in place) and ``out_views[i]`` its
+        [loss, gradient] after ``eval_pinned`` (read in place: the next evaluation overwrites it).
+        Valid until a plan's fit vector changes size; then ask again."""
+        n = len(self.plans)
+        hp, ho = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        off_p, off_o = (C.c_int64 * (n + 1))(), (C.c_int64 * (n + 1))()
+        _lib.check(self.lib.jb_batch_host_buffers(self.handle, C.byref(hp), C.byref(ho), off_p, off_o))
+        flat_p = np.ctypeslib.as_array(hp, shape=(max(off_p[n], 1),))
+        flat_o = np.ctypeslib.as_array(ho, shape=(off_o[n],))
+        self._pinned = (flat_p, flat_o)
+        return ([flat_p[off_p[i]:off_p[i + 1]] for i in range(n)],
+                [flat_o[off_o[i]:off_o[i + 1]] for i in range(n)])
+
+    def eval_pinned(self):
+        """Evaluate every plan from / into the ``host_buffers`` views: one H2D copy, one launch per
+        kernel, one D2H copy, one synchronisation -- and no staging copy on the host."""
+        _lib.check(self.lib.jb_batch_eval_pinned(self.handle))
+
     def soft_range(self, enable=True):
         """Out-of-range plans give a NaN loss in ``eval_host`` instead of failing the whole call."""
         _lib.check(self.lib.jb_batch_soft_range(self.handle, int(bool(enable))))
@@ -504,7 +524,7 @@ class LockstepEvaluator:
 
     def request(self, i, p):
         with self.cv:
-            self.pending[i] = np.ascontiguousarray(p, dtype=np.float64).reshape(-1).copy()
+            self.pending[i] = np.array(p, dtype=np.float64).reshape(-1)
             if set(self.pending) >= self.active:
                 self._flush()
             else:
@@ -524,11 +544,15 @@ class LockstepEvaluator:
     def _flush(self):          # called with the lock held, by the thread whose request completed the set
         idx = tuple(sorted(self.pending))
         try:
-            batch = self.batches.get(idx)
-            if batch is None:
-                batch = self.batches[idx] = Batch([self.objs[i].plan for i in idx])
+            entry = self.batches.get(idx)
+            if entry is None:
+                batch = Batch([self.objs[i].plan for i in idx])
                 batch.soft_range(True)
-            outs = batch.eval_host([self.pending[i] for i in idx])
+                entry = self.batches[idx] = (batch,) + batch.host_buffers()
+            batch, p_views, outs = entry
+            for v, i in zip(p_views, idx):
+                v[:] = self.pending[i]
+            batch.eval_pinned()
             for i, o in zip(idx, outs):
                 if np.isfinite(o[0]):
                     self.results[i] = (float(o[0]), o[1:].copy())
@@ -542,8 +566,8 @@ class LockstepEvaluator:
         self.cv.notify_all()
 
     def close(self):
-        for b in self.batches.values():
-            b.close()
+        for entry in self.batches.values():
+            entry[0].close()
         self.batches.clear()
         for o in self.objs:
             o._data_eval = o.plan.eval
