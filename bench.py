@@ -314,8 +314,7 @@ def run_b200(args, rank, world, local_rank):
             v[:] = p
 
     def eval_host_pinned():
-        for v in pin_p:
-            v += 1e-13
+        batch._pinned[0][...] += 1e-13        # all fit vectors (they lie back to back in the pinned buffer)
         batch.eval_pinned()
         return [float(o[0]) for o in pin_out]
 

@@ -673,3 +673,21 @@ def test_full_size_chunk_vs_c_oracle(E, P, chunk):
     assert abs(v32 - oval) <= TOL32 * abs(oval)
     _check_grad(model, g32, ograd, tol=TOL32)
     p32.close(); plan.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_cardinal_basis_and_vmap_model_vs_golden(n):
+    """CardinalSplineKernel.__call__ (cardinalspline.py:44-55) and cardinal_vmap_model
+    (model.py:951-989) through the CUDA forward kernel, against the reference's own outputs."""
+    g = load_golden("basis.npz")
+    kernel = jabble.cardinalspline.CardinalSplineKernel(n)
+    t = g["t"]
+    B = kernel(t)
+    assert B.shape == t.shape
+    assert np.max(np.abs(B - g[f"B_{n}"])) <= 1e-12 * np.max(np.abs(g[f"B_{n}"]))
+    assert kernel(np.array([[0.0, 10.0], [-7.5, 0.25]])).shape == (2, 2) and kernel(10.0) == 0.0
+    y = jabble.model.cardinal_vmap_model(g["spline_x"], g["spline_xp"], g[f"spline_{n}_ap"], kernel, (n + 1) / 2)
+    assert rel_err(y, g[f"spline_{n}_y"]) < TOL
+    shuffled = np.random.default_rng(0).permutation(len(g["spline_x"]))
+    y2 = jabble.model.cardinal_vmap_model(g["spline_x"][shuffled], g["spline_xp"], g[f"spline_{n}_ap"], n)
+    assert np.array_equal(y2, y[shuffled])

@@ -202,3 +202,53 @@ def test_summary_files_and_load_model_dir(tmp_path):
     rv_array2, _, table2, _ = qp.load_model_dir(str(tmp_path), files)
     assert np.array_equal(rv_array2["RV_comb"], rv_array["RV_comb"])
     assert np.array_equal(table2["Loss_Avg"], table["Loss_Avg"])
+
+
+def test_loss_save_load_round_trip(tmp_path):
+    """jabble.loss.save / load (loss.py:10-24, 87-92, 143-161, 201-208): the terms, their order,
+    coefficients, constants and index paths; group names ``<Class>_<n>`` as in the reference."""
+    from wobble_jax_b200 import store
+    L = jabble.loss
+    loss = L.ChiSquare() + 3.0 * L.L2Reg([0, 1], constant=0.5) + L.L1Reg([1, 1]) * 2.0 + 0.5 * L.L2Loss()
+    path = str(tmp_path / "loss.h5")
+    L.save(path, loss)
+    with store.File(path, "r") as hf:
+        assert list(hf.keys()) == ["LossSequential"]
+        assert list(hf["LossSequential"].keys()) == ["ChiSquare_0", "L2Reg_0", "L1Reg_0", "L2Loss_0"]
+        assert set(hf["LossSequential"]["L2Reg_0"].keys()) == {"coeff", "const", "submodel_inds"}
+    (back,) = L.load(path)
+    assert repr(back) == repr(loss)
+    assert [type(t) for t in back.loss_funcs] == [L.ChiSquare, L.L2Reg, L.L1Reg, L.L2Loss]
+    assert back.loss_funcs[1].constant == 0.5 and back.loss_funcs[1].submodel_inds == [0, 1]
+    assert back.loss_funcs[2].coefficient == 2.0 and back.loss_funcs[3].coefficient == 0.5
+    L.save(path, L.ChiSquare() * 2.5)
+    (single,) = L.load(path)
+    assert type(single) is L.ChiSquare and single.coefficient == 2.5
+    # the regularisers' row-level values (loss.py:197-199, 219-222)
+    ch = synth.make_chunk(chunk=0, n_epochs=4, n_pix=150, p_val=3, n_lines=3)
+    model = synth.fit_all(ch.model)
+    p = np.asarray(model.get_parameters())
+    reg = back.loss_funcs[1]
+    reg.ready_indices(model)
+    np.testing.assert_allclose(reg(p, None, None, model), 3.0 * 0.5 * (p[reg.indices] - 0.5) ** 2)
+    l1 = back.loss_funcs[2]
+    l1.ready_indices(model)
+    np.testing.assert_allclose(l1(p, None, None, model), 2.0 * np.abs(p[l1.indices]))
+
+
+def test_cardinal_spline_kernel_tables_match_reference_golden():
+    """cardinalspline.py:6-42: the alphas tables of CardinalSplineKernel(n), n = 0..4, and
+    _alpha_recursion entry by entry, against the reference's own (tests/golden/basis.npz); the
+    known answers of SURVEY.md section 8 a1."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "basis.npz"))
+    cs = jabble.cardinalspline
+    for n in range(5):
+        k = cs.CardinalSplineKernel(n)
+        assert k.n == n and np.array_equal(k.alphas, g[f"alphas_{n}"])
+        for j in range(n + 1):
+            for kk in range(n + 1):
+                assert cs._alpha_recursion(j, kk, n + 1) == g[f"alphas_{n}"][j, kk]
+    assert np.array_equal(cs.CardinalSplineKernel(1).alphas, [[0, 2], [1, -1]])
+    assert np.array_equal(cs.CardinalSplineKernel(2).alphas, [[0, -3, 9], [0, 6, -6], [1, -2, 1]])
+    assert np.array_equal(cs.CardinalSplineKernel(3).alphas,
+                          [[0, 4, -44, 64], [0, -12, 60, -48], [0, 12, -24, 12], [1, -3, 3, -1]])

@@ -16,6 +16,29 @@ the sum.
 import numpy as np
 
 
+def load(filename):
+    """loss.py:10-18 -- the list of losses saved in ``filename`` (one per top-level group)."""
+    from . import store
+    out = []
+    with store.File(filename, "r") as hf:
+        for key in hf.keys():
+            obj_name = key.split("_")[0]
+            if obj_name in _SAVED_CLASSES:
+                out.append(_SAVED_CLASSES[obj_name].load(hf[key]))
+    return out
+
+
+def save(filename, loss):
+    """loss.py:20-24 -- group ``<Class>`` holding the loss (HDF5 with h5py, else the .npz mirror)."""
+    from . import store
+    with store.File(filename, "w") as hf:
+        loss.save(hf.create_group(loss.__class__.__name__))
+
+
+def _row_field(datarow, key):
+    return np.asarray(datarow[key] if not hasattr(datarow, key) else getattr(datarow, key))
+
+
 class LossFunc:
     """loss.py:27-92."""
 
@@ -50,6 +73,16 @@ class LossFunc:
         from . import engine
         return engine.Objective.cached(self, model, datablock, metablock).gradient(p)
 
+    def save(self, group):
+        """loss.py:87-88."""
+        group.create_dataset("coeff", data=self.coefficient)
+
+    @classmethod
+    def load(cls, group):
+        """loss.py:90-92 -- the class is named by the group (``ChiSquare_0`` -> ChiSquare)."""
+        obj_name = group.name.split("/")[-1].split("_")[0]
+        return _SAVED_CLASSES[obj_name]() * float(group["coeff"][()])
+
 
 class ChiSquare(LossFunc):
     """loss.py:164-173 -- inverse-variance chi-square."""
@@ -64,6 +97,12 @@ class ChiSquare(LossFunc):
 
 class L2Loss(LossFunc):
     """loss.py:175-184 -- unweighted squared residuals: coef * where(~mask, (ys - model)**2, 0)."""
+
+    def __call__(self, p, datarow, metarow, model, margs=()):
+        """Per-pixel loss of one row: (P,) array (the model row comes from the CUDA forward)."""
+        m = model(p, _row_field(datarow, "xs"), metarow, margs)
+        return self.coefficient * np.where(~_row_field(datarow, "mask").astype(bool),
+                                           (_row_field(datarow, "ys") - m) ** 2, 0.0)
 
 
 class L2Reg(LossFunc):
@@ -87,6 +126,25 @@ class L2Reg(LossFunc):
         g[self.indices] = self.coefficient * d
         return self.coefficient * 0.5 * float(np.sum(d * d)), g
 
+    def __call__(self, p, datarow, metarow, model, margs=()):
+        """loss.py:197-199 -- one entry per regularised parameter (``ready_indices`` first)."""
+        p = np.asarray(p, dtype=np.float64)
+        return self.coefficient * 0.5 * (p[self.indices] - self.constant) ** 2
+
+    def save(self, group):
+        """loss.py:201-204."""
+        group.create_dataset("coeff", data=self.coefficient)
+        group.create_dataset("const", data=self.constant)
+        group.create_dataset("submodel_inds", data=np.asarray(self.submodel_inds))
+
+    @classmethod
+    def load(cls, group):
+        """loss.py:206-208."""
+        obj_name = group.name.split("/")[-1].split("_")[0]
+        inds = np.asarray(group["submodel_inds"][()])
+        inds = [int(i) for i in inds.reshape(-1)] if inds.dtype.kind in "iu" else bool(inds)
+        return _SAVED_CLASSES[obj_name](constant=float(group["const"][()]), submodel_inds=inds) * float(group["coeff"][()])
+
     def __repr__(self):
         return str(self.coefficient) + " {obj.__class__.__name__}".format(obj=self) + "({obj.submodel_inds})".format(obj=self)
 
@@ -99,6 +157,11 @@ class L1Reg(L2Reg):
         g = np.zeros_like(p)
         g[self.indices] = self.coefficient * np.sign(d)
         return self.coefficient * float(np.sum(np.abs(d))), g
+
+    def __call__(self, p, datarow, metarow, model, margs=()):
+        """loss.py:219-222."""
+        p = np.asarray(p, dtype=np.float64)
+        return self.coefficient * np.abs(p[self.indices] - self.constant)
 
 
 class LossSequential(LossFunc):
@@ -130,5 +193,29 @@ class LossSequential(LossFunc):
         for loss in self.loss_funcs:
             loss.ready_indices(model)
 
+    def __call__(self, p, datarow, metarow, model, margs=()):
+        """loss.py:100-105 -- the scalar sum of every term over one row."""
+        return sum(float(np.sum(loss(p, datarow, metarow, model, margs))) for loss in self.loss_funcs)
+
+    def save(self, hf):
+        """loss.py:143-150 -- one sub-group ``<Class>_<n>`` per term, in order."""
+        iteration = 0
+        for loss in self.loss_funcs:
+            while loss.__class__.__name__ + f"_{iteration}" in hf.keys():
+                iteration += 1
+            loss.save(hf.create_group(loss.__class__.__name__ + f"_{iteration}"))
+
+    @classmethod
+    def load(cls, hf):
+        """loss.py:152-161."""
+        terms = []
+        for group_key in hf.keys():
+            obj_name = hf[group_key].name.split("/")[-1].split("_")[0]
+            terms.append(_SAVED_CLASSES[obj_name].load(hf[group_key]))
+        return cls(terms)
+
     def __repr__(self):
         return " + ".join(repr(loss) for loss in self.loss_funcs)
+
+
+_SAVED_CLASSES = {c.__name__: c for c in (LossFunc, ChiSquare, L2Loss, L2Reg, L1Reg, LossSequential)}

@@ -56,6 +56,22 @@ def spline_alphas(n):
                           for i in range(k + 1)) for k in range(n + 1)] for j in range(n + 1)], dtype=np.float64)
 
 
+def cardinal_vmap_model(x, xp, ap, basis, a=None):
+    """model.py:951-989 -- ``y(x) = sum_k ap[idx - k] * basis(frac + k)`` on the evenly spaced knots
+    ``xp``: the CUDA forward kernel on a one-row plan (``jb_plan_forward``).  ``basis`` is a
+    ``CardinalSplineKernel`` (or its degree); ``a`` (half the support) follows from the degree and
+    is accepted for the reference's signature.  An ``x`` whose taps leave the knot grid raises
+    ``ValueError`` where the reference clamps the gather (model.py:985)."""
+    p_val = int(getattr(basis, "n", basis))
+    x = np.asarray(x, dtype=np.float64)
+    flat = x.reshape(-1)
+    order = np.argsort(flat, kind="stable")
+    spline = CardinalSplineMixture(np.asarray(xp, dtype=np.float64), p_val, p=np.asarray(ap, dtype=np.float64))
+    out = np.empty(flat.shape)
+    out[order] = spline([], flat[order], {})
+    return out.reshape(x.shape)
+
+
 def load(filename):
     """model.py:35-54 -- rebuild a saved model tree (and its metadata)."""
     from . import store
