@@ -897,9 +897,10 @@ struct ReduceParams {
     // plan does not compute it
     int nq;
     int rq[kMaxComp][3];
-    double* tmp;        // [n_comp][n_groups][max_knots]
-    double* rowsum;     // [E][NQ]
+    double* tilepart;   // [n_comp][n_tiles][max_knots]: per-tile sums over the row groups (k_reduce_stage1)
+    int* tile_rng;      // [n_comp][n_tiles][2]: the knots [lo, hi) of tilepart that are valid
     int64_t max_knots;
+    double* rowsum;     // [E][NQ]
     double coef;
     double* grad_all; double* fisher_all;
     const int64_t* fit_map; int64_t n_fit;
@@ -907,69 +908,78 @@ struct ReduceParams {
     int* status;
 };
 
-// blocks [0, nb_ctrl): tmp[c][g][k] = sum over tiles of the group, in tile order, of the windows
-// covering knot k.  blocks [nb_ctrl, ...): rowsum[r][q] = sum over tiles of rowpart.
+// Gradient of the control points.  A task (row group g, tile t) leaves a window of `wincap` knot sums
+// in `part`; the windows of one tile start at nearly the same knot in every group (the groups differ
+// by their rows' shifts only).  Blocks [0, nb_ctrl) of k_reduce_stage1, one per (component, tile): a
+// thread owns one knot of the union of the tile's windows and adds, in group order, the element of
+// every group's window that lies on it -- one predicated load per (knot, group), all independent,
+// every element of `part` read exactly once.  The result, tilepart[c][t][knot] on the knots
+// [tile_rng[c][t][0], tile_rng[c][t][1]), is a few hundred doubles per tile; k_reduce_stage2 adds
+// the (one to three) tiles that cover a knot in tile order.  One fixed order throughout.
+constexpr int kRedSlab = 256;      // threads per block of the reducers
+constexpr int kRedBases = 2048;    // window bases of one tile held in shared memory at a time
+
+// blocks [0, nb_ctrl): tilepart (above).  blocks [nb_ctrl, ...): rowsum[r][q] = sum over tiles of rowpart.
 __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int* __restrict__ off, int n) {
-    extern __shared__ double sacc[];     // [max_knots] of the launch
     const int pi = find_plan(off, n, blockIdx.x);
     const ReduceParams& a = arr[pi];
     const int blk = blockIdx.x - off[pi];
-    const int nb_ctrl = a.nb_ctrl;       // = n_comp * n_groups: one block per (component, row group)
+    const int nb_ctrl = a.nb_ctrl;       // = n_comp * n_tiles
     const int NQ = a.nq;
     if (blk < nb_ctrl) {
-        // tmp[c][g][:] = sum over the group's tasks, in tile order, of their gradient windows: the
-        // windows of consecutive tiles overlap, so the block adds them one tile at a time into a
-        // shared-memory copy of the knot axis (distinct addresses within a tile, a barrier between
-        // tiles): coalesced reads of `part`, no scan, one fixed order.
-        const int g = blk % a.n_groups;
-        const int c = blk / a.n_groups;
+        __shared__ int sb[kRedBases];
+        __shared__ int s_lo, s_hi;
+        const int NT = a.n_tiles, W = a.wincap, n_groups = a.n_groups;
+        const int c = blk / NT, t = blk - c * NT;
         const int M = a.comp[c].n_knots;
-        for (int k = threadIdx.x; k < M; k += blockDim.x) sacc[k] = 0.0;
+        const int* __restrict__ bases = a.part_base + (int64_t)c * a.n_tasks + t;      // group g at [g * NT]
+        const double* __restrict__ part = a.part + ((int64_t)c * a.n_tasks + t) * W;   // group g at [g * NT * W]
+        const int64_t gstride = (int64_t)NT * W;
+        if (threadIdx.x == 0) { s_lo = INT_MAX; s_hi = -1; }
         __syncthreads();
-        // Windows of tiles two apart normally do not overlap (a tile is wider than the window's
-        // margin): then all even tiles are added at once (disjoint addresses, every load of the
-        // block in flight together), a barrier, then all odd tiles.  Otherwise one tile at a time.
-        // Either way each knot sums its contributions in one fixed order.
-        __shared__ int sbase[256];
-        __shared__ int s_disjoint;
-        const int NT = a.n_tiles;
-        const int64_t task0 = (int64_t)c * a.n_tasks + (int64_t)g * NT;
-        if (threadIdx.x == 0) s_disjoint = NT <= 256 ? 1 : 0;
-        __syncthreads();
-        if (NT <= 256) {
-            for (int t = threadIdx.x; t < NT; t += blockDim.x) sbase[t] = a.part_base[task0 + t];
-            __syncthreads();
-            for (int t = threadIdx.x; t + 2 < NT; t += blockDim.x) {
-                // the next valid tile of the same parity must start behind this tile's window
-                if (sbase[t] == INT_MAX) continue;
-                int u = t + 2;
-                while (u < NT && sbase[u] == INT_MAX) u += 2;
-                if (u < NT && sbase[u] - sbase[t] < a.wincap) s_disjoint = 0;
+        {   // the union of the tile's windows over the groups
+            int lo = INT_MAX, hi = -1;
+            for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+                const int base = bases[(int64_t)g * NT];
+                if (base != INT_MAX) { lo = min(lo, base); hi = max(hi, base); }
             }
-            __syncthreads();
+            if (hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
         }
-        if (s_disjoint) {
-            for (int par = 0; par < 2; ++par) {
-                const int n_par = (NT - par + 1) / 2;              // tiles par, par+2, ...
-                for (int e = threadIdx.x; e < n_par * a.wincap; e += blockDim.x) {
-                    const int t = par + 2 * (e / a.wincap), w = e % a.wincap;
-                    const int base = sbase[t];
-                    if (base != INT_MAX && base + w < M) sacc[base + w] += a.part[(task0 + t) * a.wincap + w];
+        __syncthreads();
+        const int k_lo = s_lo, k_hi = s_hi < 0 ? -1 : min(s_hi + W, M);    // knots [k_lo, k_hi)
+        if (threadIdx.x == 0) {
+            a.tile_rng[2 * blk] = s_hi < 0 ? 0 : k_lo;
+            a.tile_rng[2 * blk + 1] = s_hi < 0 ? 0 : k_hi;
+        }
+        if (s_hi < 0) return;
+        double* __restrict__ dst = a.tilepart + (int64_t)blk * a.max_knots;
+        for (int kb = k_lo; kb < k_hi; kb += blockDim.x) {          // normally one pass
+            const int k = kb + (int)threadIdx.x;
+            double s = 0.0;
+            for (int g0 = 0; g0 < n_groups; g0 += kRedBases) {      // normally one pass
+                const int ng = min(kRedBases, n_groups - g0);
+                __syncthreads();
+                for (int g = threadIdx.x; g < ng; g += blockDim.x) sb[g] = bases[(int64_t)(g0 + g) * NT];
+                __syncthreads();
+                const double* __restrict__ pg = part + (int64_t)g0 * gstride;
+                int g = 0;
+                for (; g + 7 < ng; g += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const unsigned w = (unsigned)(k - sb[g + u]);       // no window (INT_MAX): wraps far above W
+                        v[u] = w < (unsigned)W ? __ldg(pg + (int64_t)(g + u) * gstride + w) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s += v[u];
                 }
-                __syncthreads();
+                for (; g < ng; ++g) {
+                    const unsigned w = (unsigned)(k - sb[g]);
+                    s += w < (unsigned)W ? __ldg(pg + (int64_t)g * gstride + w) : 0.0;
+                }
             }
-        } else {
-            for (int t = 0; t < NT; ++t) {
-                const int base = a.part_base[task0 + t];      // uniform over the block
-                if (base == INT_MAX) continue;
-                const double* src = a.part + (task0 + t) * a.wincap;
-                for (int w = threadIdx.x; w < a.wincap; w += blockDim.x)
-                    if (base + w < M) sacc[base + w] += src[w];
-                __syncthreads();
-            }
+            if (k < k_hi) dst[k] = s;
         }
-        double* dst = a.tmp + ((int64_t)c * a.n_groups + g) * a.max_knots;
-        for (int k = threadIdx.x; k < M; k += blockDim.x) dst[k] = sacc[k];
     } else if (blk < nb_ctrl + a.nb_stage1_rows) {
         const int64_t i = (int64_t)(blk - nb_ctrl) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * NQ) return;
@@ -1012,9 +1022,15 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
                 a.grad_all[a.norm_ctrl_off + i] = -a.coef * s;
                 return;
             }
+            // control point i of template c: the tiles whose windows cover it, in tile order
+            const int NT = a.n_tiles;
+            const int* __restrict__ rng = a.tile_rng + 2 * c * NT;
+            const double* __restrict__ tp = a.tilepart + (int64_t)c * NT * a.max_knots + i;
             double s = 0.0;
-#pragma unroll 8
-            for (int g = 0; g < a.n_groups; ++g) s += a.tmp[((int64_t)c * a.n_groups + g) * a.max_knots + i];
+            for (int t = 0; t < NT; ++t) {
+                const int2 r = *reinterpret_cast<const int2*>(rng + 2 * t);
+                if ((int)i >= r.x && (int)i < r.y) s += tp[(int64_t)t * a.max_knots];
+            }
             a.grad_all[a.ctrl_off[c] + i] = -a.coef * s;
             return;
         }

@@ -101,6 +101,7 @@ struct jb_plan {
     int G = 0, n_groups = 0, wincap = 0;
     int64_t n_tasks = 0;
     double *d_part = nullptr, *d_rowpart = nullptr, *d_tmp = nullptr, *d_rowsum = nullptr, *d_losspart = nullptr;
+    int* d_tile_rng = nullptr;
     double *d_normpart = nullptr, *d_normrow = nullptr;
     int norm_stride = 0;
     int* d_part_base = nullptr;
@@ -191,7 +192,6 @@ int alloc_scratch(jb_plan* pl) {
     if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_glob * pl->n_tasks * pl->wincap, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_glob * pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_losspart, (size_t)pl->n_tasks, true))) return rc;
-    if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_glob * pl->n_groups * pl->max_knots, true))) return rc;
     pl->pack_dirty = true;
     return JB_OK;
 }
@@ -311,7 +311,8 @@ int refresh_pack(jb_plan* pl) {
     }
     rp.n_rows = pl->E; rp.n_tasks = pl->n_tasks; rp.n_tiles = pl->n_tiles; rp.n_groups = pl->n_groups; rp.wincap = pl->wincap;
     rp.part = pl->d_part; rp.part_base = pl->d_part_base; rp.rowpart = pl->d_rowpart; rp.losspart = pl->d_losspart;
-    rp.tmp = pl->d_tmp; rp.rowsum = pl->d_rowsum; rp.max_knots = pl->max_knots;
+    rp.tilepart = pl->d_tmp; rp.tile_rng = pl->d_tile_rng; rp.max_knots = pl->max_knots;
+    rp.rowsum = pl->d_rowsum;
     rp.coef = pl->coef;
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
     rp.fit_map = pl->d_fit_map; rp.n_fit = pl->n_fit;
@@ -330,7 +331,7 @@ int refresh_pack(jb_plan* pl) {
             for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, fl, c, q);
     }
     rp.nq = NQ;
-    rp.nb_ctrl = pl->n_groups * pl->n_glob;
+    rp.nb_ctrl = pl->n_glob * pl->n_tiles;
     rp.nb_stage1_rows = (int)((pl->E * NQ + 255) / 256);
     int64_t n2 = 0;
     for (int c = 0; c < pl->n_comp; ++c)
@@ -486,12 +487,7 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
         prof->prof_used++;
         prof->prof_stream = st;
     }
-    {
-        const size_t smem1 = (size_t)L.max_knots * sizeof(double);
-        if (smem1 > 200 * 1024) return fail(JB_ERR_UNSUPPORTED, "%lld knots per template (the reducer holds one knot axis in shared memory)", (long long)L.max_knots);
-        JB_CUDA(cudaFuncSetAttribute(jb::k_reduce_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
-        jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], 256, smem1, st>>>(L.re, L.off[K_STAGE1], L.n);
-    }
+    jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], jb::kRedSlab, 0, st>>>(L.re, L.off[K_STAGE1], L.n);
     jb::k_reduce_stage2<<<(unsigned)L.total[K_STAGE2], 256, 0, st>>>(L.re, L.off[K_STAGE2], L.n);
     jb::k_finish<<<(unsigned)L.total[K_FINISH], 1024, 0, st>>>(L.re, L.off[K_FINISH], L.n, out_override);
     JB_CUDA(cudaGetLastError());
@@ -625,6 +621,8 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->E = E; pl->P = P;
     pl->ppad = (P + jb::kTile - 1) / jb::kTile * jb::kTile;
     pl->n_tiles = (int)(pl->ppad / jb::kTile);
+    if (pl->n_tiles > jb::kRedBases)
+        return fail(JB_ERR_UNSUPPORTED, "%lld pixels per row (at most %d)", (long long)pl->P, jb::kRedBases * jb::kTile);
     pl->has_data = d->ys != nullptr;
     pl->coef = d->coefficient;
     pl->general_only = (d->flags & JB_PLAN_GENERAL_KERNEL) != 0;
@@ -868,6 +866,8 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->G = choose_rows_per_group(E, pl->n_tiles, d->rows_per_group);
     if ((rc = dev_alloc(pl, &pl->d_rowpart, (size_t)E * pl->n_tiles * NQ, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_rowsum, (size_t)E * NQ, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_tmp, (size_t)pl->n_glob * pl->n_tiles * pl->max_knots, true))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_tile_rng, (size_t)2 * pl->n_glob * pl->n_tiles, true))) return rc;
     if ((rc = alloc_scratch(pl))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_status, 2))) return rc;
     JB_CUDA(cudaMemset(pl->d_status, 0, 2 * sizeof(int)));
