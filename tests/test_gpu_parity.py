@@ -691,3 +691,44 @@ def test_cardinal_basis_and_vmap_model_vs_golden(n):
     shuffled = np.random.default_rng(0).permutation(len(g["spline_x"]))
     y2 = jabble.model.cardinal_vmap_model(g["spline_x"][shuffled], g["spline_xp"], g[f"spline_{n}_ap"], n)
     assert np.array_equal(y2, y[shuffled])
+
+
+def test_reducer_with_more_row_groups_than_one_shared_memory_batch():
+    """k_reduce_stage1 holds the window bases of 2048 row groups at a time: 2300 rows in groups of one
+    make it stream two batches; wide RV spread makes the union of a tile's windows wider than one block
+    of threads.  Against the C oracle, and the same numbers as with the default grouping to 1e-12."""
+    import os, subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")])
+    from oracle import c_oracle
+    ch = synth.make_chunk(chunk=2, n_epochs=2300, n_pix=300, p_val=3, n_lines=8)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, _, _ = c_oracle.evaluate(p, dbd, mbd, model)
+    ref = engine.build_plan(model, db, mb)
+    rval, rgrad = ref.eval(p)
+    plan = engine.build_plan(model, db, mb, rows_per_group=1)
+    assert plan.info()["n_tasks"] >= 2300 * 3
+    val, grad = plan.eval(p)
+    for v, g in ((rval, rgrad), (val, grad)):
+        assert abs(v - oval) <= TOL * abs(oval)
+        _check_grad(model, g, ograd)
+    assert abs(val - rval) <= 1e-12 * abs(rval)
+    _check_grad(model, grad, rgrad, tol=1e-12)
+    plan.close(); ref.close()
+
+
+def test_reducer_with_windows_wider_than_a_block():
+    """Coarse pixels (1.7 knots each): a tile's windows are 256 knots wide, their union over the row
+    groups wider than the 256 threads of a reducer block, which then walks it in two passes."""
+    ch = synth.make_chunk(chunk=6, n_epochs=60, n_pix=500, p_val=3, n_lines=8, pixel_step=1.7 * 4.3478e-6)
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd = O.loss_and_grad(p, dbd, mbd, model)
+    for G in (0, 3):
+        plan = engine.build_plan(model, db, mb, rows_per_group=G)
+        val, grad = plan.eval(p)
+        assert abs(val - oval) <= TOL * abs(oval)
+        _check_grad(model, grad, ograd)
+        plan.close()
