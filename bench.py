@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--chunks", type=int, default=64, help="chunks per GPU")
     ap.add_argument("--float32", action="store_true",
                     help="the float32 tier (JB_PLAN_FLOAT32: float records, k_fused32; 13 B/pixel) instead of float64")
-    ap.add_argument("--epochs", type=int, default=2000)
-    ap.add_argument("--pixels", type=int, default=4096)
+    ap.add_argument("--epochs", type=int, default=None, help="default: 2000 (chunks workload), 50000 (epochs workload)")
+    ap.add_argument("--pixels", type=int, default=None, help="default: 4096 (chunks workload), 8192 (epochs workload)")
     ap.add_argument("--p-val", type=int, default=3)
     ap.add_argument("--rows-per-group", type=int, default=0)
     ap.add_argument("--e2e", default="pinned", choices=["pinned", "batch", "threads"],
@@ -55,7 +55,13 @@ def parse():
                     help="chunks: BASELINE configs[3] (default, the metric's config); epochs: configs[4], one chunk "
                          "of --epochs x --pixels sharded by epoch over the ranks with an NCCL all-reduce of the "
                          "loss and control-point gradients")
-    return ap.parse_args()
+    args = ap.parse_args()
+    big = args.workload == "epochs"          # BASELINE.json configs[4]: one chunk of 50000 epochs x 8192 px
+    if args.epochs is None:
+        args.epochs = 50000 if big else 2000
+    if args.pixels is None:
+        args.pixels = 8192 if big else 4096
+    return args
 
 
 def measured_peaks():
