@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--rows-per-group", type=int, default=0)
     ap.add_argument("--e2e", default="pinned", choices=["pinned", "batch", "threads"],
                     help="host-buffer path of the end-to-end leg (chunks workload)")
+    ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches in flight in the pinned end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget")
     ap.add_argument("--workload", default="chunks", choices=["chunks", "epochs"],
@@ -318,15 +319,25 @@ def run_b200(args, rank, world, local_rank):
 
     if e2e_path == "pinned":
         # the batch's own page-locked host buffers: the fit vectors are written there (as the optimiser
-        # threads of model.optimize_many do), one H2D copy, the evaluation, one D2H copy, read in place
-        pin_p, pin_out = batch.host_buffers()
-        for v, p in zip(pin_p, p_host):
+        # threads of model.optimize_many do), one H2D copy, the evaluation, one D2H copy, read in place.
+        # The chunks go as two half-batches on two streams (begin, begin, end, end): the copies of one
+        # half overlap the kernels of the other.
+        nparts = max(1, min(args.e2e_parts, len(plans)))
+        cuts = [len(plans) * i // nparts for i in range(nparts + 1)]
+        halves = [engine.Batch(plans[cuts[i]:cuts[i + 1]]) for i in range(nparts)]
+        pins = [hb.host_buffers() for hb in halves]
+        pin_out = [o for _, outs_ in pins for o in outs_]
+        for v, p in zip([v for vs, _ in pins for v in vs], p_host):
             v[:] = p
 
     def eval_host_pinned():
-        batch._pinned[0][::61] += 1e-13       # every step's inputs differ (a stride through all the fit vectors,
+        for hb in halves:
+            hb._pinned[0][::61] += 1e-13      # every step's inputs differ (a stride through all the fit vectors,
                                               # which lie back to back in the pinned buffer); all of it is copied
-        batch.eval_pinned()
+        for hb in halves:
+            hb.eval_pinned_begin()
+        for hb in halves:
+            hb.eval_pinned_end()
         return [float(o[0]) for o in pin_out]
 
     with ThreadPoolExecutor(min(16, args.chunks)) as pool:
@@ -373,8 +384,9 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps,
                 "api": {"threads": "jb_plan_eval (host p_fit in, host loss+gradient out), 16 host threads over the chunks",
                         "batch": "jb_batch_eval_host (host fit vectors in, host loss+gradient out, all chunks of the rank in one call, one host thread)",
-                        "pinned": "jb_batch_host_buffers + jb_batch_eval_pinned (fit vectors written into / [loss, gradient] read from the "
-                                  "batch's page-locked host buffers; one H2D copy, 6 launches, one D2H copy, one sync per step)"}[e2e_path],
+                        "pinned": "jb_batch_host_buffers + jb_batch_eval_pinned_begin/_end (fit vectors written into / [loss, gradient] "
+                                  "read from the batch's page-locked host buffers; the chunks as two half-batches on two streams, "
+                                  "each one H2D copy, 6 launches, one D2H copy, one sync per step)"}[e2e_path],
                 "host_cores_per_rank": cores_per_rank},
         "device_api": "jb_batch_eval_device: 6 launches per step for all chunks of the GPU",
         "gpu_launches": int(launches),

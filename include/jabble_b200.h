@@ -233,6 +233,11 @@ int jb_batch_eval_host_end(jb_batch *batch, double *const *out_host);
 int jb_batch_host_buffers(jb_batch *batch, double **p_fit_pinned, double **out_pinned,
                           int64_t *off_p, int64_t *off_out);
 int jb_batch_eval_pinned(jb_batch *batch);
+/* _begin copies host->device and enqueues the evaluation and the copy back on the batch's own stream
+ * and returns; _end waits, settles and checks.  Two batches (two halves of a GPU's chunks) driven
+ * begin, begin, end, end overlap the copies of one with the kernels of the other. */
+int jb_batch_eval_pinned_begin(jb_batch *batch);
+int jb_batch_eval_pinned_end(jb_batch *batch);
 /* enable != 0: a plan whose trial point puts an unmasked pixel outside a knot grid does not fail the
  * batched host call; its loss comes back NaN (gradient undefined) and the caller decides -- an
  * optimiser's line search treats it as a rejected step (the reference's clamped gather, model.py:985,

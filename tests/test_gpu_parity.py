@@ -240,6 +240,18 @@ def test_batch_eval_host_equals_per_plan_results():
     assert batch.eval_host(ps)[0][0] == refs[0][0]
     batch.eval_pinned()
     assert out_views[2][0] == refs[2][0]
+    # two batches in flight (begin, begin, end, end), each over its own plans
+    ba, bb = engine.Batch(plans[:2]), engine.Batch(plans[2:])
+    (pa, oa), (pb, ob) = ba.host_buffers(), bb.host_buffers()
+    for v, p in zip(pa + pb, ps):
+        v[:] = p
+    ba.eval_pinned_begin(); bb.eval_pinned_begin()
+    with pytest.raises(ValueError, match="pending"):
+        ba.eval_pinned_begin()
+    ba.eval_pinned_end(); bb.eval_pinned_end()
+    for (f, g), o in zip(refs, oa + ob):
+        assert o[0] == f and np.array_equal(o[1:], g)
+    ba.close(); bb.close()
     # a fit vector that changes size invalidates the views: the call says so, new views work
     plans[0].spec.root.fix(); plans[0].spec.root.fit(0, 1)
     plans[0].sync_from_model()

@@ -84,6 +84,8 @@ SYMBOLS = [
     ("jb_batch_host_buffers", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("jb_batch_eval_pinned", C.c_int, [C.c_void_p]),
+    ("jb_batch_eval_pinned_begin", C.c_int, [C.c_void_p]),
+    ("jb_batch_eval_pinned_end", C.c_int, [C.c_void_p]),
     ("jb_batch_soft_range", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_batch_check", C.c_int, [C.c_void_p]),
     ("jb_batch_launches", C.c_int64, [C.c_void_p]),

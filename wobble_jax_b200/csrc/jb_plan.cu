@@ -1328,9 +1328,9 @@ int jb_batch_host_buffers(jb_batch* b, double** p_fit_pinned, double** out_pinne
     return JB_OK;
 }
 
-int jb_batch_eval_pinned(jb_batch* b) {
+int jb_batch_eval_pinned_begin(jb_batch* b) {
     if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
-    if (b->host_pending) return fail(JB_ERR_BAD_ARG, "an evaluation is pending (jb_batch_eval_host_end)");
+    if (b->host_pending) return fail(JB_ERR_BAD_ARG, "an evaluation is pending (jb_batch_eval_pinned_end / jb_batch_eval_host_end)");
     if (!b->host_bound || !b->h_flat_p) return fail(JB_ERR_BAD_ARG, "jb_batch_host_buffers has not been called");
     JB_CUDA(cudaSetDevice(b->device));
     const size_t n = b->plans.size();
@@ -1339,11 +1339,28 @@ int jb_batch_eval_pinned(jb_batch* b) {
             return fail(JB_ERR_BAD_ARG, "the fit vector of plan %zu changed size: call jb_batch_host_buffers again", i);
     int rc = batch_host_launch(b);
     if (rc) return rc;
-    if ((rc = batch_settle(b, b->stream, true))) return rc;
+    b->host_pending = true;
+    return JB_OK;
+}
+
+int jb_batch_eval_pinned_end(jb_batch* b) {
+    if (!b) return fail(JB_ERR_BAD_ARG, "null batch");
+    if (!b->host_pending) return fail(JB_ERR_BAD_ARG, "jb_batch_eval_pinned_begin has not been called");
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t n = b->plans.size();
+    b->host_pending = false;
+    int rc = batch_settle(b, b->stream, true);
+    if (rc) return rc;
     if (!b->soft_range)
         for (size_t i = 0; i < n; ++i)
             if (!std::isfinite(b->h_flat_out[b->off_out[i]])) return fail(JB_ERR_NONFINITE, "loss of plan %zu is not finite", i);
     return JB_OK;
+}
+
+int jb_batch_eval_pinned(jb_batch* b) {
+    int rc = jb_batch_eval_pinned_begin(b);
+    if (rc) return rc;
+    return jb_batch_eval_pinned_end(b);
 }
 
 int jb_batch_eval_host_end(jb_batch* b, double* const* out_host) {

@@ -361,6 +361,14 @@ class Batch:
         kernel, one D2H copy, one synchronisation -- and no staging copy on the host."""
         _lib.check(self.lib.jb_batch_eval_pinned(self.handle))
 
+    def eval_pinned_begin(self):
+        """Copy in, enqueue the evaluation and the copy back on the batch's stream; returns at once."""
+        _lib.check(self.lib.jb_batch_eval_pinned_begin(self.handle))
+
+    def eval_pinned_end(self):
+        """Wait for ``eval_pinned_begin``; afterwards the ``host_buffers`` views hold the results."""
+        _lib.check(self.lib.jb_batch_eval_pinned_end(self.handle))
+
     def soft_range(self, enable=True):
         """Out-of-range plans give a NaN loss in ``eval_host`` instead of failing the whole call."""
         _lib.check(self.lib.jb_batch_soft_range(self.handle, int(bool(enable))))
