@@ -46,7 +46,7 @@ __host__ __device__ constexpr int f2_slot(int NC, int FL, int comp, int kind) {
 // lanes with lane / (32 / NV) == q.  Fixed order.
 template <int NV>
 __device__ __forceinline__ double warp_sum_n(double (&v)[NV], int lane) {
-    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8, "NV");
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16, "NV");
     int bit = 16;
 #pragma unroll
     for (int n = NV / 2; n >= 1; n >>= 1) {
@@ -65,6 +65,9 @@ __device__ __forceinline__ double warp_sum_n(double (&v)[NV], int lane) {
 
 // lane l accumulates into copy l % kClasses2 of the gradient window: lanes l and l + kClasses2 are
 // 4 * kClasses2 pixels apart, which the plan checks is more than a spline support (jb_plan.cu)
+#ifndef JB_F2_PAIRSUM
+#define JB_F2_PAIRSUM 1
+#endif
 #ifndef JB_F2_CLASSES
 #define JB_F2_CLASSES 3
 #endif
@@ -299,9 +302,12 @@ template <int NC> struct F2Ctx {
 
 // Row i of the group: wait for its record in the ring, walk it, reduce and store its per-row sums,
 // refill the ring stage.
-template <int NC, int PV, int FL, int DIR>
+// DEFER: the per-row sums are left in `sums` for the caller, which reduces the sums of an (up, down) pair
+// of rows in one butterfly (half as many dependent shuffle rounds per row).
+template <int NC, int PV, int FL, int DIR, bool DEFER>
 __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<NC>& rc, Win2<PV> (&win)[NC],
-                                          const uint32_t (&abase)[NC], uint32_t cdelta, double& loss, bool& was_live) {
+                                          const uint32_t (&abase)[NC], uint32_t cdelta, double& loss, bool& was_live,
+                                          double (&sums)[f2_pad(f2_nsums(NC, FL))]) {
     constexpr int NS = f2_nsums(NC, FL), NSP = f2_pad(NS);
     using L = F2Lay<NC>;
     const FusedParams& a = g_f2_plan;
@@ -313,7 +319,6 @@ __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<N
     const unsigned live_mask = (unsigned)rec.nkey;      // lanes that own a weighted pixel in this row of the tile
     const uint32_t bar = smem_u32(cx.wb + L::bars) + 8 * s;
     mbar_wait(bar, (uint32_t)((i / kStages) & 1));
-    double sums[NSP];
 #pragma unroll
     for (int q = 0; q < NSP; ++q) sums[q] = 0.0;
     if (live_mask != 0) {      // some weighted pixel in this row of the tile
@@ -325,18 +330,39 @@ __device__ __forceinline__ void f2_do_row(int i, const F2Ctx<NC>& cx, RowConst<N
             f2_row<NC, PV, FL, DIR, false>(px, rc, win, abase, cdelta, loss, sums, live, !was_live, cx.lane, DIR > 0 && i == 0);
         was_live = live;
     } else was_live = false;
-    if (NS > 0) {
-        // per-row sums of this tile (fixed order); the total of value q sits on lanes q*(32/NSP)..
-        const double tot = warp_sum_n<NSP>(sums, cx.lane);
-        if ((cx.lane & (32 / NSP - 1)) == 0)
-            a.rowpart[((int64_t)recs[i].row * a.n_tiles + cx.tile) * NSP + cx.lane / (32 / NSP)] = tot;
-    }
     // every lane has consumed stage s: refill it
     __syncwarp();
     if (cx.lane == 0 && i + kStages < cx.nrow) {
         mbar_expect_tx(bar, kTileBytes);
         tma_load_1d(smem_u32(cx.wb + L::ring + (size_t)s * kTileBytes),
                     a.data + ((int64_t)recs[i + kStages].row * a.n_tiles + cx.tile) * kTileDoubles, kTileBytes, bar);
+    }
+    if (NS > 0 && !DEFER) {
+        // per-row sums of this tile (fixed order); the total of value q sits on lanes q*(32/NSP)..
+        const double tot = warp_sum_n<NSP>(sums, cx.lane);
+        if ((cx.lane & (32 / NSP - 1)) == 0)
+            a.rowpart[((int64_t)recs[i].row * a.n_tiles + cx.tile) * NSP + cx.lane / (32 / NSP)] = tot;
+    }
+}
+
+// the sums of rows i (su) and i + 1 (sd) in one butterfly: value q of row i ends on lanes q * (32 / 2NSP) ..,
+// value q of row i + 1 behind them; the same addition tree per value as warp_sum_n<NSP>
+template <int NC, int FL>
+__device__ __forceinline__ void f2_store_pair(int i, const F2Ctx<NC>& cx, const double (&su)[f2_pad(f2_nsums(NC, FL))],
+                                              const double (&sd)[f2_pad(f2_nsums(NC, FL))]) {
+    constexpr int NSP = f2_pad(f2_nsums(NC, FL));
+    using L = F2Lay<NC>;
+    const FusedParams& a = g_f2_plan;
+    const RowRec<NC, 0>* recs = reinterpret_cast<const RowRec<NC, 0>*>(cx.wb + L::recs);
+    double v[2 * NSP];
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) { v[q] = su[q]; v[NSP + q] = sd[q]; }
+    const double tot = warp_sum_n<2 * NSP>(v, cx.lane);
+    constexpr int LPV = 32 / (2 * NSP);        // lanes per value
+    if ((cx.lane & (LPV - 1)) == 0) {
+        const int q = cx.lane / LPV;
+        const int row = recs[i + (q >= NSP ? 1 : 0)].row;
+        a.rowpart[((int64_t)row * a.n_tiles + cx.tile) * NSP + (q & (NSP - 1))] = tot;
     }
 }
 
@@ -489,9 +515,20 @@ __global__ void __maxnreg__(JB_MAXREG) k_fused2(const FusedParams* __restrict__ 
 
     // ---- 4. stream the rows of the group, two at a time (up, down) ------------------------------
     bool was_live = false;
-    for (int i = 0; i < nrow; i += 2) {
-        f2_do_row<NC, PV, FL, +1>(i, cx, rc, win, abase, cdelta, loss, was_live);
-        if (i + 1 < nrow) f2_do_row<NC, PV, FL, -1>(i + 1, cx, rc, win, abase, cdelta, loss, was_live);
+    {
+        constexpr int NSPr = f2_pad(f2_nsums(NC, FL));
+        constexpr bool kPair = JB_F2_PAIRSUM != 0 && f2_nsums(NC, FL) > 0 && 2 * NSPr <= 16;
+        int i = 0;
+        for (; i + 1 < nrow; i += 2) {
+            double su[NSPr], sd[NSPr];
+            f2_do_row<NC, PV, FL, +1, kPair>(i, cx, rc, win, abase, cdelta, loss, was_live, su);
+            f2_do_row<NC, PV, FL, -1, kPair>(i + 1, cx, rc, win, abase, cdelta, loss, was_live, sd);
+            if (kPair) f2_store_pair<NC, FL>(i, cx, su, sd);
+        }
+        if (i < nrow) {
+            double su[NSPr];
+            f2_do_row<NC, PV, FL, +1, false>(i, cx, rc, win, abase, cdelta, loss, was_live, su);
+        }
     }
 
     // ---- 5. flush, fold the accumulator copies in a fixed order, publish the window ------------
