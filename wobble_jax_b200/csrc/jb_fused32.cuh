@@ -51,7 +51,7 @@ template <> struct BasisF<3> {
 
 template <int NV>
 __device__ __forceinline__ float warp_sum_nf(float (&v)[NV], int lane) {
-    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8, "NV");
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16, "NV");
     int bit = 16;
 #pragma unroll
     for (int n = NV / 2; n >= 1; n >>= 1) {
@@ -261,10 +261,10 @@ __host__ __device__ constexpr size_t fused32_warp_smem(int wincap) {
 
 struct F32Ctx { unsigned char* wb; int nrow, tile, lane; };
 
-template <int NC, int PV, int FL, int DIR>
+template <int NC, int PV, int FL, int DIR, bool DEFER>
 __device__ __forceinline__ void f32_do_row(int i, const F32Ctx& cx, RowConst32<NC>& rc, Win32<PV> (&win)[NC],
                                            const uint32_t (&abase)[NC], uint32_t cdelta, float& loss, bool& was_live,
-                                           const unsigned char* data32) {
+                                           const unsigned char* data32, float (&sums)[f2_pad(f2_nsums(NC, FL))]) {
     constexpr int NS = f2_nsums(NC, FL), NSP = f2_pad(NS);
     using L = F32Lay<NC>;
     const FusedParams& a = g_f2_plan;
@@ -276,7 +276,6 @@ __device__ __forceinline__ void f32_do_row(int i, const F32Ctx& cx, RowConst32<N
     const unsigned live_mask = rec.live;
     const uint32_t bar = smem_u32(cx.wb + L::bars) + 8 * s;
     mbar_wait(bar, (uint32_t)((i / kStages) & 1));
-    float sums[NSP];
 #pragma unroll
     for (int q = 0; q < NSP; ++q) sums[q] = 0.0f;
     if (live_mask != 0) {
@@ -289,16 +288,36 @@ __device__ __forceinline__ void f32_do_row(int i, const F32Ctx& cx, RowConst32<N
         f32_row<NC, PV, FL, DIR>(px, pk, rc, win, ab, cdelta, loss, sums, live, !was_live, cx.lane, DIR > 0 && i == 0);
         was_live = live;
     } else was_live = false;
-    if (NS > 0) {
-        const float tot = warp_sum_nf<NSP>(sums, cx.lane);
-        if ((cx.lane & (32 / NSP - 1)) == 0)
-            a.rowpart[((int64_t)rec.row * a.n_tiles + cx.tile) * NSP + cx.lane / (32 / NSP)] = (double)tot;
-    }
     __syncwarp();
     if (cx.lane == 0 && i + kStages < cx.nrow) {
         mbar_expect_tx(bar, kTileBytes32);
         tma_load_1d(smem_u32(cx.wb + L::ring + (size_t)s * kTileBytes32),
                     data32 + ((int64_t)recs[i + kStages].row * a.n_tiles + cx.tile) * kTileBytes32, kTileBytes32, bar);
+    }
+    if (NS > 0 && !DEFER) {
+        const float tot = warp_sum_nf<NSP>(sums, cx.lane);
+        if ((cx.lane & (32 / NSP - 1)) == 0)
+            a.rowpart[((int64_t)recs[i].row * a.n_tiles + cx.tile) * NSP + cx.lane / (32 / NSP)] = (double)tot;
+    }
+}
+
+// the sums of rows i (su) and i + 1 (sd) in one butterfly (see f2_store_pair)
+template <int NC, int FL>
+__device__ __forceinline__ void f32_store_pair(int i, const F32Ctx& cx, const float (&su)[f2_pad(f2_nsums(NC, FL))],
+                                               const float (&sd)[f2_pad(f2_nsums(NC, FL))]) {
+    constexpr int NSP = f2_pad(f2_nsums(NC, FL));
+    using L = F32Lay<NC>;
+    const FusedParams& a = g_f2_plan;
+    const Rec32<NC>* recs = reinterpret_cast<const Rec32<NC>*>(cx.wb + L::recs);
+    float v[2 * NSP];
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) { v[q] = su[q]; v[NSP + q] = sd[q]; }
+    const float tot = warp_sum_nf<2 * NSP>(v, cx.lane);
+    constexpr int LPV = 32 / (2 * NSP);
+    if ((cx.lane & (LPV - 1)) == 0) {
+        const int q = cx.lane / LPV;
+        const int row = recs[i + (q >= NSP ? 1 : 0)].row;
+        a.rowpart[((int64_t)row * a.n_tiles + cx.tile) * NSP + (q & (NSP - 1))] = (double)tot;
     }
 }
 
@@ -445,8 +464,16 @@ __global__ void __maxnreg__(JB_MAXREG32) k_fused32(const FusedParams* __restrict
     cx.wb = wbase; cx.nrow = nrow; cx.tile = tile; cx.lane = lane;
     bool was_live = false;
     for (int i = 0; i < nrow; i += 2) {
-        f32_do_row<NC, PV, FL, +1>(i, cx, rc, win, abase, cdelta, loss, was_live, data32);
-        if (i + 1 < nrow) f32_do_row<NC, PV, FL, -1>(i + 1, cx, rc, win, abase, cdelta, loss, was_live, data32);
+        constexpr int NSPr = f2_pad(f2_nsums(NC, FL));
+        constexpr bool kPair = JB_F2_PAIRSUM != 0 && f2_nsums(NC, FL) > 0 && 2 * NSPr <= 16;
+        float su[NSPr], sd[NSPr];
+        if (i + 1 < nrow) {
+            f32_do_row<NC, PV, FL, +1, kPair>(i, cx, rc, win, abase, cdelta, loss, was_live, data32, su);
+            f32_do_row<NC, PV, FL, -1, kPair>(i + 1, cx, rc, win, abase, cdelta, loss, was_live, data32, sd);
+            if (kPair) f32_store_pair<NC, FL>(i, cx, su, sd);
+        } else {
+            f32_do_row<NC, PV, FL, +1, false>(i, cx, rc, win, abase, cdelta, loss, was_live, data32, su);
+        }
     }
 
     if (__all_sync(0xffffffffu, was_live)) {
