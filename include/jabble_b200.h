@@ -100,6 +100,9 @@ typedef struct {
                                       within 1e-5 of the float64 ones.  Needs smooth tiles and no
                                       NormalizationModel component; jb_plan_grid_search and _curvature are
                                       float64 paths and not available on such a plan                  */
+#define JB_PLAN_NO_STRIP 4         /* never evaluate with the column-walk kernel (k_strip): keep k_fused2 /
+                                      k_fused even when the rows are many and regular enough for it
+                                      (cross-checks and A/B measurements)                               */
 #define JB_PLAN_GENERAL_KERNEL 1   /* always evaluate with the general fused kernel (k_fused), never the
                                       specialised one (k_fused2): cross-checks and A/B measurements   */
 
@@ -123,7 +126,8 @@ typedef struct {
     int64_t tiles_serial;         /* ... walked lane by lane (lanes of a class may share knots)      */
     int64_t tiles_empty;          /* ... without any weighted pixel                                  */
     int32_t window_knots;         /* on-chip gradient window per warp and component                  */
-    int32_t fused_variant;        /* kernel of the last evaluation: -1 general k_fused, >= 0 flags of k_fused2 */
+    int32_t fused_variant;        /* kernel of the last evaluation: -1 general k_fused, >= 0 flags of k_fused2;
+                                     bit 6 (64) float32 tier k_fused32, bit 7 (128) column-walk kernel k_strip */
 } jb_plan_info_t;
 
 const char *jb_last_error(void);

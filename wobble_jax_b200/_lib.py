@@ -17,6 +17,7 @@ JB_ERR_OUT_OF_RANGE, JB_ERR_WINDOW, JB_ERR_NONFINITE = -4, -5, -6
 JB_COMP_SPLINE, JB_COMP_NORM_SPLINE = 0, 1
 JB_PLAN_GENERAL_KERNEL = 1
 JB_PLAN_FLOAT32 = 2
+JB_PLAN_NO_STRIP = 4
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)

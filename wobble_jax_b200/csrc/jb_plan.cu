@@ -3,9 +3,11 @@
 // A plan owns: the data block in HBM (canonicalised: every row ascending in x, padded to a
 // multiple of the 128-pixel warp tile), the flat parameter vector, the fit map, the scratch for
 // per-task partials, one CUDA stream.  An evaluation is six launches on that stream:
-//   k_scatter_params -> k_prepare_rows -> k_fused2 | k_fused32 | k_fused -> k_reduce_stage1 ->
-//   k_reduce_stage2 -> k_finish
-// (plan_variant picks the fused kernel from the plan's tiles, components, fit state and flags).
+//   k_scatter_params -> k_prepare_rows | k_prepare_strip -> k_strip | k_fused2 | k_fused32 | k_fused ->
+//   k_reduce_stage1 -> k_reduce_stage2 -> k_finish
+// (plan_variant picks the fused kernel from the plan's layout, components, fit state and flags:
+// k_strip, jb_strip.cuh, when the rows are many and regular enough for the column walk; else k_fused2
+// for smooth tiles; else the general k_fused).
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -21,6 +23,7 @@
 #include "jb_kernels.cuh"
 #include "jb_fused2.cuh"
 #include "jb_fused32.cuh"
+#include "jb_strip.cuh"
 
 namespace {
 
@@ -79,9 +82,11 @@ struct jb_plan {
     std::vector<uint8_t> h_flags;          // [E][n_tiles]
     std::vector<uint32_t> h_live;          // [E][n_tiles] lanes of the tile's warp that own a weighted pixel
     std::vector<double> h_xfirst;   // per row: smallest unmasked x (sort key), +inf if none
+    std::vector<double> h_xrel;     // per row: offset of its pixel grid from a reference row's (+inf: nothing weighted); empty: undefined
     std::vector<uint8_t> h_row_rev;
 
     int64_t n_params = 0, n_fit = 0;
+    bool fit_bufs = false;      // d_fit_map / d_pfit / d_out / h_pfit / h_out sized for n_fit
     double *d_params = nullptr, *d_grad_all = nullptr, *d_fisher_all = nullptr;
     std::vector<double> h_params;
     bool params_set = false, sort_dirty = true;
@@ -92,6 +97,7 @@ struct jb_plan {
     bool f32 = false;          // JB_PLAN_FLOAT32: float records, k_fused32
     float* d_data32 = nullptr; // tile-interleaved x_rel | y | ivar as floats (f32 plans only)
     bool force_v1 = false;     // a batch whose plans disagree on the kernel variant falls back to k_fused
+    bool force_nostrip = false; // a batch whose plans disagree on k_strip (variant or rows per block) leaves it
     int variant = -1;          // fused kernel of this plan: -1 k_fused (general), else the FL flags of k_fused2
     int64_t* d_fit_map = nullptr;
     double *d_pfit = nullptr, *d_out = nullptr;
@@ -111,11 +117,27 @@ struct jb_plan {
     int* d_keys[jb::kMaxComp][3] = {};      // device copies of shift/stretch/ctrl key arrays
     std::vector<int> h_shift_key[jb::kMaxComp];   // host copy of the shift keys (jb_plan_grid_search sums rows into keys)
 
+    // ---- strip path (k_strip, jb_strip.cuh): rows in sorted order, 32-pixel strips
+    bool strip_allowed = true;      // not JB_PLAN_NO_STRIP / JB_NO_STRIP, model shape supported
+    bool strip_ok = false;          // layout built for the current sort and its preconditions hold
+    bool strip_disabled = false;    // a precondition failed at run time even after a re-sort: stay on k_fused2 / k_fused
+    int strip_fail = 0;             // consecutive evaluations that raised a strip precondition
+    int sK = 0, sBPT = 0, s_nblocks = 0, s_nrgroups = 0, s_ncls = 1, s_nstrips = 0, s_hint = 0;
+    int64_t s_ntasks = 0;
+    double *d_sdata = nullptr, *d_sxoff = nullptr, *d_sxoff_rng = nullptr, *d_sxref = nullptr;
+    int* d_srowid = nullptr;
+    void* d_srowc = nullptr;
+    jb::StripBlk* d_sblk = nullptr;
+    unsigned long long* d_sstats = nullptr;
+    double *d_spart = nullptr, *d_srowpart = nullptr, *d_stmp = nullptr, *d_slosspart = nullptr;
+    int *d_spart_base = nullptr, *d_stile_rng = nullptr;
+    int64_t s_scratch_tasks = 0;    // tasks the strip scratch was allocated for
+
     int64_t launches = 0, evaluations = 0, serial_rows = 0;
     int64_t tiles_kind[4] = {0, 0, 0, 0};   // smooth, general, serial, empty
 
     // device-resident parameter blocks of the evaluation kernels (one launch can serve many plans)
-    struct Pack { jb::ScatterParams sc; jb::PrepareParams pr; jb::FusedParams fu; jb::ReduceParams re; };
+    struct Pack { jb::ScatterParams sc; jb::PrepareParams pr; jb::FusedParams fu; jb::ReduceParams re; jb::StripParams st; jb::StripPrepParams sp; };
     Pack* h_pack = nullptr;   // pinned
     Pack* d_pack = nullptr;
     int* d_off = nullptr;     // [6][2] block ranges {0, nb} of the six kernels for this plan alone
@@ -137,6 +159,7 @@ struct jb_batch {
     std::vector<void*> dev;
     jb::ScatterParams* d_sc = nullptr; jb::PrepareParams* d_pr = nullptr;
     jb::FusedParams* d_fu = nullptr; jb::ReduceParams* d_re = nullptr;
+    jb::StripParams* d_st = nullptr; jb::StripPrepParams* d_sp = nullptr;
     int* d_off = nullptr;
     int total[6] = {0, 0, 0, 0, 0, 0};
     bool scatter = true, dirty = true;
@@ -171,6 +194,20 @@ int dev_upload(jb_plan* pl, T** out, const std::vector<T>& h) {
     return JB_OK;
 }
 
+// free one of the plan's device buffers (nullptr is fine) and forget it
+template <typename T>
+void dev_free(jb_plan* pl, T*& ptr) {
+    if (!ptr) return;
+    for (size_t i = 0; i < pl->bufs.size(); ++i)
+        if (pl->bufs[i].p == (void*)ptr) {
+            pl->device_bytes -= (int64_t)pl->bufs[i].bytes;
+            cudaFree(pl->bufs[i].p);
+            pl->bufs.erase(pl->bufs.begin() + i);
+            break;
+        }
+    ptr = nullptr;
+}
+
 int choose_rows_per_group(int64_t E, int n_tiles, int requested) {
     if (requested > 0) return (int)std::min<int64_t>(std::min(requested, jb::kMaxGroup), std::max<int64_t>(E, 1));
     // A task pays its set-up (row records, control-point window, final window write) once however
@@ -189,10 +226,173 @@ int alloc_scratch(jb_plan* pl) {
     pl->n_groups = (int)((pl->E + pl->G - 1) / pl->G);
     pl->n_tasks = (int64_t)pl->n_groups * pl->n_tiles;
     int rc;
+    JB_CUDA(cudaStreamSynchronize(pl->stream));
+    dev_free(pl, pl->d_part); dev_free(pl, pl->d_part_base); dev_free(pl, pl->d_losspart);
     if ((rc = dev_alloc(pl, &pl->d_part, (size_t)pl->n_glob * pl->n_tasks * pl->wincap, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_part_base, (size_t)pl->n_glob * pl->n_tasks, true))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_losspart, (size_t)pl->n_tasks, true))) return rc;
     pl->pack_dirty = true;
+    return JB_OK;
+}
+
+constexpr int kStripWin = 64;      // doubles per published gradient window of a k_strip task (>= kStripWs + p_val + 1)
+
+// Does the model shape suit k_strip at all?
+bool strip_shape_ok(const jb_plan* pl) {
+    static const bool env_off = getenv("JB_NO_STRIP") != nullptr;
+    return pl->strip_allowed && !env_off && !pl->general_only && !pl->f32 && pl->has_data && !pl->has_norm && pl->n_glob >= 1 &&
+           pl->n_glob <= 2 && pl->ppad / jb::kStripPx <= jb::kRedBases && !pl->h_xrel.empty();
+}
+
+// (Re)build the strip layout for the row order `perm` (sorted by `key`): pick K from the key ranges
+// of the blocks, lay the rows out in strips on the device, derive the column offsets and check the
+// static preconditions of k_strip (jb_strip.cuh).  Sets pl->strip_ok.
+int strip_build(jb_plan* pl, const std::vector<int>& perm) {
+    pl->strip_ok = false;
+    pl->pack_dirty = true;
+    if (!strip_shape_ok(pl) || pl->strip_disabled) return JB_OK;
+    const int64_t E = pl->E;
+    const int NC = pl->n_glob;
+    // per-component keys of the sorted rows
+    std::vector<double> xref(E);
+    std::vector<std::vector<double>> key(NC, std::vector<double>(E));
+    for (int64_t pos = 0; pos < E; ++pos) {
+        const int r = perm[pos];
+        xref[pos] = pl->h_xrel[r];
+        for (int c = 0; c < NC; ++c) {
+            const jb_component_desc& cd = pl->desc[c];
+            const double sh = cd.shift_offset >= 0 ? pl->h_params[cd.shift_offset + pl->h_shift_key[c][r]] : 0.0;
+            key[c][pos] = xref[pos] - sh;
+        }
+    }
+    // rows per block: the largest K whose blocks keep every component's keys within 0.85 knots
+    // (k_prepare_strip refuses 1 - 2 kStripTol = 0.9 at run time: the margin is for the optimiser's steps)
+    int K = 0;
+    for (int cand : {32, 24, 16, 8}) {
+        bool ok = true;
+        for (int64_t r0 = 0; r0 < E && ok; r0 += cand)
+            for (int c = 0; c < NC && ok; ++c) {
+                double lo = INFINITY, hi = -INFINITY;
+                for (int64_t pos = r0; pos < std::min<int64_t>(E, r0 + cand); ++pos)
+                    if (std::isfinite(xref[pos])) { lo = std::min(lo, key[c][pos]); hi = std::max(hi, key[c][pos]); }
+                if (lo <= hi && !((hi - lo) / pl->desc[c].dx < 0.85)) ok = false;
+            }
+        if (ok) { K = cand; break; }
+    }
+    if (K == 0) return JB_OK;      // rows too far apart for the column walk: k_fused2 / k_fused
+    const int n_strips = (int)(pl->ppad / jb::kStripPx);
+    const int n_blocks = (int)((E + K - 1) / K);
+    int rc;
+    cudaStream_t st = pl->stream;
+    if (!pl->d_sdata) {
+        const int max_blocks = (int)((E + 7) / 8);
+        if ((rc = dev_alloc(pl, &pl->d_sdata, (size_t)n_strips * E * jb::kStripRec))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_sxoff, (size_t)n_strips * max_blocks * 32))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_sxoff_rng, (size_t)n_strips * max_blocks * 2))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_sxref, (size_t)E))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_srowid, (size_t)E))) return rc;
+        {
+            char* p = nullptr;
+            if ((rc = dev_alloc(pl, &p, (size_t)E * sizeof(jb::StripRow<2>)))) return rc;
+            pl->d_srowc = p;
+        }
+        if ((rc = dev_alloc(pl, &pl->d_sblk, (size_t)max_blocks))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_sstats, (size_t)16))) return rc;
+    }
+    JB_CUDA(cudaMemcpyAsync(pl->d_srowid, perm.data(), E * sizeof(int), cudaMemcpyHostToDevice, st));
+    JB_CUDA(cudaMemcpyAsync(pl->d_sxref, xref.data(), E * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        unsigned long long init[16];
+        for (int i = 0; i < 16; ++i) init[i] = i >= 3 ? ~0ULL : 0ULL;     // [3..10]: minima
+        JB_CUDA(cudaMemcpyAsync(pl->d_sstats, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    {
+        jb::StripLayoutParams lp;
+        lp.tiled = pl->d_data; lp.rowid = pl->d_srowid; lp.sdata = pl->d_sdata; lp.n_rows = E; lp.n_tiles = pl->n_tiles;
+        const int64_t warps = E * pl->n_tiles;
+        jb::k_strip_layout<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(lp);
+        double dx_min = INFINITY;
+        for (int c = 0; c < NC; ++c) dx_min = std::min(dx_min, pl->desc[c].dx);
+        jb::StripXoffParams xp;
+        xp.sdata = pl->d_sdata; xp.xref = pl->d_sxref; xp.xoff = pl->d_sxoff; xp.n_rows = E; xp.n_strips = n_strips; xp.K = K;
+        xp.n_blocks = n_blocks; xp.tol_x = 0.999 * jb::kStripTol * dx_min; xp.stats = pl->d_sstats;
+        const int64_t w2 = (int64_t)n_strips * n_blocks;
+        jb::k_strip_xoff<<<(unsigned)((w2 + 7) / 8), 256, 0, st>>>(xp);
+        JB_CUDA(cudaGetLastError());
+        pl->launches += 2;
+    }
+    unsigned long long stats[16];
+    JB_CUDA(cudaMemcpyAsync(stats, pl->d_sstats, sizeof stats, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    if (stats[0] != 0) return JB_OK;           // precondition (1): the pixel grid differs from row to row
+    double dx_max = 0.0, dx_min = INFINITY;
+    for (int c = 0; c < NC; ++c) { dx_max = std::max(dx_max, pl->desc[c].dx); dx_min = std::min(dx_min, pl->desc[c].dx); }
+    int ncls = 0;
+    for (int nn = 1; nn <= 8 && !ncls; ++nn) {
+        double gap;
+        if (stats[2 + nn] == ~0ULL) gap = INFINITY;        // no two weighted columns that far apart
+        else memcpy(&gap, &stats[2 + nn], sizeof gap);
+        if (gap >= dx_max * (1.0 + 1.0e-9)) ncls = nn;
+    }
+    if (!ncls) return JB_OK;                   // precondition (3): more than 8 pixels per knot
+    double span;
+    memcpy(&span, &stats[1], sizeof span);
+    // rows per task.  The window of a task holds kStripWs base intervals: the strip itself plus the drift
+    // of the keys over the task's blocks.  Within that, a lone plan wants at least one task per warp
+    // slot (148 SMs x 16 warps); a batch (hint > 0) wants long tasks.
+    const double room = (double)jb::kStripWs - 3.0 - span / dx_min;      // knots left for the drift
+    if (!(room > 1.0)) return JB_OK;
+    int bpt_fit = 0;
+    {
+        for (int cand = 32; cand >= 1 && !bpt_fit; --cand) {
+            bool ok = true;
+            for (int b0 = 0; b0 < n_blocks && ok; b0 += cand)
+                for (int c = 0; c < NC && ok; ++c) {
+                    double lo = INFINITY, hi = -INFINITY;
+                    const int64_t p0 = (int64_t)b0 * K, p1 = std::min<int64_t>(E, (int64_t)(b0 + cand) * K);
+                    for (int64_t pos = p0; pos < p1; ++pos)
+                        if (std::isfinite(xref[pos])) { lo = std::min(lo, key[c][pos]); hi = std::max(hi, key[c][pos]); }
+                    if (lo <= hi && !((hi - lo) / pl->desc[c].dx < room)) ok = false;
+                }
+            if (ok) bpt_fit = cand;
+        }
+    }
+    if (!bpt_fit) return JB_OK;
+    int bpt;
+    if (pl->s_hint > 0) bpt = std::max(1, (4 * pl->s_hint + K / 2) / K);
+    else {
+        const int64_t groups_wanted = (148LL * 16 + n_strips - 1) / n_strips;
+        bpt = (int)std::max<int64_t>(1, n_blocks / std::max<int64_t>(groups_wanted, 1));
+        bpt = std::min(bpt, std::max(1, 128 / K));
+    }
+    bpt = std::min(bpt, bpt_fit);
+    pl->sK = K; pl->sBPT = bpt; pl->s_nblocks = n_blocks; pl->s_nstrips = n_strips; pl->s_ncls = ncls;
+    pl->s_nrgroups = (n_blocks + bpt - 1) / bpt;
+    pl->s_ntasks = (int64_t)pl->s_nrgroups * n_strips;
+    {
+        jb::StripRngParams rp;
+        rp.xoff = pl->d_sxoff; rp.rng = pl->d_sxoff_rng; rp.n_strips = n_strips; rp.n_blocks = n_blocks;
+        rp.blocks_per_task = bpt; rp.n_rgroups = pl->s_nrgroups;
+        jb::k_strip_rng<<<(unsigned)((pl->s_ntasks + 7) / 8), 256, 0, st>>>(rp);
+        JB_CUDA(cudaGetLastError());
+        pl->launches++;
+    }
+    if (pl->s_scratch_tasks < pl->s_ntasks || !pl->d_spart) {
+        JB_CUDA(cudaStreamSynchronize(st));
+        dev_free(pl, pl->d_spart); dev_free(pl, pl->d_spart_base); dev_free(pl, pl->d_slosspart);
+        if ((rc = dev_alloc(pl, &pl->d_spart, (size_t)NC * pl->s_ntasks * kStripWin, true))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_spart_base, (size_t)NC * pl->s_ntasks, true))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_slosspart, (size_t)pl->s_ntasks, true))) return rc;
+        pl->s_scratch_tasks = pl->s_ntasks;
+    }
+    if (!pl->d_srowpart) {
+        const size_t nq = 8;
+        if ((rc = dev_alloc(pl, &pl->d_srowpart, (size_t)E * n_strips * nq, true))) return rc;
+        JB_CUDA(cudaMemsetAsync(pl->d_srowpart, 0, (size_t)E * n_strips * nq * sizeof(double), st));
+        if ((rc = dev_alloc(pl, &pl->d_stmp, (size_t)NC * n_strips * pl->max_knots, true))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_stile_rng, (size_t)2 * NC * n_strips, true))) return rc;
+    }
+    pl->strip_ok = true;
     return JB_OK;
 }
 
@@ -203,14 +403,11 @@ int resort_rows(jb_plan* pl) {
     const jb_component_desc* sc = nullptr;
     for (int c = 0; c < pl->n_comp; ++c)
         if (pl->desc[c].shift_offset >= 0) { sc = &pl->desc[c]; break; }
-    std::vector<int> skey;
-    if (sc && pl->params_set && pl->d_keys[sc - pl->desc][0]) {
-        skey.resize(pl->E);
-        JB_CUDA(cudaMemcpy(skey.data(), pl->d_keys[sc - pl->desc][0], pl->E * sizeof(int), cudaMemcpyDeviceToHost));
-    }
+    const std::vector<int>* skey = (sc && pl->params_set) ? &pl->h_shift_key[sc - pl->desc] : nullptr;
+    const std::vector<double>& xpos = pl->h_xrel.empty() ? pl->h_xfirst : pl->h_xrel;     // where the row's pixel grid sits
     for (int64_t r = 0; r < pl->E; ++r) {
-        double k = pl->h_xfirst[r];
-        if (!skey.empty()) k -= pl->h_params[sc->shift_offset + skey[r]];
+        double k = xpos[r];
+        if (skey && !skey->empty()) k -= pl->h_params[sc->shift_offset + (*skey)[r]];
         key[r] = k;
     }
     std::vector<int> perm(pl->E);
@@ -228,6 +425,10 @@ int resort_rows(jb_plan* pl) {
     JB_CUDA(cudaMemcpyAsync(pl->d_tinfo, tinfo.data(), tinfo.size() * sizeof(jb::TileInfo), cudaMemcpyHostToDevice, pl->stream));
     JB_CUDA(cudaStreamSynchronize(pl->stream));
     pl->sort_dirty = false;
+    if (pl->params_set) {
+        int rc = strip_build(pl, perm);
+        if (rc) return rc;
+    }
     return JB_OK;
 }
 
@@ -258,12 +459,16 @@ int check_supported_for_eval(const jb_plan* pl) {
 // the environment keeps the general kernel (A/B measurements).
 int plan_variant(const jb_plan* pl) {
     static const bool env_v1 = getenv("JB_FUSED_V1") != nullptr;
-    if ((env_v1 && !pl->f32) || pl->general_only || pl->force_v1 || !pl->f2_ok || pl->has_norm || pl->n_glob > 2) return -1;
     int fl = 0;
-    for (int c = 0; c < pl->n_glob; ++c) {
+    for (int c = 0; c < pl->n_glob && c < 2; ++c) {
         if (pl->desc[c].shift_offset >= 0 && (pl->fit_shift[c] || pl->force_der)) fl |= 1 << c;
         if (pl->desc[c].stretch_offset >= 0) fl |= 4 << c;
     }
+    // k_strip (bit 7): cubic splines get the kernel of their fit state, the other degrees one kernel
+    // per shape that forms every sum (a component without a StretchingModel has stretch 1)
+    if (pl->strip_ok && !pl->strip_disabled && !pl->force_nostrip && !pl->force_v1 && !env_v1 && strip_shape_ok(pl))
+        return 128 | (pl->desc[0].p_val == 3 ? fl : (pl->n_glob == 1 ? 5 : 15));
+    if ((env_v1 && !pl->f32) || pl->general_only || pl->force_v1 || !pl->f2_ok || pl->has_norm || pl->n_glob > 2) return -1;
     // float32 tier (bit 6): cubic splines get the kernel of their fit state, the other degrees one
     // kernel per shape that forms every sum
     if (pl->f32) return 64 | (pl->desc[0].p_val == 3 ? fl : (pl->n_glob == 1 ? 5 : 15));
@@ -309,9 +514,28 @@ int refresh_pack(jb_plan* pl) {
         rp.shift_rowptr[c] = pl->d_key_ptr[c][0];   rp.shift_rows[c] = pl->d_key_rows[c][0];
         rp.stretch_rowptr[c] = pl->d_key_ptr[c][1]; rp.stretch_rows[c] = pl->d_key_rows[c][1];
     }
+    const bool strip = pl->variant >= 0 && (pl->variant & 128);
     rp.n_rows = pl->E; rp.n_tasks = pl->n_tasks; rp.n_tiles = pl->n_tiles; rp.n_groups = pl->n_groups; rp.wincap = pl->wincap;
     rp.part = pl->d_part; rp.part_base = pl->d_part_base; rp.rowpart = pl->d_rowpart; rp.losspart = pl->d_losspart;
     rp.tilepart = pl->d_tmp; rp.tile_rng = pl->d_tile_rng; rp.max_knots = pl->max_knots;
+    if (strip) {
+        // the reducers take the partials of k_strip as they take those of k_fused2: a "tile" is a strip,
+        // a "group" the row range of a task
+        rp.n_tasks = pl->s_ntasks; rp.n_tiles = pl->s_nstrips; rp.n_groups = pl->s_nrgroups; rp.wincap = kStripWin;
+        rp.part = pl->d_spart; rp.part_base = pl->d_spart_base; rp.rowpart = pl->d_srowpart; rp.losspart = pl->d_slosspart;
+        rp.tilepart = pl->d_stmp; rp.tile_rng = pl->d_stile_rng;
+        jb::StripParams& sp = k.st;
+        sp.data = pl->d_sdata; sp.xoff = pl->d_sxoff; sp.xoff_rng = pl->d_sxoff_rng; sp.rowc = pl->d_srowc; sp.blk = pl->d_sblk;
+        sp.rowid = pl->d_srowid; sp.n_rows = pl->E; sp.n_strips = pl->s_nstrips; sp.K = pl->sK; sp.blocks_per_task = pl->sBPT;
+        sp.n_blocks = pl->s_nblocks; sp.n_rgroups = pl->s_nrgroups; sp.ncls = pl->s_ncls; sp.n_tasks = pl->s_ntasks;
+        sp.wincap = kStripWin; sp.n_comp = pl->n_glob;
+        sp.part = pl->d_spart; sp.part_base = pl->d_spart_base; sp.rowpart = pl->d_srowpart; sp.losspart = pl->d_slosspart;
+        sp.status = pl->d_status;
+        jb::StripPrepParams& pp = k.sp;
+        pp.rowid = pl->d_srowid; pp.xref = pl->d_sxref; pp.rowc = pl->d_srowc; pp.blk = pl->d_sblk; pp.n_rows = pl->E;
+        pp.K = pl->sK; pp.n_blocks = pl->s_nblocks; pp.n_comp = pl->n_glob; pp.status = pl->d_status;
+        for (int c = 0; c < pl->n_glob; ++c) sp.comp[c] = pp.comp[c] = pl->comp[c];
+    }
     rp.rowsum = pl->d_rowsum;
     rp.coef = pl->coef;
     rp.grad_all = pl->d_grad_all; rp.fisher_all = pl->d_fisher_all;
@@ -325,20 +549,21 @@ int refresh_pack(jb_plan* pl) {
             for (int q = 0; q < 3; ++q) rp.rq[c][q] = c * jb::kRowQ + q;
         if (pl->has_norm) { rp.rq[pl->n_glob][0] = pl->n_glob * jb::kRowQ; rp.rq[pl->n_glob][1] = pl->n_glob * jb::kRowQ + 1; }
     } else {
-        const int fl = pl->variant & 15;       // bit 6 marks the float32 tier
+        const int fl = pl->variant & 15;       // bit 6 marks the float32 tier, bit 7 k_strip
         NQ = jb::f2_pad(jb::f2_nsums(pl->n_glob, fl));
         for (int c = 0; c < pl->n_glob; ++c)
             for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, fl, c, q);
     }
     rp.nq = NQ;
-    rp.nb_ctrl = pl->n_glob * pl->n_tiles;
+    rp.nb_ctrl = pl->n_glob * rp.n_tiles;
     rp.nb_stage1_rows = (int)((pl->E * NQ + 255) / 256);
     int64_t n2 = 0;
     for (int c = 0; c < pl->n_comp; ++c)
         n2 += (c < pl->n_glob ? pl->comp[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys) + rp.n_shift[c] + rp.n_stretch[c];
     pl->nb[K_SCATTER] = (int)std::max<int64_t>(1, (pl->n_fit + 255) / 256);
-    pl->nb[K_PREPARE] = (int)((pl->E + 127) / 128);
-    pl->nb[K_FUSED] = (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
+    pl->nb[K_PREPARE] = strip ? (pl->s_nblocks + 3) / 4 : (int)((pl->E + 127) / 128);
+    pl->nb[K_FUSED] = strip ? (int)((pl->s_ntasks + jb::kStripWarps - 1) / jb::kStripWarps)
+                            : (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
     pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + 255) / 256) : 0);
     pl->nb[K_STAGE2] = (int)((n2 + 255) / 256);
     pl->nb[K_FINISH] = (int)(1 + (pl->n_fit + 1023) / 1024);
@@ -354,6 +579,8 @@ int refresh_pack(jb_plan* pl) {
 // What one launch sequence needs: where the parameter blocks of the n plans live.
 struct LaunchSet {
     const jb::ScatterParams* sc; const jb::PrepareParams* pr; const jb::FusedParams* fu; const jb::ReduceParams* re;
+    const jb::StripParams* st; const jb::StripPrepParams* sp;
+    int strip_K;             // rows per block of the k_strip plans of the launch (its shared-memory layout)
     const int* off[K_COUNT]; // n+1 block offsets per kernel
     int total[K_COUNT];
     int n;
@@ -439,12 +666,49 @@ int launch_fused2_f(const LaunchSet& L, cudaStream_t st) {
     return fail(JB_ERR_UNSUPPORTED, "no k_fused2 for flags %d", L.variant);
 }
 
+template <int NC, int PV, int FL>
+int launch_strip_t(const LaunchSet& L, cudaStream_t st) {
+    using Lay = jb::StripLay<NC, PV, FL>;
+    const size_t smem = Lay::launch_bytes(L.strip_K);
+    JB_CUDA(cudaFuncSetAttribute(jb::k_strip<NC, PV, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jb::k_strip<NC, PV, FL><<<(unsigned)L.total[K_FUSED], jb::kStripWarps * 32, smem, st>>>(L.st, L.off[K_FUSED], L.n);
+    JB_CUDA(cudaGetLastError());
+    return JB_OK;
+}
+
+template <int NC, int PV>
+int launch_strip_f(const LaunchSet& L, cudaStream_t st) {
+    if constexpr (PV != 3) return launch_strip_t<NC, PV, (NC == 1 ? 5 : 15)>(L, st);
+    else {
+#define JB_ST(f) case f: return launch_strip_t<NC, PV, f>(L, st);
+#ifdef JB_F2_FAST_BUILD   // kernel-tuning builds: only the benchmark's variant
+        if constexpr (NC == 2) { switch (L.variant & 15) { JB_ST(9) } }
+        else
+#endif
+        if constexpr (NC == 1) {
+            switch (L.variant & 15) { JB_ST(0) JB_ST(1) JB_ST(4) JB_ST(5) }
+        } else {
+            switch (L.variant & 15) {
+                JB_ST(0) JB_ST(1) JB_ST(2) JB_ST(3) JB_ST(4) JB_ST(5) JB_ST(6) JB_ST(7)
+                JB_ST(8) JB_ST(9) JB_ST(10) JB_ST(11) JB_ST(12) JB_ST(13) JB_ST(14) JB_ST(15)
+            }
+        }
+#undef JB_ST
+        return fail(JB_ERR_UNSUPPORTED, "no k_strip for flags %d", L.variant & 15);
+    }
+}
+
 // Six launches for the n plans of L (n = 1: the plan's own blocks; n > 1: the dense arrays of a jb_batch).
 int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override, double* out_override,
                jb_plan* prof /* may be null */) {
     if (L.scatter)
         jb::k_scatter_params<<<(unsigned)L.total[K_SCATTER], 256, 0, st>>>(L.sc, L.off[K_SCATTER], L.n, p_fit_override);
-    {
+    const bool strip = L.variant >= 0 && (L.variant & 128);
+    if (strip) {
+        const unsigned nb = (unsigned)L.total[K_PREPARE];
+        if (L.n_comp == 1) jb::k_prepare_strip<1><<<nb, 128, 0, st>>>(L.sp, L.off[K_PREPARE], L.n);
+        else jb::k_prepare_strip<2><<<nb, 128, 0, st>>>(L.sp, L.off[K_PREPARE], L.n);
+    } else {
         const unsigned nb = (unsigned)L.total[K_PREPARE];
         if (L.n_comp == 1 && !L.pvn) jb::k_prepare_rows<1, 0><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
         else if (L.n_comp == 1) jb::k_prepare_rows<1, 1><<<nb, 128, 0, st>>>(L.pr, L.off[K_PREPARE], L.n);
@@ -461,7 +725,17 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
         JB_CUDA(cudaEventRecord(prof->prof_events[prof->prof_used].first, st));
     }
     int rc;
-    if (L.variant >= 0) {
+    if (strip) {
+        switch (L.n_comp * 10 + L.p_val) {
+            case 11: rc = launch_strip_f<1, 1>(L, st); break;
+            case 12: rc = launch_strip_f<1, 2>(L, st); break;
+            case 13: rc = launch_strip_f<1, 3>(L, st); break;
+            case 21: rc = launch_strip_f<2, 1>(L, st); break;
+            case 22: rc = launch_strip_f<2, 2>(L, st); break;
+            case 23: rc = launch_strip_f<2, 3>(L, st); break;
+            default: rc = fail(JB_ERR_UNSUPPORTED, "no strip kernel for %d components of degree %d", L.n_comp, L.p_val);
+        }
+    } else if (L.variant >= 0) {
         switch (L.n_comp * 10 + L.p_val) {
             case 11: rc = launch_fused2_f<1, 1>(L, st); break;
             case 12: rc = launch_fused2_f<1, 2>(L, st); break;
@@ -503,6 +777,7 @@ int enqueue_eval(jb_plan* pl, const double* d_p_fit, double* d_out, cudaStream_t
     if ((rc = refresh_pack(pl))) return rc;
     LaunchSet L;
     L.sc = &pl->d_pack->sc; L.pr = &pl->d_pack->pr; L.fu = &pl->d_pack->fu; L.re = &pl->d_pack->re;
+    L.st = &pl->d_pack->st; L.sp = &pl->d_pack->sp; L.strip_K = pl->sK;
     for (int i = 0; i < K_COUNT; ++i) { L.off[i] = pl->d_off + 2 * i; L.total[i] = pl->nb[i]; }
     L.n = 1; L.n_comp = pl->n_glob; L.p_val = pl->desc[0].p_val; L.wincap = pl->wincap;
     L.pvn = pl->has_norm ? pl->desc[pl->n_glob].p_val : 0;
@@ -526,10 +801,33 @@ int read_status(jb_plan* pl, cudaStream_t st, bool* window) {
         return fail(JB_ERR_CUDA, "JB_DEBUG_BOUNDS: a window address left its shared-memory copy (kernel bug)");
     if (bits & jb::kStatOutOfRange)
         return fail(JB_ERR_OUT_OF_RANGE, "an unmasked warped pixel lies outside the knot grid of a spline component");
-    if (bits & jb::kStatWindow) {
+    if (bits & (jb::kStatWindow | jb::kStatStrip)) {
         if (window) *window = true;
+        if (pl->variant >= 0 && (pl->variant & 128))
+            return fail(JB_ERR_WINDOW, "rows of a block moved more than a knot apart (the shifts drifted since the rows were sorted)");
         return fail(JB_ERR_WINDOW, "knot window of a pixel tile exceeds %d knots (grid much finer than the pixels, or rows of one group far apart)", pl->wincap);
     }
+    return JB_OK;
+}
+
+// A window overflow was reported for `pl`: what to change before evaluating again.  k_strip plans
+// first re-sort (and re-lay out) their rows with the current parameters, then leave k_strip; the
+// other kernels re-sort, then widen the window, then shorten the row groups.  false: give up.
+int window_retry(jb_plan* pl, int attempt, bool* again) {
+    *again = false;
+    JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
+    if (pl->variant >= 0 && (pl->variant & 128)) {
+        if (pl->strip_fail++ > 0) { pl->strip_disabled = true; pl->strip_ok = false; pl->pack_dirty = true; }
+    } else if (attempt > 0) {
+        if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
+        else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
+        else return JB_OK;
+        int rc2 = alloc_scratch(pl);
+        if (rc2) return rc2;
+    }
+    int rc2 = resort_rows(pl);
+    if (rc2) return rc2;
+    *again = true;
     return JB_OK;
 }
 
@@ -544,18 +842,13 @@ int eval_sync(jb_plan* pl, const double* d_p_fit) {
         JB_CUDA(cudaMemcpyAsync(pl->h_out, pl->d_out, (pl->n_fit + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
         bool window = false;
         rc = read_status(pl, st, &window);
-        if (rc == JB_OK) return JB_OK;
-        if (!window || attempt >= 12) return rc;
-        JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
-        if (attempt > 0) {
-            if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
-            else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
-            else return rc;
-            int rc2 = alloc_scratch(pl);
-            if (rc2) return rc2;
-        }
-        int rc2 = resort_rows(pl);
+        if (rc == JB_OK) { pl->strip_fail = 0; return JB_OK; }
+        if (!window || attempt >= 14) return rc;
+        const std::string msg = g_err;
+        bool again = false;
+        int rc2 = window_retry(pl, attempt, &again);
         if (rc2) return rc2;
+        if (!again) { g_err = msg; return rc; }
     }
 }
 
@@ -626,6 +919,8 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->has_data = d->ys != nullptr;
     pl->coef = d->coefficient;
     pl->general_only = (d->flags & JB_PLAN_GENERAL_KERNEL) != 0;
+    pl->strip_allowed = (d->flags & JB_PLAN_NO_STRIP) == 0;
+    pl->s_hint = d->rows_per_group;
     pl->f32 = (d->flags & JB_PLAN_FLOAT32) != 0;
     if (pl->f32 && (pl->general_only || !d->ys)) return fail(JB_ERR_BAD_ARG, "a float32 plan needs ys / yivar and cannot ask for the general kernel");
     pl->n_comp = d->n_components;
@@ -756,6 +1051,26 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             pl->tiles_kind[!any_w ? 3 : bad ? 2 : jumpy ? 1 : 0]++;
         }
     }
+    // Position of every row relative to one reference row (k_strip, jb_strip.cuh): x[r][p] - x[ref][p]
+    // at the row's first weighted pixel whose reference pixel carries an x of its own.  Unlike the
+    // first weighted x this does not jump by a pixel when a row's first pixel is masked.
+    {
+        std::vector<int64_t> nw(E, 0);
+        for (int64_t r = 0; r < E; ++r)
+            for (int64_t p = 0; p < P; ++p) nw[r] += hm[(size_t)r * ppad + p] ? 0 : 1;
+        const int64_t ref = std::max_element(nw.begin(), nw.end()) - nw.begin();
+        pl->h_xrel.assign(E, INFINITY);
+        for (int64_t r = 0; r < E && nw[ref] > 0; ++r) {
+            if (!nw[r]) continue;
+            double o = NAN;
+            for (int64_t p = 0; p < P; ++p) {
+                const size_t i = (size_t)r * ppad + p, j = (size_t)ref * ppad + p;
+                if (!hm[i] && (!hm[j] || hxf[j] == hx[j])) { o = hxf[i] - hxf[j]; break; }
+            }
+            pl->h_xrel[r] = o;
+            if (!std::isfinite(o)) { pl->h_xrel.clear(); break; }      // a row without a common pixel: no column walk
+        }
+    }
     int rc;
     pl->h_txmin = txmin; pl->h_txmax = txmax; pl->h_flags = dense; pl->h_live = live;
     if ((rc = dev_alloc(pl, &pl->d_tinfo, (size_t)NT * E))) return rc;
@@ -881,6 +1196,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     if ((rc = dev_alloc(pl, &pl->d_out, 1))) return rc;
     JB_CUDA(cudaMallocHost(&pl->h_pfit, sizeof(double)));
     JB_CUDA(cudaMallocHost(&pl->h_out, sizeof(double)));
+    pl->fit_bufs = true;
 
     guard.p = nullptr;
     *out = pl;
@@ -892,7 +1208,10 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     memset(info, 0, sizeof *info);
     info->n_rows = pl->E; info->n_pix = pl->P; info->n_pix_padded = pl->ppad;
     info->n_params = pl->n_params; info->n_fit = pl->n_fit;
-    info->n_tasks = pl->n_tasks; info->rows_per_group = pl->G; info->tile_pixels = jb::kTile;
+    const bool strip = pl->variant >= 0 && (pl->variant & 128);
+    info->n_tasks = strip ? pl->s_ntasks : pl->n_tasks;
+    info->rows_per_group = strip ? pl->sK * pl->sBPT : pl->G;
+    info->tile_pixels = strip ? jb::kStripPx : jb::kTile;
     info->device_bytes = pl->device_bytes; info->scratch_bytes = pl->scratch_bytes;
     // x, y, ivar (8 B each) + 1-byte mask per pixel; read S,T and write their
     // gradients; per row read shift/stretch and write their gradients, Fisher and row loss
@@ -904,7 +1223,7 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     info->serial_rows = pl->serial_rows;
     info->tiles_smooth = pl->tiles_kind[0]; info->tiles_general = pl->tiles_kind[1];
     info->tiles_serial = pl->tiles_kind[2]; info->tiles_empty = pl->tiles_kind[3];
-    info->window_knots = pl->wincap;
+    info->window_knots = strip ? kStripWin : pl->wincap;
     info->fused_variant = pl->variant;
     return JB_OK;
 }
@@ -928,14 +1247,18 @@ int jb_plan_set_fit(jb_plan* pl, const int64_t* fit_index, int64_t n_fit) {
     JB_CUDA(cudaSetDevice(pl->device));
     JB_CUDA(cudaStreamSynchronize(pl->stream));
     int rc;
-    if ((rc = dev_alloc(pl, &pl->d_fit_map, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
-    if ((rc = dev_alloc(pl, &pl->d_pfit, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
-    if ((rc = dev_alloc(pl, &pl->d_out, (size_t)n_fit + 1))) return rc;
+    if (n_fit != pl->n_fit || !pl->fit_bufs) {      // same length as before: the buffers are reused
+        dev_free(pl, pl->d_fit_map); dev_free(pl, pl->d_pfit); dev_free(pl, pl->d_out);
+        if ((rc = dev_alloc(pl, &pl->d_fit_map, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_pfit, (size_t)std::max<int64_t>(n_fit, 1)))) return rc;
+        if ((rc = dev_alloc(pl, &pl->d_out, (size_t)n_fit + 1))) return rc;
+        cudaFreeHost(pl->h_pfit); cudaFreeHost(pl->h_out);
+        pl->h_pfit = pl->h_out = nullptr;
+        JB_CUDA(cudaMallocHost(&pl->h_pfit, std::max<int64_t>(n_fit, 1) * sizeof(double)));
+        JB_CUDA(cudaMallocHost(&pl->h_out, (n_fit + 1) * sizeof(double)));
+        pl->fit_bufs = true;
+    }
     if (n_fit) JB_CUDA(cudaMemcpy(pl->d_fit_map, fit_index, n_fit * sizeof(int64_t), cudaMemcpyHostToDevice));
-    cudaFreeHost(pl->h_pfit); cudaFreeHost(pl->h_out);
-    pl->h_pfit = pl->h_out = nullptr;
-    JB_CUDA(cudaMallocHost(&pl->h_pfit, std::max<int64_t>(n_fit, 1) * sizeof(double)));
-    JB_CUDA(cudaMallocHost(&pl->h_out, (n_fit + 1) * sizeof(double)));
     pl->n_fit = n_fit;
     for (int c = 0; c < pl->n_comp; ++c) {
         pl->fit_shift[c] = false;
@@ -1231,15 +1554,12 @@ static int batch_settle(jb_batch* b, cudaStream_t st, bool copy_out) {
             rc = read_status(pl, st, &window);
             if (rc == JB_OK) continue;
             if (rc == JB_ERR_OUT_OF_RANGE && b->soft_range) continue;     // its loss came back NaN (k_finish)
-            if (!window || attempt >= 12) return rc;
-            JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
-            if (attempt > 0) {
-                if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
-                else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
-                else return rc;
-                if ((rc = alloc_scratch(pl))) return rc;
-            }
-            if ((rc = resort_rows(pl))) return rc;
+            if (!window || attempt >= 14) return rc;
+            const std::string msg = g_err;
+            bool retry = false;
+            int rc2 = window_retry(pl, attempt, &retry);
+            if (rc2) return rc2;
+            if (!retry) { g_err = msg; return rc; }
             again = true;
         }
         if (!again) return JB_OK;
@@ -1401,14 +1721,33 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     const int n = (int)b->plans.size();
     int rc;
     bool regroup = b->dirty;
-    {   // one launch -> one kernel: plans that disagree on the variant all take the general kernel
-        bool same = true;
-        for (jb_plan* pl : b->plans) same = same && plan_variant(pl) == plan_variant(b->plans[0]);
-        for (jb_plan* pl : b->plans)
-            if (pl->force_v1 != !same) { pl->force_v1 = !same; pl->pack_dirty = true; }
+    for (jb_plan* pl : b->plans)
+        if (pl->sort_dirty) { if ((rc = resort_rows(pl))) return rc; }
+    {   // one launch -> one kernel: plans that disagree on k_strip (its variant or its rows per block)
+        // all leave it; plans that then still disagree on the variant all take the general kernel
+        auto all_same = [&]() {
+            bool same = true;
+            for (jb_plan* pl : b->plans) {
+                const int v = plan_variant(pl), v0 = plan_variant(b->plans[0]);
+                same = same && v == v0 && (!(v >= 0 && (v & 128)) || pl->sK == b->plans[0]->sK);
+            }
+            return same;
+        };
+        std::vector<std::pair<bool, bool>> old;
+        for (jb_plan* pl : b->plans) { old.emplace_back(pl->force_nostrip, pl->force_v1); pl->force_nostrip = pl->force_v1 = false; }
+        bool want_nostrip = false, want_v1 = false;
+        if (!all_same()) {
+            want_nostrip = true;
+            for (jb_plan* pl : b->plans) pl->force_nostrip = true;
+            want_v1 = !all_same();
+        }
+        for (size_t i = 0; i < b->plans.size(); ++i) {
+            jb_plan* pl = b->plans[i];
+            pl->force_nostrip = want_nostrip; pl->force_v1 = want_v1;
+            if (old[i].first != want_nostrip || old[i].second != want_v1) pl->pack_dirty = true;
+        }
     }
     for (jb_plan* pl : b->plans) {
-        if (pl->sort_dirty) { if ((rc = resort_rows(pl))) return rc; }
         if (pl->pack_dirty) regroup = true;
         if ((rc = refresh_pack(pl))) return rc;
         if (pl->wincap != b->plans[0]->wincap) {   // one kernel launch -> one shared-memory layout
@@ -1425,11 +1764,12 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
         b->dev.clear();
         std::vector<jb::ScatterParams> sc(n); std::vector<jb::PrepareParams> pr(n);
         std::vector<jb::FusedParams> fu(n); std::vector<jb::ReduceParams> re(n);
+        std::vector<jb::StripParams> stv(n); std::vector<jb::StripPrepParams> spv(n);
         std::vector<int> off((size_t)K_COUNT * (n + 1), 0);
         b->scatter = true;
         for (int i = 0; i < n; ++i) {
             const jb_plan::Pack& k = *b->plans[i]->h_pack;
-            sc[i] = k.sc; pr[i] = k.pr; fu[i] = k.fu; re[i] = k.re;
+            sc[i] = k.sc; pr[i] = k.pr; fu[i] = k.fu; re[i] = k.re; stv[i] = k.st; spv[i] = k.sp;
             sc[i].p_fit = b->p_fit.empty() ? nullptr : b->p_fit[i];
             re[i].out = b->out[i];
             for (int q = 0; q < K_COUNT; ++q) off[(size_t)q * (n + 1) + i + 1] = off[(size_t)q * (n + 1) + i] + b->plans[i]->nb[q];
@@ -1445,11 +1785,14 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
         if ((rc = up(pr.data(), n * sizeof pr[0], (void**)&b->d_pr))) return rc;
         if ((rc = up(fu.data(), n * sizeof fu[0], (void**)&b->d_fu))) return rc;
         if ((rc = up(re.data(), n * sizeof re[0], (void**)&b->d_re))) return rc;
+        if ((rc = up(stv.data(), n * sizeof stv[0], (void**)&b->d_st))) return rc;
+        if ((rc = up(spv.data(), n * sizeof spv[0], (void**)&b->d_sp))) return rc;
         if ((rc = up(off.data(), off.size() * sizeof(int), (void**)&b->d_off))) return rc;
         b->dirty = false;
     }
     LaunchSet L;
-    L.sc = b->d_sc; L.pr = b->d_pr; L.fu = b->d_fu; L.re = b->d_re;
+    L.sc = b->d_sc; L.pr = b->d_pr; L.fu = b->d_fu; L.re = b->d_re; L.st = b->d_st; L.sp = b->d_sp;
+    L.strip_K = b->plans[0]->sK;
     for (int q = 0; q < K_COUNT; ++q) { L.off[q] = b->d_off + (size_t)q * (n + 1); L.total[q] = b->total[q]; }
     L.n = n; L.n_comp = b->plans[0]->n_glob; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
     L.pvn = b->plans[0]->has_norm ? b->plans[0]->desc[b->plans[0]->n_glob].p_val : 0;

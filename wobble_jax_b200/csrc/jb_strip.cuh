@@ -708,4 +708,109 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Building the strip layout (on the device, from the plan's tile-interleaved canonical block).
+
+struct StripLayoutParams {
+    const double* tiled;     // [E][n_tiles][3][128] lane-interleaved (jb_kernels.cuh)
+    const int* rowid;        // [E] caller's row of sorted position
+    double* sdata;           // [n_strips][E][3][32]
+    int64_t n_rows;
+    int n_tiles;
+};
+
+// One warp per (sorted row, 128-pixel tile): read the 3 KB record as it lies, write its four strips.
+__global__ void k_strip_layout(StripLayoutParams a) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= a.n_rows * a.n_tiles) return;
+    const int64_t pos = w / a.n_tiles;
+    const int tile = (int)(w - pos * a.n_tiles);
+    const double* src = a.tiled + ((int64_t)a.rowid[pos] * a.n_tiles + tile) * kTileDoubles;
+    const int n_strips = a.n_tiles * (kTile / kStripPx);
+#pragma unroll
+    for (int e0 = 0; e0 < kTileDoubles; e0 += 32) {
+        const int e = e0 + lane;
+        const int arr = e / kTile, q = e % kTile;                  // array (x, y, ivar), interleaved position
+        const int p = (q % 32) * kPixPerLane + q / 32;             // pixel of the tile
+        const int strip = tile * (kTile / kStripPx) + p / kStripPx;
+        a.sdata[((int64_t)strip * a.n_rows + pos) * kStripRec + arr * kStripPx + p % kStripPx] = src[e];
+    }
+    (void)n_strips;
+}
+
+struct StripXoffParams {
+    const double* sdata; const double* xref;      // xref [E] sorted order: first weighted x of the row (+inf: none)
+    double* xoff;                                  // [n_strips][n_blocks][32]
+    int64_t n_rows; int n_strips, K, n_blocks;
+    double tol_x;                                  // kStripTol knots of the finest grid, in x
+    unsigned long long* stats;                     // [0] rows that break precondition (1)  [1] widest strip (x, as bits)  [2 + n] smallest x[p + n] - x[p], n = 1..8
+};
+
+// One warp per (strip, block): the column offsets of the block and the checks of preconditions (1), (3).
+__global__ void k_strip_xoff(StripXoffParams a) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)a.n_strips * a.n_blocks) return;
+    const int strip = (int)(w / a.n_blocks), b = (int)(w - (int64_t)strip * a.n_blocks);
+    const int64_t r0 = (int64_t)b * a.K;
+    const int rows = (int)min((int64_t)a.K, a.n_rows - r0);
+    const double* rec = a.sdata + ((int64_t)strip * a.n_rows + r0) * kStripRec + lane;
+    double xo = -INFINITY, dev = 0.0;
+    bool have = false;
+    for (int i = 0; i < rows; ++i) {
+        const double x = rec[(int64_t)i * kStripRec], iv = rec[(int64_t)i * kStripRec + 2 * kStripPx];
+        if (iv != 0.0) {
+            const double o = x - a.xref[r0 + i];
+            if (!have) { xo = o; have = true; }
+            else dev = fmax(dev, fabs(o - xo));
+        }
+    }
+    a.xoff[((int64_t)strip * a.n_blocks + b) * 32 + lane] = xo;
+    const bool bad = dev > a.tol_x || (have && !(fabs(xo) < 1.0e300));
+    const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad));
+    double xmin = have ? xo : INFINITY, xmax = have ? xo : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) {
+        if (nbad) atomicAdd(a.stats, (unsigned long long)nbad);
+        if (xmin <= xmax) atomicMax(a.stats + 1, (unsigned long long)__double_as_longlong(xmax - xmin));   // >= 0: bits order like values
+    }
+    // smallest distance between weighted columns n lanes apart (negative: not monotone -> 0)
+#pragma unroll
+    for (int nn = 1; nn <= 8; ++nn) {
+        const double other = __shfl_down_sync(0xffffffffu, xo, nn);
+        const bool oh = __shfl_down_sync(0xffffffffu, have ? 1 : 0, nn) != 0;
+        double gap = (have && oh && lane + nn < 32) ? fmax(other - xo, 0.0) : INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gap = fmin(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+        if (lane == 0 && gap < 1.0e300) atomicMin(a.stats + 2 + nn, (unsigned long long)__double_as_longlong(gap));
+    }
+}
+
+struct StripRngParams { const double* xoff; double* rng; int n_strips, n_blocks, blocks_per_task, n_rgroups; };
+
+// One warp per task (row group, strip): range of the finite column offsets of its blocks.
+__global__ void k_strip_rng(StripRngParams a) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)a.n_rgroups * a.n_strips) return;
+    const int g = (int)(w / a.n_strips), strip = (int)(w - (int64_t)g * a.n_strips);
+    const int b0 = g * a.blocks_per_task, b1 = min(b0 + a.blocks_per_task, a.n_blocks);
+    double xmin = INFINITY, xmax = -INFINITY;
+    for (int b = b0; b < b1; ++b) {
+        const double xo = a.xoff[((int64_t)strip * a.n_blocks + b) * 32 + lane];
+        if (xo > -1.0e300) { xmin = fmin(xmin, xo); xmax = fmax(xmax, xo); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) { a.rng[2 * w] = xmin; a.rng[2 * w + 1] = xmax; }
+}
+
 }  // namespace jb

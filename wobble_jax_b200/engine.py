@@ -136,7 +136,7 @@ class Plan:
     """Owner of one ``jb_plan`` (data block resident in HBM + compiled model)."""
 
     def __init__(self, spec, xs, ys, yivar, mask, metablock, coefficient=1.0, device=0, rows_per_group=0,
-                 general_kernel=False, float32=False):
+                 general_kernel=False, float32=False, no_strip=False):
         lib = _lib.load()
         self.lib = lib
         self.spec = spec
@@ -206,7 +206,8 @@ class Plan:
         desc.n_params = spec.n_params
         desc.coefficient = float(coefficient)
         desc.rows_per_group = int(rows_per_group)
-        desc.flags = (_lib.JB_PLAN_GENERAL_KERNEL if general_kernel else 0) | (_lib.JB_PLAN_FLOAT32 if float32 else 0)
+        desc.flags = ((_lib.JB_PLAN_GENERAL_KERNEL if general_kernel else 0) | (_lib.JB_PLAN_FLOAT32 if float32 else 0) |
+                      (_lib.JB_PLAN_NO_STRIP if no_strip else 0))
         handle = C.c_void_p()
         _lib.check(lib.jb_plan_create(C.byref(desc), C.byref(handle)))
         self.handle = handle
@@ -408,11 +409,11 @@ class Batch:
 
 
 def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_group=0, general_kernel=False,
-               float32=False):
+               float32=False, no_strip=False):
     spec = TreeSpec(model)
     plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
                 coefficient=coefficient, device=device, rows_per_group=rows_per_group, general_kernel=general_kernel,
-                float32=float32)
+                float32=float32, no_strip=no_strip)
     plan.sync_from_model()
     return plan
 
