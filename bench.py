@@ -393,7 +393,8 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic * args.chunks if traffic else None,
-                     "kernel": (f"k_fused32<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 64 else
+                     "kernel": (f"k_strip<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 128 else
+                                f"k_fused32<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 64 else
                                 f"k_fused2<2,{args.p_val},{info['fused_variant']}>" if info["fused_variant"] >= 0 else f"k_fused<2,{args.p_val}>"),
                      "kernel_ms": fused_batch_avg_ms, "launches_timed": int(fused_batch_n),
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": peak_src,

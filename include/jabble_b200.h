@@ -128,6 +128,11 @@ typedef struct {
     int32_t window_knots;         /* on-chip gradient window per warp and component                  */
     int32_t fused_variant;        /* kernel of the last evaluation: -1 general k_fused, >= 0 flags of k_fused2;
                                      bit 6 (64) float32 tier k_fused32, bit 7 (128) column-walk kernel k_strip */
+    int32_t strip_reason;         /* why k_strip does not serve the plan: 0 it does / not decided yet, 1 model shape or
+                                     flags, 2 sorted rows more than a knot apart (too few epochs), 3 pixel grid differs
+                                     from row to row, 4 more than 8 pixels per knot, 5 a task's knot window too wide,
+                                     6 left at run time (the shifts drifted twice)                                   */
+    int32_t strip_rows_per_block; /* K of k_strip (rows between two re-basings of a column), 0 when not in use          */
 } jb_plan_info_t;
 
 const char *jb_last_error(void);

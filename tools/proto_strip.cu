@@ -205,12 +205,11 @@ int main(int argc, char** argv) {
             printf("grad ctrl comp %d: norm-rel %.2e (norm %.3e)\n", c, std::sqrt(num / den), std::sqrt(den));
         }
         CK(cudaMemcpy(ra.data(), rows, E * 32, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(rb.data(), nrows, E * 32, cudaMemcpyDeviceToHost));
-        // strip row sums are in caller's row order, carry 1/PV and st; naive ones are in sorted order, raw
         for (int q = 0; q < 3; ++q) {
             double num = 0, den = 0;
             for (int64_t pos = 0; pos < E; ++pos) {
                 const double sc = 1.0;   // both in the S' / PV convention of the reducers
-                const double va = ra[(int64_t)perm[pos] * 4 + (q == 0 ? 0 : q == 1 ? 1 : 2)];
+                const double va = ra[pos * 4 + q];      // k_strip numbers the rows in sorted order
                 const double vb = rb[pos * 4 + q] * sc;
                 num += (va - vb) * (va - vb); den += vb * vb;
             }

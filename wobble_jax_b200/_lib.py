@@ -53,7 +53,7 @@ class PlanInfo(C.Structure):
                [(n, C.c_int64) for n in ("device_bytes", "scratch_bytes", "algorithmic_bytes",
                                          "kernel_launches", "evaluations", "serial_rows", "tiles_smooth",
                                          "tiles_general", "tiles_serial", "tiles_empty")] + \
-               [("window_knots", C.c_int32), ("fused_variant", C.c_int32)]
+               [("window_knots", C.c_int32), ("fused_variant", C.c_int32), ("strip_reason", C.c_int32), ("strip_rows_per_block", C.c_int32)]
 
 
 #: every symbol include/jabble_b200.h declares: (name, restype, argtypes)

@@ -901,6 +901,7 @@ struct ReduceParams {
     int* tile_rng;      // [n_comp][n_tiles][2]: the knots [lo, hi) of tilepart that are valid
     int64_t max_knots;
     double* rowsum;     // [E][NQ]
+    const int* row_of_pos;   // k_strip plans: rowpart row -> caller's row (nullptr: the same)
     double coef;
     double* grad_all; double* fisher_all;
     const int64_t* fit_map; int64_t n_fit;
@@ -988,7 +989,7 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
         double s = 0.0;
 #pragma unroll 8
         for (int t = 0; t < a.n_tiles; ++t) s += a.rowpart[(r * a.n_tiles + t) * NQ + q];
-        a.rowsum[i] = s;
+        a.rowsum[(a.row_of_pos ? (int64_t)a.row_of_pos[r] : r) * NQ + q] = s;       // k_strip numbers the rows in sorted order
     } else {   // normalisation control points: per row, sum of the tile partials
         const int64_t i = (int64_t)(blk - nb_ctrl - a.nb_stage1_rows) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * a.norm_stride) return;

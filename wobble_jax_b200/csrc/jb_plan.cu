@@ -122,6 +122,8 @@ struct jb_plan {
     bool strip_ok = false;          // layout built for the current sort and its preconditions hold
     bool strip_disabled = false;    // a precondition failed at run time even after a re-sort: stay on k_fused2 / k_fused
     int strip_fail = 0;             // consecutive evaluations that raised a strip precondition
+    int strip_reason = 0;           // jb_plan_info_t.strip_reason
+    int sK_force = 0;               // rows per block imposed by a batch (its plans share one launch, hence one K)
     int sK = 0, sBPT = 0, s_nblocks = 0, s_nrgroups = 0, s_ncls = 1, s_nstrips = 0, s_hint = 0;
     int64_t s_ntasks = 0;
     double *d_sdata = nullptr, *d_sxoff = nullptr, *d_sxoff_rng = nullptr, *d_sxref = nullptr;
@@ -250,6 +252,7 @@ bool strip_shape_ok(const jb_plan* pl) {
 int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     pl->strip_ok = false;
     pl->pack_dirty = true;
+    pl->strip_reason = pl->strip_disabled ? 6 : 1;
     if (!strip_shape_ok(pl) || pl->strip_disabled) return JB_OK;
     const int64_t E = pl->E;
     const int NC = pl->n_glob;
@@ -268,7 +271,8 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     // rows per block: the largest K whose blocks keep every component's keys within 0.85 knots
     // (k_prepare_strip refuses 1 - 2 kStripTol = 0.9 at run time: the margin is for the optimiser's steps)
     int K = 0;
-    for (int cand : {32, 24, 16, 8}) {
+    for (int cand : {32, 28, 24, 20, 16, 12, 8}) {
+        if (pl->sK_force && cand > pl->sK_force) continue;
         bool ok = true;
         for (int64_t r0 = 0; r0 < E && ok; r0 += cand)
             for (int c = 0; c < NC && ok; ++c) {
@@ -279,6 +283,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
             }
         if (ok) { K = cand; break; }
     }
+    pl->strip_reason = 2;
     if (K == 0) return JB_OK;      // rows too far apart for the column walk: k_fused2 / k_fused
     const int n_strips = (int)(pl->ppad / jb::kStripPx);
     const int n_blocks = (int)((E + K - 1) / K);
@@ -324,6 +329,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     unsigned long long stats[16];
     JB_CUDA(cudaMemcpyAsync(stats, pl->d_sstats, sizeof stats, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
+    pl->strip_reason = 3;
     if (stats[0] != 0) return JB_OK;           // precondition (1): the pixel grid differs from row to row
     double dx_max = 0.0, dx_min = INFINITY;
     for (int c = 0; c < NC; ++c) { dx_max = std::max(dx_max, pl->desc[c].dx); dx_min = std::min(dx_min, pl->desc[c].dx); }
@@ -334,6 +340,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
         else memcpy(&gap, &stats[2 + nn], sizeof gap);
         if (gap >= dx_max * (1.0 + 1.0e-9)) ncls = nn;
     }
+    pl->strip_reason = 4;
     if (!ncls) return JB_OK;                   // precondition (3): more than 8 pixels per knot
     double span;
     memcpy(&span, &stats[1], sizeof span);
@@ -341,6 +348,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     // of the keys over the task's blocks.  Within that, a lone plan wants at least one task per warp
     // slot (148 SMs x 16 warps); a batch (hint > 0) wants long tasks.
     const double room = (double)jb::kStripWs - 3.0 - span / dx_min;      // knots left for the drift
+    pl->strip_reason = 5;
     if (!(room > 1.0)) return JB_OK;
     int bpt_fit = 0;
     {
@@ -393,6 +401,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
         if ((rc = dev_alloc(pl, &pl->d_stile_rng, (size_t)2 * NC * n_strips, true))) return rc;
     }
     pl->strip_ok = true;
+    pl->strip_reason = 0;
     return JB_OK;
 }
 
@@ -523,7 +532,7 @@ int refresh_pack(jb_plan* pl) {
         // a "group" the row range of a task
         rp.n_tasks = pl->s_ntasks; rp.n_tiles = pl->s_nstrips; rp.n_groups = pl->s_nrgroups; rp.wincap = kStripWin;
         rp.part = pl->d_spart; rp.part_base = pl->d_spart_base; rp.rowpart = pl->d_srowpart; rp.losspart = pl->d_slosspart;
-        rp.tilepart = pl->d_stmp; rp.tile_rng = pl->d_stile_rng;
+        rp.tilepart = pl->d_stmp; rp.tile_rng = pl->d_stile_rng; rp.row_of_pos = pl->d_srowid;
         jb::StripParams& sp = k.st;
         sp.data = pl->d_sdata; sp.xoff = pl->d_sxoff; sp.xoff_rng = pl->d_sxoff_rng; sp.rowc = pl->d_srowc; sp.blk = pl->d_sblk;
         sp.rowid = pl->d_srowid; sp.n_rows = pl->E; sp.n_strips = pl->s_nstrips; sp.K = pl->sK; sp.blocks_per_task = pl->sBPT;
@@ -817,7 +826,7 @@ int window_retry(jb_plan* pl, int attempt, bool* again) {
     *again = false;
     JB_CUDA(cudaMemcpy(pl->h_params.data(), pl->d_params, pl->n_params * sizeof(double), cudaMemcpyDeviceToHost));
     if (pl->variant >= 0 && (pl->variant & 128)) {
-        if (pl->strip_fail++ > 0) { pl->strip_disabled = true; pl->strip_ok = false; pl->pack_dirty = true; }
+        if (pl->strip_fail++ > 0) { pl->strip_disabled = true; pl->strip_ok = false; pl->pack_dirty = true; pl->strip_reason = 6; }
     } else if (attempt > 0) {
         if (pl->wincap < jb::kWinCapMax) pl->wincap = std::min(jb::kWinCapMax, pl->wincap + 32);
         else if (pl->G > 1) pl->G = std::max(1, pl->G / 4);
@@ -1225,6 +1234,8 @@ int jb_plan_info(const jb_plan* pl, jb_plan_info_t* info) {
     info->tiles_serial = pl->tiles_kind[2]; info->tiles_empty = pl->tiles_kind[3];
     info->window_knots = strip ? kStripWin : pl->wincap;
     info->fused_variant = pl->variant;
+    info->strip_reason = pl->strip_reason;
+    info->strip_rows_per_block = strip ? pl->sK : 0;
     return JB_OK;
 }
 
@@ -1735,6 +1746,21 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
         };
         std::vector<std::pair<bool, bool>> old;
         for (jb_plan* pl : b->plans) { old.emplace_back(pl->force_nostrip, pl->force_v1); pl->force_nostrip = pl->force_v1 = false; }
+        {   // k_strip plans that differ only in their rows per block: all take the smallest
+            int kmin = INT_MAX, kmax = 0;
+            bool all_strip = true;
+            for (jb_plan* pl : b->plans) {
+                const int v = plan_variant(pl);
+                all_strip = all_strip && v >= 0 && (v & 128);
+                kmin = std::min(kmin, pl->sK); kmax = std::max(kmax, pl->sK);
+            }
+            if (all_strip && kmin != kmax)
+                for (jb_plan* pl : b->plans)
+                    if (pl->sK != kmin) {
+                        pl->sK_force = kmin;
+                        if ((rc = resort_rows(pl))) return rc;
+                    }
+        }
         bool want_nostrip = false, want_v1 = false;
         if (!all_same()) {
             want_nostrip = true;

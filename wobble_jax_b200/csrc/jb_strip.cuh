@@ -86,7 +86,7 @@ struct StripParams {
     CompDev comp[kMaxComp];
     double* part;            // [n_comp][n_tasks][wincap]
     int* part_base;          // [n_comp][n_tasks]
-    double* rowpart;         // [E][n_strips][NSP]
+    double* rowpart;         // [E][n_strips][NSP], rows in SORTED order (k_reduce_stage1 maps them back through rowid)
     double* losspart;        // [n_tasks]
     int* status;
 };
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     extern __shared__ __align__(256) unsigned char strip_smem[];
     using Lay = StripLay<NC, PV, FL>;
     constexpr int NS = Lay::NS, NSP = Lay::NSP, TE = Lay::TE;
-    static_assert(kStageRows == 4 && kStripIlp >= 1 && kStageRows % kStripIlp == 0 && (kStripStages & (kStripStages - 1)) == 0, "stage shape");
+    static_assert(kStageRows == 4 && kStripIlp >= 1 && kStageRows % kStripIlp == 0 && kStripStages == 2, "stage shape");
     const int pi = find_plan(off, n, blockIdx.x);
     const StripParams& a = arr[pi];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     const int strip = (int)(task % a.n_strips);
     const int rgroup = (int)(task / a.n_strips);
     const int K = a.K;
-    const int spb = K / kStageRows;                // stages per block
+    const int spb = K >> 2;                        // stages per block (kStageRows = 4)
     const int blk0 = rgroup * a.blocks_per_task;
     const int nblk = min(a.blocks_per_task, a.n_blocks - blk0);
     const int64_t row0 = (int64_t)blk0 * K;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
         // nothing weighted (or an error): the row sums of this strip are zero
         if (NS > 0)
             for (int i = lane; i < nrow * NSP; i += 32)
-                a.rowpart[((int64_t)a.rowid[row0 + i / NSP] * a.n_strips + strip) * NSP + i % NSP] = 0.0;
+                a.rowpart[((row0 + i / NSP) * a.n_strips + strip) * NSP + i % NSP] = 0.0;
         // copies are in flight into this warp's shared memory: let them land before leaving
         mbar_wait(hbar0, 0);
         if (nblk > 1) mbar_wait(hbar0 + 8, 0);
@@ -535,7 +535,31 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     const uint32_t tile32 = wb32 + Lay::tile;
     const uint32_t rd_addr = tile32 + (uint32_t)(vsel * 256 + (lane & 1) * 16 + rsel * 32);
     const uint32_t park_addr = tile32 + (uint32_t)(lane * 8);
-    const int* rowid_p = a.rowid + row0 + rsel;
+    // where this lane stores the sum it adds up (v0 = 0 round; later rounds 16 / kStageRows sums further), per stage
+    double* rowpart_p = a.rowpart + ((row0 + rsel) * a.n_strips + strip) * NSP + vsel / kStageRows;
+    const int64_t rowpart_step = (int64_t)kStageRows * a.n_strips * NSP;
+    // scale of that sum: the reducers expect S' / PV (jb_fused2.cuh); a stretched component's derivative
+    // sums carry the row's stretch (only then does the scale depend on the row)
+    constexpr bool kRowScale = (f2_der(FL, 0) && f2_str(FL, 0)) || (NC > 1 && f2_der(FL, 1) && f2_str(FL, 1));
+    auto sum_scale = [&](int q, const StripRow<NC>* rc) {
+        constexpr double ipv = 1.0 / PV;
+        double sc = 1.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (f2_der(FL, c)) {
+                const double st = f2_str(FL, c) ? rc->st[c] : 1.0;
+                if (q == f2_slot(NC, FL, c, 0)) sc = st * ipv;
+                if (q == f2_slot(NC, FL, c, 2)) sc = (st * ipv) * (st * ipv);
+            }
+        return sc;
+    };
+    StripRow<NC> unit_row;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { unit_row.sh[c] = 0.0; unit_row.st[c] = 1.0; }
+    double sc_lane[NS > 0 ? (NS * kStageRows + 15) / 16 : 1];
+#pragma unroll
+    for (int v0 = 0; v0 < NS * kStageRows; v0 += 16) sc_lane[v0 / 16] = sum_scale((v0 + vsel) / kStageRows, &unit_row);
+    uint32_t ring_off = 0, bar_off = 0;              // slot of the current stage: toggled, not computed
     const double* src_next = strip_data + (int64_t)kStripStages * kStageRows * kStripRec;
     const int rows_last = nrow - (nstage - 1) * kStageRows;
     const int nfull = rows_last == kStageRows ? nstage : nstage - 1;      // only the last stage of a task can be ragged
@@ -590,11 +614,9 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     // one stage; FULL: all kStageRows rows present
     auto stage_body = [&](int s, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        const int slot = s & (kStripStages - 1);
         const int rows = FULL ? kStageRows : rows_last;
-        const int my_row = (NS > 0 && (FULL || rsel < rows)) ? __ldg(rowid_p) : 0;       // caller's row, for the store below
-        mbar_wait(bar0 + 8 * slot, (uint32_t)((s / kStripStages) & 1));
-        const double* px = reinterpret_cast<const double*>(wb + Lay::ring + slot * Lay::slot_bytes) + lane;
+        mbar_wait(bar0 + bar_off, (uint32_t)((s / kStripStages) & 1));
+        const double* px = reinterpret_cast<const double*>(wb + Lay::ring + ring_off) + lane;
         const StripRow<NC>* rowc = reinterpret_cast<const StripRow<NC>*>(hd) + sb * kStageRows;
         constexpr int G = FULL ? kStripIlp : 1;          // rows computed together
 #pragma unroll(G == kStageRows ? kStageRows : 1)
@@ -613,36 +635,28 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
         __syncwarp();                                  // rows consumed, row terms parked
         if (lane == 0 && s + kStripStages < nstage) {
             const int rows_n = (s + kStripStages + 1 < nstage) ? kStageRows : rows_last;
-            mbar_expect_tx(bar0 + 8 * slot, rows_n * kStripRecBytes);
-            tma_load_1d(wb32 + Lay::ring + slot * Lay::slot_bytes, src_next, rows_n * kStripRecBytes, bar0 + 8 * slot);
+            mbar_expect_tx(bar0 + bar_off, rows_n * kStripRecBytes);
+            tma_load_1d(wb32 + Lay::ring + ring_off, src_next, rows_n * kStripRecBytes, bar0 + bar_off);
         }
 #pragma unroll
         for (int v0 = 0; v0 < NS * kStageRows; v0 += 16) {          // 16 vectors per round (two lanes each)
             const int nv = NS * kStageRows - v0 < 16 ? NS * kStageRows - v0 : 16;
-            double tx = 0.0, ty = 0.0;
+            double tot = 0.0;
             if (vsel < nv) {
+                double tx, ty;
+                lds_v2f64(rd_addr + v0 * 256, tx, ty);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 1; j < 8; ++j) {
                     double wx, wy;
                     lds_v2f64((rd_addr + v0 * 256) ^ (uint32_t)(32 * j), wx, wy);
                     tx += wx; ty += wy;
                 }
+                tot = tx + ty;
             }
-            double tot = tx + ty;
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             if ((lane & 1) == 0 && vsel < nv && (FULL || rsel < rows)) {
-                const int q = (v0 + vsel) / kStageRows;            // compact index of the sum
-                double sc = 1.0;
-                constexpr double ipv = 1.0 / PV;                    // the reducers expect S' / PV (jb_fused2.cuh)
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    if (f2_der(FL, c)) {
-                        const double st = f2_str(FL, c) ? rowc[rsel].st[c] : 1.0;
-                        if (q == f2_slot(NC, FL, c, 0)) sc = st * ipv;
-                        if (q == f2_slot(NC, FL, c, 2)) sc = (st * ipv) * (st * ipv);
-                    }
-                }
-                a.rowpart[((int64_t)my_row * a.n_strips + strip) * NSP + q] = tot * sc;
+                const double sc = kRowScale ? sum_scale((v0 + vsel) / kStageRows, rowc + rsel) : sc_lane[v0 / 16];
+                rowpart_p[v0 / kStageRows] = tot * sc;
             }
         }
         if (NS > 0) __syncwarp();                          // the tile is free for the next stage
@@ -651,8 +665,9 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     for (int s = 0; s < nfull; ++s) {
         if (sb == 0) checkpoint();
         stage_body(s, std::true_type{});
-        rowid_p += kStageRows;
+        rowpart_p += rowpart_step;
         src_next += kStageRows * kStripRec;
+        ring_off ^= Lay::slot_bytes; bar_off ^= 8u;
         if (++sb == spb) {
             // last stage of a block: its header slot is free, fetch the block after next
             if (lane == 0 && b + 2 < nblk) issue_hdr(b + 2);
