@@ -397,6 +397,7 @@ def run_b200(args, rank, world, local_rank):
                                 f"k_fused32<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 64 else
                                 f"k_fused2<2,{args.p_val},{info['fused_variant']}>" if info["fused_variant"] >= 0 else f"k_fused<2,{args.p_val}>"),
                      "kernel_ms": fused_batch_avg_ms, "launches_timed": int(fused_batch_n),
+                     "rows_per_task": int(info["rows_per_group"]), "strip_rows_per_block": int(info.get("strip_rows_per_block", 0)),
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": peak_src,
                      "timed": "CUDA events around the kernel on the launch stream inside the timed steps (one launch = all chunks of the GPU)",
                      "single_chunk_launch": {"kernel_ms": fused_avg_ms,

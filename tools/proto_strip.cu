@@ -139,7 +139,7 @@ int main(int argc, char** argv) {
         void* rowc; CK(cudaMalloc(&rowc, E * sizeof(StripRow<2>))); s.rowc = rowc;
         StripBlk* blk; CK(cudaMalloc(&blk, n_blocks * sizeof(StripBlk))); s.blk = blk;
         s.n_rows = E; s.n_strips = n_strips; s.K = K; s.blocks_per_task = BPT; s.n_blocks = n_blocks; s.n_rgroups = n_rgroups; s.ncls = ncls;
-        s.n_tasks = n_tasks; s.wincap = W; s.n_comp = 2;
+        s.n_tasks = n_tasks; s.wincap = W; s.n_comp = 2; s.tol = 0.004;
         for (int c = 0; c < 2; ++c) {
             CompDev& cd = s.comp[c]; memset(&cd, 0, sizeof cd);
             cd.p_val = 3; cd.n_knots = M; cd.xp0 = xp0; cd.inv_dx = 1.0 / dx; cd.ctrl = d_params + c * M;
@@ -151,7 +151,7 @@ int main(int argc, char** argv) {
         s.status = d_status;
         StripPrepParams& q = pp[i]; memset(&q, 0, sizeof q);
         q.rowid = d_rowid; q.xref = d_xref; q.rowc = rowc; q.blk = blk; q.n_rows = E; q.K = K; q.n_blocks = n_blocks; q.n_comp = 2;
-        q.comp[0] = s.comp[0]; q.comp[1] = s.comp[1]; q.status = nullptr;
+        q.comp[0] = s.comp[0]; q.comp[1] = s.comp[1]; q.status = nullptr; q.tol = 0.004;
         off_strip[i + 1] = off_strip[i] + (int)((n_tasks + kStripWarps - 1) / kStripWarps);
         off_prep[i + 1] = off_prep[i] + (n_blocks + 3) / 4;
     }

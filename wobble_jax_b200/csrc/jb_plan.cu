@@ -123,6 +123,7 @@ struct jb_plan {
     bool strip_disabled = false;    // a precondition failed at run time even after a re-sort: stay on k_fused2 / k_fused
     int strip_fail = 0;             // consecutive evaluations that raised a strip precondition
     int strip_reason = 0;           // jb_plan_info_t.strip_reason
+    double s_tol = 0.05;            // StripParams::tol of this plan
     int sK_force = 0;               // rows per block imposed by a batch (its plans share one launch, hence one K)
     int sK = 0, sBPT = 0, s_nblocks = 0, s_nrgroups = 0, s_ncls = 1, s_nstrips = 0, s_hint = 0;
     int64_t s_ntasks = 0;
@@ -268,25 +269,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
             key[c][pos] = xref[pos] - sh;
         }
     }
-    // rows per block: the largest K whose blocks keep every component's keys within 0.85 knots
-    // (k_prepare_strip refuses 1 - 2 kStripTol = 0.9 at run time: the margin is for the optimiser's steps)
-    int K = 0;
-    for (int cand : {32, 28, 24, 20, 16, 12, 8}) {
-        if (pl->sK_force && cand > pl->sK_force) continue;
-        bool ok = true;
-        for (int64_t r0 = 0; r0 < E && ok; r0 += cand)
-            for (int c = 0; c < NC && ok; ++c) {
-                double lo = INFINITY, hi = -INFINITY;
-                for (int64_t pos = r0; pos < std::min<int64_t>(E, r0 + cand); ++pos)
-                    if (std::isfinite(xref[pos])) { lo = std::min(lo, key[c][pos]); hi = std::max(hi, key[c][pos]); }
-                if (lo <= hi && !((hi - lo) / pl->desc[c].dx < 0.85)) ok = false;
-            }
-        if (ok) { K = cand; break; }
-    }
-    pl->strip_reason = 2;
-    if (K == 0) return JB_OK;      // rows too far apart for the column walk: k_fused2 / k_fused
     const int n_strips = (int)(pl->ppad / jb::kStripPx);
-    const int n_blocks = (int)((E + K - 1) / K);
     int rc;
     cudaStream_t st = pl->stream;
     if (!pl->d_sdata) {
@@ -304,35 +287,66 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
         if ((rc = dev_alloc(pl, &pl->d_sblk, (size_t)max_blocks))) return rc;
         if ((rc = dev_alloc(pl, &pl->d_sstats, (size_t)16))) return rc;
     }
+    double dx_max = 0.0, dx_min = INFINITY;
+    for (int c = 0; c < NC; ++c) { dx_max = std::max(dx_max, pl->desc[c].dx); dx_min = std::min(dx_min, pl->desc[c].dx); }
     JB_CUDA(cudaMemcpyAsync(pl->d_srowid, perm.data(), E * sizeof(int), cudaMemcpyHostToDevice, st));
     JB_CUDA(cudaMemcpyAsync(pl->d_sxref, xref.data(), E * sizeof(double), cudaMemcpyHostToDevice, st));
-    {
-        unsigned long long init[16];
-        for (int i = 0; i < 16; ++i) init[i] = i >= 3 ? ~0ULL : 0ULL;     // [3..10]: minima
-        JB_CUDA(cudaMemcpyAsync(pl->d_sstats, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
     {
         jb::StripLayoutParams lp;
         lp.tiled = pl->d_data; lp.rowid = pl->d_srowid; lp.sdata = pl->d_sdata; lp.n_rows = E; lp.n_tiles = pl->n_tiles;
         const int64_t warps = E * pl->n_tiles;
         jb::k_strip_layout<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(lp);
-        double dx_min = INFINITY;
-        for (int c = 0; c < NC; ++c) dx_min = std::min(dx_min, pl->desc[c].dx);
-        jb::StripXoffParams xp;
-        xp.sdata = pl->d_sdata; xp.xref = pl->d_sxref; xp.xoff = pl->d_sxoff; xp.n_rows = E; xp.n_strips = n_strips; xp.K = K;
-        xp.n_blocks = n_blocks; xp.tol_x = 0.999 * jb::kStripTol * dx_min; xp.stats = pl->d_sstats;
-        const int64_t w2 = (int64_t)n_strips * n_blocks;
-        jb::k_strip_xoff<<<(unsigned)((w2 + 7) / 8), 256, 0, st>>>(xp);
         JB_CUDA(cudaGetLastError());
-        pl->launches += 2;
+        pl->launches++;
     }
     unsigned long long stats[16];
-    JB_CUDA(cudaMemcpyAsync(stats, pl->d_sstats, sizeof stats, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
+    // column offsets of the blocks of K rows + the checks of preconditions (1) and (3)
+    auto run_xoff = [&](int K) -> int {
+        unsigned long long init[16];
+        for (int i = 0; i < 16; ++i) init[i] = i >= 3 ? ~0ULL : 0ULL;     // [3..10]: minima
+        JB_CUDA(cudaMemcpyAsync(pl->d_sstats, init, sizeof init, cudaMemcpyHostToDevice, st));
+        jb::StripXoffParams xp;
+        xp.sdata = pl->d_sdata; xp.xref = pl->d_sxref; xp.xoff = pl->d_sxoff; xp.n_rows = E; xp.n_strips = n_strips; xp.K = K;
+        xp.n_blocks = (int)((E + K - 1) / K); xp.tol_x = 0.999 * jb::kStripTol * dx_min; xp.stats = pl->d_sstats;
+        const int64_t w2 = (int64_t)n_strips * xp.n_blocks;
+        jb::k_strip_xoff<<<(unsigned)((w2 + 7) / 8), 256, 0, st>>>(xp);
+        JB_CUDA(cudaGetLastError());
+        pl->launches++;
+        JB_CUDA(cudaMemcpyAsync(stats, pl->d_sstats, sizeof stats, cudaMemcpyDeviceToHost, st));
+        JB_CUDA(cudaStreamSynchronize(st));
+        return JB_OK;
+    };
+    // first with the longest blocks: how far do the rows' pixel grids deviate from one another?  That
+    // sets the plan's tolerance, and with it how far apart the keys of a block may be.
+    if ((rc = run_xoff(32))) return rc;
     pl->strip_reason = 3;
     if (stats[0] != 0) return JB_OK;           // precondition (1): the pixel grid differs from row to row
-    double dx_max = 0.0, dx_min = INFINITY;
-    for (int c = 0; c < NC; ++c) { dx_max = std::max(dx_max, pl->desc[c].dx); dx_min = std::min(dx_min, pl->desc[c].dx); }
+    double dev;
+    memcpy(&dev, &stats[2], sizeof dev);
+    const double tol = std::min(jb::kStripTol, 1.5 * dev / dx_min + 2.0e-3);
+    pl->s_tol = tol;
+    // rows per block: the largest K whose blocks keep every component's keys 0.04 knots inside the
+    // 1 - 2 tol that k_prepare_strip refuses at run time (the margin is for the optimiser's steps)
+    // (K <= 20: a block's row records live in shared memory, and 20 rows is what leaves room for 16 warps per SM)
+    int K = 0;
+    for (int cand : {20, 16, 12, 8}) {
+        if (pl->sK_force && cand > pl->sK_force) continue;
+        bool ok = true;
+        for (int64_t r0 = 0; r0 < E && ok; r0 += cand)
+            for (int c = 0; c < NC && ok; ++c) {
+                double lo = INFINITY, hi = -INFINITY;
+                for (int64_t pos = r0; pos < std::min<int64_t>(E, r0 + cand); ++pos)
+                    if (std::isfinite(xref[pos])) { lo = std::min(lo, key[c][pos]); hi = std::max(hi, key[c][pos]); }
+                if (lo <= hi && !((hi - lo) / pl->desc[c].dx < 1.0 - 2.0 * tol - 0.04)) ok = false;
+            }
+        if (ok) { K = cand; break; }
+    }
+    pl->strip_reason = 2;
+    if (K == 0) return JB_OK;      // rows too far apart for the column walk: k_fused2 / k_fused
+    const int n_blocks = (int)((E + K - 1) / K);
+    if (K != 32 && (rc = run_xoff(K))) return rc;
+    pl->strip_reason = 3;
+    if (stats[0] != 0) return JB_OK;
     int ncls = 0;
     for (int nn = 1; nn <= 8 && !ncls; ++nn) {
         double gap;
@@ -367,7 +381,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     }
     if (!bpt_fit) return JB_OK;
     int bpt;
-    if (pl->s_hint > 0) bpt = std::max(1, (4 * pl->s_hint + K / 2) / K);
+    if (pl->s_hint > 0) bpt = 12;       // a batch keeps every warp slot busy anyway: long tasks (their set-up is ~15 % of a 120-row task)
     else {
         const int64_t groups_wanted = (148LL * 16 + n_strips - 1) / n_strips;
         bpt = (int)std::max<int64_t>(1, n_blocks / std::max<int64_t>(groups_wanted, 1));
@@ -537,12 +551,12 @@ int refresh_pack(jb_plan* pl) {
         sp.data = pl->d_sdata; sp.xoff = pl->d_sxoff; sp.xoff_rng = pl->d_sxoff_rng; sp.rowc = pl->d_srowc; sp.blk = pl->d_sblk;
         sp.rowid = pl->d_srowid; sp.n_rows = pl->E; sp.n_strips = pl->s_nstrips; sp.K = pl->sK; sp.blocks_per_task = pl->sBPT;
         sp.n_blocks = pl->s_nblocks; sp.n_rgroups = pl->s_nrgroups; sp.ncls = pl->s_ncls; sp.n_tasks = pl->s_ntasks;
-        sp.wincap = kStripWin; sp.n_comp = pl->n_glob;
+        sp.wincap = kStripWin; sp.n_comp = pl->n_glob; sp.tol = pl->s_tol;
         sp.part = pl->d_spart; sp.part_base = pl->d_spart_base; sp.rowpart = pl->d_srowpart; sp.losspart = pl->d_slosspart;
         sp.status = pl->d_status;
         jb::StripPrepParams& pp = k.sp;
         pp.rowid = pl->d_srowid; pp.xref = pl->d_sxref; pp.rowc = pl->d_srowc; pp.blk = pl->d_sblk; pp.n_rows = pl->E;
-        pp.K = pl->sK; pp.n_blocks = pl->s_nblocks; pp.n_comp = pl->n_glob; pp.status = pl->d_status;
+        pp.K = pl->sK; pp.n_blocks = pl->s_nblocks; pp.n_comp = pl->n_glob; pp.status = pl->d_status; pp.tol = pl->s_tol;
         for (int c = 0; c < pl->n_glob; ++c) sp.comp[c] = pp.comp[c] = pl->comp[c];
     }
     rp.rowsum = pl->d_rowsum;

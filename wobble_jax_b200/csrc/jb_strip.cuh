@@ -58,7 +58,8 @@ constexpr int kStripStages = JB_STRIP_STAGES;      // copies in flight per warp
 constexpr int kBatchRows = 8;                      // rows per transposed row-sum reduction
 constexpr int kStripWs = 32;                       // base intervals a task's table holds (lane j builds entry j)
 constexpr int kStripMaxK = 32;                     // rows per block, at most (multiple of kBatchRows)
-constexpr double kStripTol = 0.05;                 // knots: what precondition (1) allows
+constexpr double kStripTol = 0.05;                 // knots: the most precondition (1) allows; a plan's own tolerance
+                                                   // (StripParams::tol) is what its pixel grid needs, usually far less
 constexpr int kStatStrip = 8;                      // status bit: a weighted pixel left its two-interval span
 constexpr int kStripNoBase = INT_MIN;
 #ifndef JB_STRIP_WARPS
@@ -82,6 +83,7 @@ struct StripParams {
     int n_strips, K, blocks_per_task, n_blocks, n_rgroups, ncls;   // ncls: lanes this far apart never share a base interval
     int64_t n_tasks;
     int wincap;              // doubles per published gradient window (>= kStripWs + PV + 1, multiple of 32)
+    double tol;              // knots: how far a row's pixel grid may deviate from the block's column offsets
     int n_comp;
     CompDev comp[kMaxComp];
     double* part;            // [n_comp][n_tasks][wincap]
@@ -95,6 +97,7 @@ struct StripPrepParams {
     const int* rowid; const double* xref;      // [E] sorted order; xref = +inf for a row without weighted pixels
     void* rowc; StripBlk* blk;
     int64_t n_rows; int K, n_blocks, n_comp;
+    double tol;                                 // as StripParams::tol
     CompDev comp[kMaxComp];
     int* status;
 };
@@ -134,7 +137,7 @@ __global__ void k_prepare_strip(const StripPrepParams* __restrict__ arr, const i
         bool wide = false;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
-            if (kmin[c] <= kmax[c] && !((kmax[c] - kmin[c]) * a.comp[c].inv_dx < 1.0 - 2.0 * kStripTol - 1.0e-6)) wide = true;
+            if (kmin[c] <= kmax[c] && !((kmax[c] - kmin[c]) * a.comp[c].inv_dx < 1.0 - 2.0 * a.tol - 1.0e-6)) wide = true;
 
         StripBlk bk;
 #pragma unroll
@@ -404,20 +407,21 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     double xp0[NC], inv_dx[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { xp0[c] = a.comp[c].xp0; inv_dx[c] = a.comp[c].inv_dx; }
+    const double tol = a.tol;
     constexpr double kHalf = (PV & 1) ? 0.5 : 0.0;       // piece I covers u = t - kHalf in [I - 1/2, I + 1/2)
     constexpr double kKnot = (PV & 1) ? 1.0 : 0.5;       // t of the knot between piece I and piece I + 1, minus I
     // base interval of a column over a block: the piece that holds its smallest coordinate minus the
-    // tolerance.  The block's key range is less than 1 - 2 kStripTol knots wide (k_prepare_strip raises
+    // tolerance.  The block's key range is less than 1 - 2 tol knots wide (k_prepare_strip raises
     // kStatWindow otherwise), so every row of the block then lies in [base, base + 2).
     auto predict = [&](double xo, double kmin, int c, int& base) {
         const double umin = ((xo + kmin) - xp0[c]) * inv_dx[c] - kHalf;
-        const double fl = floor(umin - kStripTol + 0.5);
+        const double fl = floor(umin - tol + 0.5);
         base = fabs(fl) < 1.0e9 ? (int)fl : INT_MAX / 2;
     };
     // does the column reach into piece base + 1 during the block?
     auto needs_next = [&](double xo, double kmax, int c, int base) {
         const double umax = ((xo + kmax) - xp0[c]) * inv_dx[c] - kHalf;
-        return umax + kStripTol >= (double)base + 0.5;
+        return umax + tol >= (double)base + 0.5;
     };
 
     // ---- 1. window of the task: bases of its smallest and largest column offset over the key range
@@ -759,7 +763,8 @@ struct StripXoffParams {
     double* xoff;                                  // [n_strips][n_blocks][32]
     int64_t n_rows; int n_strips, K, n_blocks;
     double tol_x;                                  // kStripTol knots of the finest grid, in x
-    unsigned long long* stats;                     // [0] rows that break precondition (1)  [1] widest strip (x, as bits)  [2 + n] smallest x[p + n] - x[p], n = 1..8
+    unsigned long long* stats;                     // [0] rows that break precondition (1)  [1] widest strip (x, as bits)  [2] largest deviation (x, as bits)
+                                                   // [2 + n] smallest x[p + n] - x[p], n = 1..8
 };
 
 // One warp per (strip, block): the column offsets of the block and the checks of preconditions (1), (3).
@@ -784,6 +789,8 @@ __global__ void k_strip_xoff(StripXoffParams a) {
     a.xoff[((int64_t)strip * a.n_blocks + b) * 32 + lane] = xo;
     const bool bad = dev > a.tol_x || (have && !(fabs(xo) < 1.0e300));
     const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
     double xmin = have ? xo : INFINITY, xmax = have ? xo : -INFINITY;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -793,6 +800,7 @@ __global__ void k_strip_xoff(StripXoffParams a) {
     if (lane == 0) {
         if (nbad) atomicAdd(a.stats, (unsigned long long)nbad);
         if (xmin <= xmax) atomicMax(a.stats + 1, (unsigned long long)__double_as_longlong(xmax - xmin));   // >= 0: bits order like values
+        if (dev > 0.0 && dev < 1.0e300) atomicMax(a.stats + 2, (unsigned long long)__double_as_longlong(dev));
     }
     // smallest distance between weighted columns n lanes apart (negative: not monotone -> 0)
 #pragma unroll
