@@ -51,6 +51,10 @@ def parse():
                     help="host-buffer path of the end-to-end leg (chunks workload)")
     ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches in flight in the pinned end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the strong-scaling leg (64 chunks in total) and the epoch-sharded leg (configs[4])")
+    ap.add_argument("--es-epochs", type=int, default=50000, help="epochs of the epoch-sharded leg's single chunk")
+    ap.add_argument("--es-pixels", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget")
     ap.add_argument("--workload", default="chunks", choices=["chunks", "epochs"],
                     help="chunks: BASELINE configs[3] (default, the metric's config); epochs: configs[4], one chunk "
@@ -201,28 +205,28 @@ def run_b200(args, rank, world, local_rank):
     # ---- build: generate chunks on host threads, upload each into its plan ------------------
     t_setup = time.perf_counter()
 
+    # rows per task: a LONE plan sizes its tasks to one wave of the GPU; in a batched launch of many
+    # chunks there are dozens of waves anyway and long tasks amortise their set-up best (the hint)
+    rows_per_group = args.rows_per_group or (32 if args.chunks > 1 else 0)
+
     def make(c):
+        # generated, canonicalised and uploaded on a host thread of its own (ctypes drops the GIL)
+        torch.cuda.set_device(local_rank)
         ch = synth.make_chunk(rank * args.chunks + c, n_epochs=args.epochs, n_pix=args.pixels,
                               p_val=args.p_val, as_block=True)
         model = synth.fit_all(ch.model)
-        return ch, model
+        plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
+                           ch.datablock["mask"], ch.metablock, device=local_rank,
+                           rows_per_group=rows_per_group, float32=args.float32)
+        plan.sync_from_model()
+        return plan, np.asarray(model.get_parameters()).copy()
 
-    # rows per task: the plan's own choice (0) sizes a LONE plan to one wave of the GPU (28 rows here);
-    # in a batched launch of many chunks there are dozens of waves anyway and the longest groups the
-    # kernel takes (32 rows) amortise a task's set-up best (measured: 3.75 vs 3.78 ms per step)
-    rows_per_group = args.rows_per_group or (32 if args.chunks > 1 else 0)
     plans, p_host = [], []
-    nworkers = min(8, len(os.sched_getaffinity(0)), args.chunks)
+    nworkers = max(1, min(8, len(os.sched_getaffinity(0)) // max(world, 1), args.chunks))
     with ThreadPoolExecutor(nworkers) as pool:
-        for ch, model in pool.map(make, range(args.chunks)):
-            spec = engine.TreeSpec(model)
-            plan = engine.Plan(spec, ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
-                               ch.datablock["mask"], ch.metablock, device=local_rank,
-                               rows_per_group=rows_per_group, float32=args.float32)
-            plan.sync_from_model()
+        for plan, p in pool.map(make, range(args.chunks)):
             plans.append(plan)
-            p_host.append(np.asarray(model.get_parameters()).copy())
-            del ch
+            p_host.append(p)
     info = plans[0].info()
     n_fit = info["n_fit"]
     setup_s = time.perf_counter() - t_setup
@@ -355,6 +359,42 @@ def run_b200(args, rank, world, local_rank):
         e2e_s = time.perf_counter() - t0
     assert all(np.isfinite(host_losses))
 
+    # ---- strong scaling of the same workload: 64 chunks IN TOTAL (BASELINE.json configs[3]) -------
+    strong = None
+    total_chunks = 64
+    if not args.no_extra_legs and total_chunks % world == 0 and total_chunks // world <= len(plans):
+        per_gpu = total_chunks // world
+        if per_gpu == len(plans):
+            strong_ms = dev_ms / args.steps
+        else:
+            sub = engine.Batch(plans[:per_gpu])
+            sub.bind([t.data_ptr() for t in d_p[:per_gpu]], [t.data_ptr() for t in d_out[:per_gpu]])
+
+            def step_sub():
+                P_all.add_(1e-13)
+                sub.eval_device(main.cuda_stream)
+            for _ in range(args.warmup):
+                step_sub()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(main)
+            for _ in range(args.steps):
+                step_sub()
+            s1.record(main)
+            barrier()
+            strong_ms = s0.elapsed_time(s1) / args.steps
+            sub.check()
+            sub.close()
+        tt = torch.tensor([strong_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong_ms = float(tt[0])
+        strong = {"workload": f"synthetic {args.epochs} epochs x {args.pixels} px x {total_chunks} chunks IN TOTAL (BASELINE.json configs[3]), "
+                              f"{per_gpu} per GPU, chunk-sharded, no collective",
+                  "value": args.epochs * args.pixels * total_chunks / (strong_ms * 1e-3) / 1e9, "unit": UNIT,
+                  "ms_per_step": strong_ms, "chunks_per_gpu": per_gpu, "scaling": "strong",
+                  "hbm_frac_per_gpu": info["algorithmic_bytes"] * per_gpu / (strong_ms * 1e-3) / 1e9 / measured_peaks()[0]}
+
     # ---- reduce over ranks (max time) ---------------------------------------------------------
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -367,7 +407,7 @@ def run_b200(args, rank, world, local_rank):
     bytes_per_launch = info["algorithmic_bytes"] * args.chunks       # one launch serves every chunk of the GPU
     achieved = bytes_per_launch / (fused_batch_avg_ms * 1e-3) / 1e9
     traffic = None     # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath) and (args.epochs, args.pixels, args.p_val) == (2000, 4096, 3) and not args.float32:
         with open(tpath) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
@@ -393,6 +433,8 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic * args.chunks if traffic else None,
+                     "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per chunk of the committed "
+                                       "ncu --set full capture of this kernel, times the chunks of the launch (not measured in this run)" if traffic else None,
                      "kernel": (f"k_strip<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 128 else
                                 f"k_fused32<2,{args.p_val},{info['fused_variant'] & 15}>" if info["fused_variant"] >= 64 else
                                 f"k_fused2<2,{args.p_val},{info['fused_variant']}>" if info["fused_variant"] >= 0 else f"k_fused<2,{args.p_val}>"),
@@ -407,6 +449,20 @@ def run_b200(args, rank, world, local_rank):
         "setup_s": setup_s,
         "loss_chunk0": losses[0],
     }
+    out["strong_scaling"] = strong
+    # ---- BASELINE.json configs[4]: one chunk, epochs sharded over the ranks, NCCL all-reduce ---------
+    out["epoch_sharded"] = None
+    if not args.no_extra_legs and not args.float32:
+        if e2e_path == "pinned":
+            for hb in halves:
+                hb.close()
+        batch.close()
+        for pl in plans:
+            pl.close()
+        del P_all, O_all, d_p, d_out
+        torch.cuda.empty_cache()
+        out["epoch_sharded"] = epoch_sharded_leg(args, rank, world, local_rank, dist, args.es_epochs, args.es_pixels,
+                                                 args.steps, args.warmup)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
         ch, model, p, rows, cores = cpu_baseline(args, args.cpu_seconds)
@@ -428,89 +484,126 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_epochs(args, rank, world, local_rank):
-    """BASELINE configs[4]: ONE chunk, epochs sharded contiguously over the ranks; per evaluation the
-    ranks all-reduce [loss, dS, dT] (NCCL over NVLink); per-epoch gradients and Fisher stay local."""
+def epoch_sharded_leg(args, rank, world, local_rank, dist, epochs, pixels, steps, warmup):
+    """BASELINE configs[4]: ONE chunk of `epochs` x `pixels`, its epochs sharded contiguously over the
+    ranks.  A step is jb_group_eval_device: the rank's slabs in one launch per kernel, then the sum of
+    [loss, dS, dT] over the slabs, ONE ncclAllReduce of it (8 (1 + 2 M) bytes, NVLink) and the scatter
+    back, all enqueued by the library on one stream; per-epoch gradients and Fisher sums stay local."""
     import torch
     from wobble_jax_b200 import engine, synth
 
+    per = (epochs + world - 1) // world
+    e0 = rank * per
+    E = max(0, min(per, epochs - e0))
+    slab = 2048             # rows per plan: generated, canonicalised and uploaded slab by slab on host threads
+    starts = list(range(0, E, slab))
+    t_setup = time.perf_counter()
+
+    def make(s0):
+        torch.cuda.set_device(local_rank)
+        n = min(slab, E - s0)
+        ch = synth.make_chunk(0, n_epochs=n, n_pix=pixels, p_val=args.p_val, as_block=True,
+                              epoch_offset=e0 + s0 + 1, total_epochs=epochs)
+        model = synth.fit_all(ch.model)
+        plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
+                           ch.datablock["mask"], ch.metablock, device=local_rank, rows_per_group=32)
+        plan.sync_from_model()
+        return plan, np.asarray(model.get_parameters()).copy(), len(ch.grid)
+
+    plans, p_host = [], []
+    M = 0
+    nworkers = max(1, min(8, len(os.sched_getaffinity(0)) // max(world, 1), len(starts)))
+    with ThreadPoolExecutor(nworkers) as pool:
+        for plan, p, m in pool.map(make, starts):
+            plans.append(plan); p_host.append(p); M = m
+    setup_s = time.perf_counter() - t_setup
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in p_host])])
+    P_all = torch.from_numpy(np.concatenate(p_host)).cuda()
+    O_all = torch.empty(int(offs[-1]) + len(plans), dtype=torch.float64, device="cuda")
+    d_p = [P_all[int(offs[i]):int(offs[i + 1])] for i in range(len(plans))]
+    d_out = [O_all[int(offs[i]) + i:int(offs[i + 1]) + i + 1] for i in range(len(plans))]
+    nccl_id = engine.Group.broadcast_unique_id(rank, world) if world > 1 else None
+    group = engine.Group(plans, rank, world, nccl_id)
+    group.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
+    stream = torch.cuda.current_stream()
+
+    def step():
+        P_all.add_(1e-13)
+        group.eval_device(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    group.eval_device_checked(stream.cuda_stream)        # settles window sizes before the timed steps
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = group.launches()
+    plans[0].profile(True); plans[0].profile_read()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fused_ms, fused_n = plans[0].profile_read()
+    plans[0].profile(False)
+    for pl in plans:
+        pl.check()
+    ms = float(t[0]) / steps
+    loss = float(d_out[0][0])
+    info = plans[0].info()
+    ginfo = group.info()
+    launches = (group.launches() - launches0) // max(steps, 1)
+    peak, _ = measured_peaks()
+    px = epochs * pixels
+    bytes_total = px * 25 + 4 * M * 8 + epochs * 56
+    out = {
+        "workload": f"synthetic {epochs} epochs x {pixels} px single chunk (BASELINE.json configs[4]), epoch-sharded x{world}",
+        "value": px / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
+        "epochs_per_gpu": per, "plans_per_gpu": len(plans),
+        "hbm_frac_per_gpu": bytes_total / world / (ms * 1e-3) / 1e9 / peak,
+        "fused_kernel_ms": fused_ms / max(fused_n, 1),
+        "fused_kernel_hbm_frac": (bytes_total / world) / (fused_ms / max(fused_n, 1) * 1e-3) / 1e9 / peak if fused_n else None,
+        "collective": "ncclAllReduce(sum, f64) of [loss, dS, dT]" if world > 1 else "none (one rank)",
+        "collective_bytes": int(ginfo["collective_bytes"]), "launches_per_step": int(launches),
+        "api": "jb_group_eval_device (include/jabble_b200.h): kernels + gather + all-reduce + scatter on one stream",
+        "kernel": "k_strip" if info["fused_variant"] >= 128 else "k_fused2" if info["fused_variant"] >= 0 else "k_fused",
+        "loss": loss, "setup_s": setup_s,
+    }
+    group.close()
+    for pl in plans:
+        pl.close()
+    del P_all, O_all
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_epochs(args, rank, world, local_rank):
+    import torch
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    E_total = args.epochs
-    per = (E_total + world - 1) // world
-    e0 = rank * per
-    E = max(0, min(per, E_total - e0))
-    # generate and upload in slabs so the host never holds more than a few GB
-    slab = 4096
-    plans, d_p, d_out, sizes = [], [], [], []
-    for s0 in range(0, E, slab):
-        n = min(slab, E - s0)
-        ch = synth.make_chunk(0, n_epochs=n, n_pix=args.pixels, p_val=args.p_val, as_block=True,
-                              epoch_offset=e0 + s0 + 1, total_epochs=E_total)
-        model = synth.fit_all(ch.model)
-        plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
-                           ch.datablock["mask"], ch.metablock, device=local_rank, rows_per_group=args.rows_per_group)
-        plan.sync_from_model()
-        plans.append(plan)
-        p = np.asarray(model.get_parameters())
-        d_p.append(torch.from_numpy(p).cuda())
-        d_out.append(torch.empty(len(p) + 1, dtype=torch.float64, device="cuda"))
-        sizes.append((n, len(ch.grid)))
-        del ch
-    M = sizes[0][1]
-    red = torch.zeros(1 + 2 * M, dtype=torch.float64, device="cuda")     # [loss, dS, dT] of this rank
-    main = torch.cuda.Stream()            # non-default: a NULL stream means "the plan's own" to the C ABI
-    main.wait_stream(torch.cuda.current_stream())
-    torch.cuda.set_stream(main)
-    # the slabs of this rank are evaluated by ONE launch per kernel (jb_batch); their parameter
-    # vectors live in one flat buffer so that one add perturbs them all
-    offs = np.concatenate([[0], np.cumsum([t.numel() for t in d_p])])
-    P_all = torch.cat(d_p)
-    d_p = [P_all[int(offs[i]):int(offs[i + 1])] for i in range(len(plans))]
-    batch = engine.Batch(plans)
-    batch.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
-    views = [do[1 + n:1 + n + 2 * M] for do, (n, _) in zip(d_out, sizes)]   # fit order: shifts(n), S(M), T(M), airmass(n)
-    heads = [do[0:1] for do in d_out]
-
-    def step():
-        P_all.add_(1e-13)
-        batch.eval_device(main.cuda_stream)
-        torch.sum(torch.stack(views), dim=0, out=red[1:])
-        torch.sum(torch.cat(heads), dim=0, out=red[0])
-        if dist is not None:
-            dist.all_reduce(red)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0_.record(main)
-    for _ in range(args.steps):
-        step()
-    e1_.record(main)
-    torch.cuda.synchronize()
-    t = torch.tensor([e0_.elapsed_time(e1_)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    for pl in plans:
-        pl.check()
-    ms = float(t[0]) / args.steps
+    main_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(main_stream)
+    res = epoch_sharded_leg(args, rank, world, local_rank, dist, args.epochs, args.pixels, args.steps, args.warmup)
     if rank == 0:
-        px = E_total * args.pixels
         peak, src = measured_peaks()
         print(json.dumps({
-            "metric": METRIC, "value": px / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {E_total} epochs x {args.pixels} px single chunk (BASELINE.json configs[4]), "
-                                   f"epoch-sharded, NCCL all-reduce of [loss, dS, dT] = {8 * (1 + 2 * M)} B per evaluation",
-                       "epochs": E_total, "pixels": args.pixels, "parallelism": f"epoch-sharded x{world}"},
-            "hbm_frac_whole_step": px * 25 / (ms * 1e-3) / 1e9 / peak / world, "loss": float(red[0])}))
+            "config": {"workload": res["workload"], "epochs": args.epochs, "pixels": args.pixels,
+                       "parallelism": f"epoch-sharded x{world}"},
+            "epoch_sharded": res}))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -255,6 +255,37 @@ int jb_batch_soft_range(jb_batch *batch, int enable);
 int jb_batch_check(jb_batch *batch);
 int64_t jb_batch_launches(const jb_batch *batch);
 
+/*
+ * One chunk whose epochs are sharded over the GPUs of a box, ONE PROCESS PER GPU (BASELINE.json
+ * configs[4]).  The reference's analogue is the epoch micro-batch loop of LossFunc.loss_all
+ * (jabble/loss.py:64-74): per-batch losses add up; here the batches live on different GPUs.
+ * Every rank creates the plans of its own rows (same model, the templates replicated; rows are
+ * split on which_key boundaries so that every epoch key lives on one rank) and one jb_group over
+ * them.  jb_group_eval_device enqueues, on one stream and without host work in between: the rank's
+ * plans (one launch per kernel, as jb_batch_eval_device), the sum over the rank's plans of the loss
+ * and of the gradient of every fit-mode template control point, one ncclAllReduce of that vector
+ * (8 (1 + n_shared) bytes) over NVLink, and the totals written back into every plan's output.
+ * Afterwards out[0] of every plan is the loss of the WHOLE chunk and the control-point entries of
+ * its gradient are those of the whole chunk; per-epoch entries (shifts, stretches, their Fisher
+ * sums) are the rank's own.  world = 1 needs no NCCL and no id.
+ * NCCL is loaded at the first use (dlopen: the one already in the process when there is one, else
+ * libnccl.so.2, else $JB_NCCL_LIB); rank 0 calls jb_nccl_unique_id and hands the 128 bytes to the
+ * other ranks by any means (the host side here uses torch.distributed).
+ */
+typedef struct jb_group jb_group;
+int jb_nccl_unique_id(void *id128);
+int jb_nccl_version(void);          /* 0: NCCL not available */
+int jb_group_create(jb_plan *const *plans, int32_t n_plans, int32_t rank, int32_t world, const void *nccl_id128,
+                    jb_group **out);
+void jb_group_destroy(jb_group *group);       /* destroys the communicator, not the plans */
+int jb_group_bind(jb_group *group, const double *const *d_p_fit, double *const *d_out);   /* as jb_batch_bind */
+int jb_group_eval_device(jb_group *group, void *stream);
+/* The same, but the rank's plans are settled first as in jb_batch_eval_device_checked (re-sort, wider
+ * windows; a rank off the knot grid contributes a NaN loss, which every rank then sees); waits. */
+int jb_group_eval_device_checked(jb_group *group, void *stream);
+int jb_group_info(const jb_group *group, int64_t *n_shared, int64_t *collective_bytes, int32_t *world);
+int64_t jb_group_launches(const jb_group *group);
+
 /* The plan's own cudaStream_t (so that a caller can order its work, or time it with events). */
 int jb_plan_stream(jb_plan *plan, void **stream_out);
 

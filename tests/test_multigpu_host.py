@@ -73,3 +73,15 @@ def _worker(rank, world, port, n):
 
 def test_all_reduce_gloo_world2():
     mp.spawn(_worker, args=(2, _free_port(), 11), nprocs=2, join=True)
+
+
+def test_epoch_sharding_refuses_empty_shards_on_every_rank_alike():
+    """More ranks than epoch keys: every rank must raise before any collective (none may hang)."""
+    import wobble_jax_b200 as jabble
+    ch = synth.make_chunk(0, n_epochs=3, n_pix=130, p_val=3, n_lines=3)
+    db, mb = ch.data.blockify()
+    parts = multigpu.shard_rows_by_key(multigpu.epoch_keys(ch.model, mb), 8)
+    assert sum(len(p) == 0 for p in parts) > 0
+    for rank in range(8):
+        with pytest.raises(ValueError, match="without rows"):
+            multigpu.EpochShardedObjective(jabble.loss.ChiSquare(), ch.model, db, mb, rank, 8)

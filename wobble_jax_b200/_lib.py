@@ -90,6 +90,15 @@ SYMBOLS = [
     ("jb_batch_soft_range", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_batch_check", C.c_int, [C.c_void_p]),
     ("jb_batch_launches", C.c_int64, [C.c_void_p]),
+    ("jb_nccl_unique_id", C.c_int, [C.c_void_p]),
+    ("jb_nccl_version", C.c_int, []),
+    ("jb_group_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("jb_group_destroy", None, [C.c_void_p]),
+    ("jb_group_bind", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("jb_group_eval_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("jb_group_eval_device_checked", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("jb_group_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    ("jb_group_launches", C.c_int64, [C.c_void_p]),
     ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("jb_plan_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_plan_profile_read", C.c_int, [C.c_void_p, c_f64p, c_i64p]),

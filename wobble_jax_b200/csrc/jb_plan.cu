@@ -87,6 +87,7 @@ struct jb_plan {
 
     int64_t n_params = 0, n_fit = 0;
     bool fit_bufs = false;      // d_fit_map / d_pfit / d_out / h_pfit / h_out sized for n_fit
+    std::vector<int64_t> h_fit_map;   // host copy of the fit map (jb_group: which outputs are sums over all rows)
     double *d_params = nullptr, *d_grad_all = nullptr, *d_fisher_all = nullptr;
     std::vector<double> h_params;
     bool params_set = false, sort_dirty = true;
@@ -1284,6 +1285,7 @@ int jb_plan_set_fit(jb_plan* pl, const int64_t* fit_index, int64_t n_fit) {
         pl->fit_bufs = true;
     }
     if (n_fit) JB_CUDA(cudaMemcpy(pl->d_fit_map, fit_index, n_fit * sizeof(int64_t), cudaMemcpyHostToDevice));
+    pl->h_fit_map.assign(fit_index, fit_index + n_fit);
     pl->n_fit = n_fit;
     for (int c = 0; c < pl->n_comp; ++c) {
         pl->fit_shift[c] = false;
@@ -1869,3 +1871,5 @@ int jb_plan_grad_all(jb_plan* pl, double* grad_all, int64_t n) {
 }
 
 }  // extern "C"
+
+#include "jb_group.cuh"

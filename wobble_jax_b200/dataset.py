@@ -139,6 +139,13 @@ class Data:
     def blockify(self, device=None):
         """dataset.py:192-237 -- pad every row to the longest one (x = y = ivar = 0, mask = True)
         and turn every metadata key into dense integer ids.  Returns (datablock, metablock)."""
+        # The same frames give the same block OBJECTS, so that everything downstream keyed on the block
+        # (the resident copy in HBM: engine.get_plan) is reused call after call.  The fingerprint holds
+        # the identity of every array and a checksum of its contents (an in-place edit is noticed).
+        fp = self._fingerprint()
+        memo = getattr(self, "_block_memo", None)
+        if memo is not None and memo[0] == fp:
+            return memo[1], memo[2]
         E = len(self)
         max_ind = int(np.max([len(f.xs) for f in self.dataframes]))
         xs = np.zeros((E, max_ind))
@@ -163,4 +170,17 @@ class Data:
                 epoch_uniques, epoch_indices = np.unique(self.metadata[key], return_inverse=True)
             self.metakeys[key] = epoch_uniques
             metablock[key] = np.asarray(epoch_indices).astype(int)
-        return DataBlock(xs=xs, ys=ys, yivar=yivar, mask=mask), DataBlock(**metablock)
+        out = DataBlock(xs=xs, ys=ys, yivar=yivar, mask=mask), DataBlock(**metablock)
+        self._block_memo = (fp, out[0], out[1])
+        return out
+
+    def _fingerprint(self):
+        parts = []
+        for f in self.dataframes:
+            for a in (f.xs, f.ys, f.yivar, f.mask):
+                arr = np.asarray(a)
+                parts.append((id(a), arr.shape, float(np.sum(arr, dtype=np.float64)) if arr.size else 0.0))
+        for key in sorted(self.metadata):
+            arr = np.asarray(self.metadata[key])
+            parts.append((key, id(self.metadata[key]), arr.shape, arr.tobytes() if arr.size <= 4096 else hash(arr.tobytes())))
+        return tuple(parts)

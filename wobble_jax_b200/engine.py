@@ -212,6 +212,10 @@ class Plan:
         _lib.check(lib.jb_plan_create(C.byref(desc), C.byref(handle)))
         self.handle = handle
         self.n_fit = 0
+        self._last_params = None      # what jb_plan_set_params last uploaded ...
+        self._params_clean = False    # ... and whether the device copy still equals it (an evaluation scatters its fit vector)
+        self._last_fit = None
+        self._owner = None            # the Objective whose fit flags / fixed parameters the plan currently holds
         del keep
 
     def close(self):
@@ -224,12 +228,18 @@ class Plan:
     # ----------------------------------------------------------------------------------------
     def set_params(self, params_all):
         p = np.ascontiguousarray(params_all, dtype=np.float64)
+        if self._params_clean and self._last_params is not None and np.array_equal(p, self._last_params):
+            return                     # nothing changed since the last upload: no copy, no re-sort
         _lib.check(self.lib.jb_plan_set_params(self.handle, p.ctypes.data_as(_lib.c_f64p), p.size))
+        self._last_params, self._params_clean = p.copy(), True
 
     def set_fit(self, fit_index):
         idx = np.ascontiguousarray(fit_index, dtype=np.int64)
+        if self._last_fit is not None and np.array_equal(idx, self._last_fit):
+            return
         _lib.check(self.lib.jb_plan_set_fit(self.handle, idx.ctypes.data_as(_lib.c_i64p), idx.size))
         self.n_fit = idx.size
+        self._last_fit = idx.copy()
 
     def sync_from_model(self):
         """Upload the tree's current parameter values and fit flags."""
@@ -238,6 +248,8 @@ class Plan:
 
     def eval(self, p_fit, want_grad=True):
         p = np.ascontiguousarray(p_fit, dtype=np.float64).reshape(-1)
+        if p.size:
+            self._params_clean = False
         loss = C.c_double()
         grad = np.empty(p.size, dtype=np.float64) if want_grad else None
         _lib.check(self.lib.jb_plan_eval(
@@ -247,6 +259,8 @@ class Plan:
 
     def forward(self, p_fit=()):
         p = np.ascontiguousarray(p_fit, dtype=np.float64).reshape(-1)
+        if p.size:
+            self._params_clean = False
         out = np.empty(self.shape, dtype=np.float64)
         _lib.check(self.lib.jb_plan_forward(self.handle, p.ctypes.data_as(_lib.c_f64p), p.size,
                                             out.ctypes.data_as(_lib.c_f64p)))
@@ -288,6 +302,7 @@ class Plan:
 
     def eval_device(self, d_p_fit_ptr, d_out_ptr, stream_ptr=0):
         """Enqueue one evaluation with device-resident in/out (see jb_plan_eval_device)."""
+        self._params_clean = False
         _lib.check(self.lib.jb_plan_eval_device(self.handle, C.c_void_p(d_p_fit_ptr), C.c_void_p(d_out_ptr),
                                                 C.c_void_p(stream_ptr)))
 
@@ -316,6 +331,8 @@ class Batch:
     def __init__(self, plans):
         self.lib = _lib.load()
         self.plans = list(plans)
+        for p in self.plans:
+            p._params_clean = False       # batched evaluations scatter fit vectors into the plans' parameters
         arr = (C.c_void_p * len(self.plans))(*[p.handle for p in self.plans])
         handle = C.c_void_p()
         _lib.check(self.lib.jb_batch_create(arr, len(self.plans), C.byref(handle)))
@@ -408,6 +425,76 @@ class Batch:
     __del__ = close
 
 
+class Group:
+    """One chunk whose epochs are sharded over the GPUs of a box, one process per GPU (``jb_group``):
+    the rank's plans evaluated with one launch per kernel, then ONE NCCL all-reduce of
+    [loss, gradient of the template control points] enqueued behind them on the same stream.
+
+    ``rank`` / ``world_size``: this process's place; ``nccl_id``: the 128 bytes of
+    ``Group.unique_id()`` made on rank 0 and handed to every rank (``broadcast_unique_id`` does it
+    through torch.distributed).  ``world_size`` 1 needs neither NCCL nor an id."""
+
+    def __init__(self, plans, rank=0, world_size=1, nccl_id=None):
+        self.lib = _lib.load()
+        self.plans = list(plans)
+        arr = (C.c_void_p * len(self.plans))(*[p.handle for p in self.plans])
+        handle = C.c_void_p()
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
+        _lib.check(self.lib.jb_group_create(arr, len(self.plans), int(rank), int(world_size), idbuf, C.byref(handle)))
+        self.handle = handle
+        self.rank, self.world_size = int(rank), int(world_size)
+        for p in self.plans:
+            p._params_clean = False
+
+    @staticmethod
+    def unique_id():
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        _lib.check(lib.jb_nccl_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def broadcast_unique_id(rank, world_size, group=None):
+        """The NCCL id of rank 0 on every rank, through torch.distributed (any backend)."""
+        if world_size <= 1:
+            return None
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(Group.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0, group=group)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def bind(self, d_p_fit_ptrs, d_out_ptrs):
+        n = len(self.plans)
+        pf = (C.c_void_p * n)(*d_p_fit_ptrs) if d_p_fit_ptrs is not None else None
+        po = (C.c_void_p * n)(*d_out_ptrs)
+        _lib.check(self.lib.jb_group_bind(self.handle, pf, po))
+
+    def eval_device(self, stream_ptr=0):
+        _lib.check(self.lib.jb_group_eval_device(self.handle, C.c_void_p(stream_ptr)))
+
+    def eval_device_checked(self, stream_ptr=0):
+        _lib.check(self.lib.jb_group_eval_device_checked(self.handle, C.c_void_p(stream_ptr)))
+
+    def info(self):
+        ns, nb, w = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(self.lib.jb_group_info(self.handle, C.byref(ns), C.byref(nb), C.byref(w)))
+        return {"n_shared": ns.value, "collective_bytes": nb.value, "world": w.value}
+
+    def launches(self):
+        return int(self.lib.jb_group_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.jb_group_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
 def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_group=0, general_kernel=False,
                float32=False, no_strip=False):
     spec = TreeSpec(model)
@@ -416,6 +503,57 @@ def build_plan(model, datablock, metablock, coefficient=1.0, device=0, rows_per_
                 float32=float32, no_strip=no_strip)
     plan.sync_from_model()
     return plan
+
+
+# ------------------------------------------------------------------------------------------
+# One resident copy of a data block serves every call made on it: Model.optimize stage after stage,
+# grid_search, f_info, the curvature, get_loss_array, train_norm's forward (the reference re-bakes the
+# data into a new XLA program per optimize() call, loss.py:47).  Between calls only parameter values
+# and fit flags change (jb_plan_set_params / jb_plan_set_fit).
+_PLAN_CACHE = []          # [(key, datablock, metablock, plan)], most recently used last
+PLAN_CACHE_SIZE = 2
+
+
+def clear_plan_cache():
+    """Forget every cached plan; its HBM is freed as soon as nothing else refers to it."""
+    del _PLAN_CACHE[:]
+
+
+def get_plan(model, datablock, metablock, coefficient=1.0, device=0, unit_weights=None):
+    """The cached Plan of (data block, tree structure, data term), synchronised with the model's
+    current parameter values and fit flags.  ``unit_weights``: a constant that replaces ``yivar``
+    (L2Loss).  The plan belongs to the cache: do not close it."""
+    spec = TreeSpec(model)
+    key = (id(datablock), id(metablock), spec.signature(), float(coefficient), unit_weights, int(device))
+    for i, (k, db, mb, plan) in enumerate(_PLAN_CACHE):
+        if k == key and db is datablock and mb is metablock and plan.handle:
+            _PLAN_CACHE.append(_PLAN_CACHE.pop(i))
+            plan.spec = spec
+            plan.sync_from_model()
+            plan._owner = None
+            return plan
+    yivar = datablock["yivar"]
+    if unit_weights is not None and datablock["ys"] is not None:
+        yivar = np.full_like(np.asarray(datablock["ys"], dtype=np.float64), float(unit_weights))
+    plan = Plan(spec, datablock["xs"], datablock["ys"], yivar, datablock["mask"], metablock,
+                coefficient=coefficient, device=device)
+    plan.sync_from_model()
+    _PLAN_CACHE.append((key, datablock, metablock, plan))
+    while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+        _PLAN_CACHE.pop(0)          # an objective still using it keeps it alive; Plan.__del__ frees the HBM
+    return plan
+
+
+def _loss_key(loss):
+    """The values a loss tree is made of (not its repr, which rounds the coefficient and omits constants)."""
+    from . import loss as L
+    terms = loss.loss_funcs if isinstance(loss, L.LossSequential) else [loss]
+    out = []
+    for t in terms:
+        inds = getattr(t, "submodel_inds", None)
+        out.append((type(t).__name__, float(getattr(t, "coefficient", 1.0)), float(getattr(t, "constant", 0.0)),
+                    None if inds is None else tuple(np.asarray(inds).reshape(-1).tolist())))
+    return tuple(out)
 
 
 class Objective:
@@ -435,13 +573,12 @@ class Objective:
         if len(data_terms) != 1:
             raise NotImplementedError("exactly one data term (ChiSquare or L2Loss) per objective is supported")
         term = data_terms[0]
-        yivar = datablock["yivar"]
-        if isinstance(term, L.L2Loss):      # (ys - m)**2 == 0.5 * 2 * (ys - m)**2 : ChiSquare with unit weights x 2
-            yivar = np.full_like(np.asarray(datablock["ys"], dtype=np.float64), 2.0)
-        spec = TreeSpec(model)
-        self.plan = Plan(spec, datablock["xs"], datablock["ys"], yivar, datablock["mask"], metablock,
-                         coefficient=term.coefficient, device=device)
-        self.plan.sync_from_model()
+        # (ys - m)**2 == 0.5 * 2 * (ys - m)**2 : an L2Loss is a ChiSquare with unit weights x 2
+        self.plan = get_plan(model, datablock, metablock, coefficient=term.coefficient, device=device,
+                             unit_weights=2.0 if isinstance(term, L.L2Loss) else None)
+        self._params_all = self.plan.spec.params_all()        # what this objective's evaluations start from
+        self._fit_index = self.plan.spec.fit_index()
+        self.plan._owner = self
         self.n_rows = len(datablock)
         for r in self.regs:
             if r.indices is None:
@@ -452,24 +589,31 @@ class Objective:
         self._f = None
         self._g = None
         self._f_inside = None                 # loss of the last evaluation that stayed inside the knot grids
-        self._data_eval = self.plan.eval      # (loss, gradient) of the data term; LockstepEvaluator reroutes it
+        self._data_eval = self._plan_eval     # (loss, gradient) of the data term; LockstepEvaluator reroutes it
+
+    def _plan_eval(self, p):
+        if self.plan._owner is not self:      # another objective used the shared plan in between
+            self.plan.set_params(self._params_all)
+            self.plan.set_fit(self._fit_index)
+            self.plan._owner = self
+        return self.plan.eval(p)
 
     @classmethod
     def cached(cls, loss, model, datablock, metablock):
-        """Reuse the resident data block between loss_all / grad_all calls on the same objects;
-        parameters and fit flags are re-read from the model tree every time."""
-        key = (id(datablock), id(metablock), id(model), repr(loss))
+        """One objective per (data block, model, loss VALUES, fit state, stored parameters) between
+        loss_all / grad_all calls: scipy's func and fprime then share one fused evaluation."""
+        spec = TreeSpec(model)
+        fit = tuple(bool(lf.node._fit) for lf in spec.leaves)
+        key = (id(datablock), id(metablock), id(model), _loss_key(loss), spec.signature(), fit)
         obj = cls._cache.get(key)
-        sig = TreeSpec(model).signature()
-        if obj is None or obj._sig != sig or obj._db is not datablock:
-            cls._cache.clear()          # one resident block at a time
-            obj = cls(loss, model, datablock, metablock)
-            obj._sig, obj._db = sig, datablock
-            cls._cache[key] = obj
-        else:
-            obj.plan.spec = TreeSpec(model)
-            obj.plan.sync_from_model()
-            obj._p = None
+        if obj is not None and obj._db is datablock and np.array_equal(obj._params_all[~obj._fit_mask], spec.params_all()[~obj._fit_mask]):
+            return obj
+        cls._cache.clear()              # one at a time
+        obj = cls(loss, model, datablock, metablock)
+        obj._db = datablock
+        obj._fit_mask = np.zeros(spec.n_params, dtype=bool)
+        obj._fit_mask[spec.fit_index()] = True
+        cls._cache[key] = obj
         return obj
 
     def _eval(self, p):
@@ -579,7 +723,7 @@ class LockstepEvaluator:
             entry[0].close()
         self.batches.clear()
         for o in self.objs:
-            o._data_eval = o.plan.eval
+            o._data_eval = o._plan_eval
 
 
 def _meta_value(meta, key):
@@ -624,13 +768,7 @@ def shift_curvature(model, shift_model, datablock, metablock, coefficient=1.0, d
             comp = i
     if comp is None:
         raise NotImplementedError("the curvature runs on the CUDA path for the ShiftingModel of an additive component only")
-    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
-                coefficient=coefficient, device=device)
-    try:
-        plan.sync_from_model()
-        return plan.curvature(comp)
-    finally:
-        plan.close()
+    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device).curvature(comp)
 
 
 def grid_search(model, shift_model, datablock, metablock, grid, coefficient=1.0, device=0):
@@ -642,13 +780,7 @@ def grid_search(model, shift_model, datablock, metablock, grid, coefficient=1.0,
             comp = i
     if comp is None:
         raise NotImplementedError("grid_search runs on the CUDA path for the ShiftingModel of an additive component only")
-    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock,
-                coefficient=coefficient, device=device)
-    try:
-        plan.sync_from_model()
-        return plan.grid_search(comp, grid)
-    finally:
-        plan.close()
+    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device).grid_search(comp, grid)
 
 
 def fisher_information(model, rv_model, datablock, metablock, device=0):
@@ -660,9 +792,4 @@ def fisher_information(model, rv_model, datablock, metablock, device=0):
             comp = i
     if comp is None:
         raise ValueError("f_info: the model is not the ShiftingModel of any additive component of the tree")
-    plan = Plan(spec, datablock["xs"], datablock["ys"], datablock["yivar"], datablock["mask"], metablock, device=device)
-    try:
-        plan.sync_from_model()
-        return plan.fisher(comp)
-    finally:
-        plan.close()
+    return get_plan(model, datablock, metablock, device=device).fisher(comp)

@@ -4,9 +4,9 @@ SURVEY.md section 8e.  The reference's only parallelism is a ``multiprocessing.P
 orders (notebooks/02-51peg.py:66-78): chunks/orders are independent fits, so they are dealt
 round-robin to the ranks and nothing is exchanged.  When ONE chunk has more epochs than a GPU
 should hold, its rows are split across ranks on ``which_key`` boundaries (every epoch key lives on
-one rank); loss and control-point gradients are sums over rows, so one
-``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs) of the ``[loss, gradient]`` vector
-completes the evaluation -- per-key entries receive zeros from the ranks that do not own the key.
+one rank); loss and control-point gradients are sums over rows, so ONE
+``ncclAllReduce`` of ``[loss, template gradients]`` enqueued by the library behind the kernels
+(``jb_group``, include/jabble_b200.h) completes them; per-epoch entries belong to one rank.
 """
 
 import numpy as np
@@ -71,10 +71,14 @@ def all_reduce_sum(vec, group=None):
 class EpochShardedObjective:
     """(func, fprime) for ONE chunk whose rows are split over the ranks of ``group``.
 
-    Every rank holds its rows in a plan; an evaluation is the local fused kernel, then one
-    all-reduce of the device-resident ``[loss, grad]`` vector, then a single D2H copy.  All ranks
-    must call ``value``/``gradient`` with the same parameter vector (scipy runs on every rank, or
-    rank 0 broadcasts).
+    Every rank holds its rows in a plan of the WHOLE model; an evaluation is ``jb_group_eval_device``
+    (the local fused kernels, then one NCCL all-reduce of [loss, template gradients], 8 (1 + 2 M)
+    bytes, enqueued behind them by the library), then -- because scipy on every rank needs the whole
+    gradient -- one all-reduce of the per-epoch entries (each key has rows on one rank only, the other
+    ranks contribute zeros), then a single D2H copy.  All ranks must call ``value`` / ``gradient``
+    with the same parameter vector.  A rank whose trial point leaves a knot grid contributes a NaN
+    loss, so every rank takes the same branch; knot-window overflows (the shifts drifted since the
+    rows were sorted) are settled inside the library, rank by rank, before the exchange.
     """
 
     def __init__(self, loss, model, datablock, metablock, rank, world_size, device=0, group=None):
@@ -84,7 +88,12 @@ class EpochShardedObjective:
             raise NotImplementedError("only ChiSquare runs on the CUDA path")
         self.torch = torch
         self.group = group
-        rows = shard_rows_by_key(epoch_keys(model, metablock), world_size)[rank]
+        parts = shard_rows_by_key(epoch_keys(model, metablock), world_size)
+        empty = [r for r, rows in enumerate(parts) if rows.size == 0]
+        if empty:      # the same on every rank: nobody enters a collective
+            raise ValueError(f"epoch sharding over {world_size} ranks leaves rank(s) {empty} without rows "
+                             f"({len(np.unique(epoch_keys(model, metablock)))} epoch keys): use fewer ranks")
+        rows = parts[rank]
         self.rows = rows
         db, mb = take_rows(datablock, metablock, rows)
         self.plan = engine.build_plan(model, db, mb, coefficient=loss.coefficient, device=device)
@@ -92,9 +101,28 @@ class EpochShardedObjective:
         self.dev = torch.device("cuda", device)
         self.d_p = torch.empty(max(self.n_fit, 1), dtype=torch.float64, device=self.dev)
         self.d_out = torch.empty(self.n_fit + 1, dtype=torch.float64, device=self.dev)
+        # which outputs are per-epoch (not template control points): they cross the ranks separately
+        spec = engine.TreeSpec(model)
+        local, o = [], 1
+        for lf in spec.leaves:
+            if lf.node._fit:
+                if hasattr(lf.node, "which_key") and not hasattr(lf.node, "xs"):
+                    local.append((o, o + lf.size))
+                o += lf.size
+        self.local_slices = local
+        # without an initialised torch.distributed the shard stands alone (its sums are the caller's to add up)
+        import torch.distributed as dist
+        comm_world = world_size if (dist.is_available() and dist.is_initialized()) else 1
+        nccl_id = None
+        if comm_world > 1:
+            torch.cuda.set_device(self.dev)
+            nccl_id = engine.Group.broadcast_unique_id(rank, comm_world, group)
+        self.jgroup = engine.Group([self.plan], rank if comm_world > 1 else 0, comm_world, nccl_id)
+        self.jgroup.bind([self.d_p.data_ptr()], [self.d_out.data_ptr()])
         # a real stream (the C ABI reads NULL as "the plan's own stream"), made current for the copies
-        # and the all-reduce so that everything is ordered on it
+        # and the second all-reduce so that everything is ordered on it
         self.stream = torch.cuda.Stream(self.dev)
+        self.world_size = comm_world
         self._p = None
         self._f = None
         self._g = None
@@ -106,25 +134,19 @@ class EpochShardedObjective:
         if self._p is None or not np.array_equal(p, self._p):
             with torch.cuda.stream(self.stream):
                 self.d_p[:self.n_fit].copy_(torch.from_numpy(p), non_blocking=True)
-                self.plan.eval_device(self.d_p.data_ptr(), self.d_out.data_ptr(), self.stream.cuda_stream)
-                all_reduce_sum(self.d_out, self.group)
+                self.jgroup.eval_device_checked(self.stream.cuda_stream)
+                if self.world_size > 1:
+                    for a, b in self.local_slices:
+                        all_reduce_sum(self.d_out[a:b], self.group)
                 out = self.d_out.cpu().numpy()
-            # A shard whose trial point leaves a knot grid writes a NaN loss (k_finish), so after the
-            # all-reduce EVERY rank sees NaN and takes the same branch: the first evaluation raises, a
-            # later one (a line-search excursion) gets the penalty engine.Objective gives it.
-            try:
-                self.plan.check()
-                err = None
-            except ValueError as exc:
-                err = exc
             if not np.isfinite(out[0]):
+                # some rank's pixels left a knot grid (its k_finish wrote NaN; the all-reduce spread it):
+                # the first evaluation raises, a later one (a line-search excursion) gets the penalty
+                # engine.Objective gives it -- on every rank alike
                 if self._f_inside is None:
-                    raise err if err is not None else ValueError(
-                        "an unmasked warped pixel lies outside the knot grid of a spline component (on another rank)")
+                    raise ValueError("an unmasked warped pixel lies outside the knot grid of a spline component (on some rank)")
                 out = np.concatenate([[1e8 * max(abs(self._f_inside), 1.0)], np.zeros(self.n_fit)])
             else:
-                if err is not None:
-                    raise err
                 self._f_inside = float(out[0])
             self._f, self._g, self._p = float(out[0]), out[1:].copy(), p.copy()
         return self._f, self._g
@@ -134,3 +156,7 @@ class EpochShardedObjective:
 
     def gradient(self, p):
         return self._eval(p)[1].copy()
+
+    def close(self):
+        self.jgroup.close()
+        self.plan.close()

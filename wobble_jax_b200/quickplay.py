@@ -236,11 +236,7 @@ def train_norm(model, dataset, loss, device_store=None, device_op=None, batch_si
         print(res1)
         model.fix()
         datablock, metablock = dataset.blockify(device_op)
-        plan = engine.build_plan(model, datablock, metablock)
-        try:
-            fwd = plan.forward()
-        finally:
-            plan.close()
+        fwd = engine.get_plan(model, datablock, metablock, coefficient=getattr(loss, "coefficient", 1.0)).forward()
         for data_epoch in range(len(dataset)):
             frame = dataset[data_epoch]
             mask = np.asarray(frame.mask, dtype=bool)
@@ -324,11 +320,8 @@ def get_loss_array(model, datablock, metablock, loss, device=None):
     if not isinstance(loss, L.ChiSquare):
         raise NotImplementedError("get_loss_array runs on the CUDA path for ChiSquare only")
     loss.ready_indices(model)
-    plan = engine.build_plan(model, datablock, metablock)
-    try:
-        fwd = plan.forward(np.asarray(model.get_parameters(), dtype=np.float64))
-    finally:
-        plan.close()
+    fwd = engine.get_plan(model, datablock, metablock, coefficient=loss.coefficient).forward(
+        np.asarray(model.get_parameters(), dtype=np.float64))
     mask = np.asarray(datablock["mask"], dtype=bool)
     with np.errstate(invalid="ignore"):
         arr = 0.5 * np.asarray(datablock["yivar"]) * (np.asarray(datablock["ys"]) - fwd) ** 2
