@@ -412,6 +412,21 @@ def run_b200(args, rank, world, local_rank):
         with open(tpath) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
 
+    # the other ceiling of this path: the FP64 pipe, measured on this device
+    import ctypes
+    from wobble_jax_b200 import _lib
+    tf = ctypes.c_double()
+    _lib.check(_lib.load().jb_double_peak(local_rank, ctypes.byref(tf)))
+    # FP64 instructions per pixel of the fused kernel (SASS of the shipped library, profiles/r2_sass_k_strip.txt):
+    # pixel code + its share of the transposed row sums
+    fp64_instr_px = 50.5 if info["fused_variant"] >= 128 else 68.0
+    px_per_s_kernel = args.epochs * args.pixels * args.chunks / (fused_batch_avg_ms * 1e-3)
+    fp64_info = {"peak_tflops_measured": tf.value,
+                 "peak_warp_instr_per_s": tf.value * 1e12 / 64.0,            # one DFMA warp instruction = 32 lanes x 2 flop
+                 "kernel_fp64_instr_per_pixel": fp64_instr_px,
+                 "kernel_fp64_pipe_frac": fp64_instr_px * px_per_s_kernel / 32.0 / (tf.value * 1e12 / 64.0),
+                 "note": "fraction of the measured FP64 issue rate the fused kernel's FP64 instructions take (any FP64 "
+                         "instruction holds the pipe like a DFMA); beside roofline.frac = the HBM side"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -445,6 +460,7 @@ def run_b200(args, rank, world, local_rank):
                      "single_chunk_launch": {"kernel_ms": fused_avg_ms,
                                              "achieved": info["algorithmic_bytes"] / (fused_avg_ms * 1e-3) / 1e9,
                                              "note": "same kernel launched for one chunk alone (a single partial wave of 148 SMs)"}},
+        "fp64": fp64_info,
         "plan": {k: info[k] for k in ("n_tasks", "rows_per_group", "tile_pixels", "device_bytes", "scratch_bytes", "n_fit")},
         "setup_s": setup_s,
         "loss_chunk0": losses[0],

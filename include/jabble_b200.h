@@ -286,6 +286,10 @@ int jb_group_eval_device_checked(jb_group *group, void *stream);
 int jb_group_info(const jb_group *group, int64_t *n_shared, int64_t *collective_bytes, int32_t *world);
 int64_t jb_group_launches(const jb_group *group);
 
+/* The device's measured FP64 FMA throughput (TFLOP/s: a register-resident DFMA kernel, best of 3):
+ * in float64 the fused kernels sit at the roofline ridge, so benchmarks quote the FP64 pipe next to HBM. */
+int jb_double_peak(int32_t device, double *tflops);
+
 /* The plan's own cudaStream_t (so that a caller can order its work, or time it with events). */
 int jb_plan_stream(jb_plan *plan, void **stream_out);
 

@@ -173,7 +173,7 @@ int main(int argc, char** argv) {
 
     auto run = [&]() {
         k_prepare_strip<2><<<off_prep[C], 128>>>(d_pp, d_off_p, C);
-        k_strip<2, 3, FL><<<off_strip[C], kStripWarps * 32, smem>>>(d_sp, d_off_s, C);
+        k_strip<2, 3, FL><<<off_strip[C], kStripWarps * 32, smem>>>(d_sp, d_off_s, C, K);
     };
     run();
     CK(cudaDeviceSynchronize());
@@ -225,7 +225,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < reps; ++i) {
         k_prepare_strip<2><<<off_prep[C], 128>>>(d_pp, d_off_p, C);
         CK(cudaEventRecord(e0));
-        k_strip<2, 3, FL><<<off_strip[C], kStripWarps * 32, smem>>>(d_sp, d_off_s, C);
+        k_strip<2, 3, FL><<<off_strip[C], kStripWarps * 32, smem>>>(d_sp, d_off_s, C, K);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("jb_group_eval_device_checked", C.c_int, [C.c_void_p, C.c_void_p]),
     ("jb_group_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("jb_group_launches", C.c_int64, [C.c_void_p]),
+    ("jb_double_peak", C.c_int, [C.c_int32, c_f64p]),
     ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("jb_plan_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_plan_profile_read", C.c_int, [C.c_void_p, c_f64p, c_i64p]),

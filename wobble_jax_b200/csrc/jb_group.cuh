@@ -269,3 +269,52 @@ int jb_group_info(const jb_group* g, int64_t* n_shared, int64_t* collective_byte
 int64_t jb_group_launches(const jb_group* g) { return g ? g->batch->launches : 0; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// The FP64 ceiling of the device, measured (in float64 this path sits at the
+// roofline ridge, so the HBM fraction is reported next to the FP64 pipe's).  Every thread runs 8
+// independent chains of dependent DFMAs; enough blocks to fill every SM several times over.
+namespace {
+__global__ void k_fp64_peak(double* out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (double)threadIdx.x * 1.0e-3 + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __fma_rn(v[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 12345.678) out[0] = s;        // never true: keeps the chains alive
+}
+}  // namespace
+
+extern "C" int jb_double_peak(int32_t device, double* tflops) {
+    if (!tflops) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    JB_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    JB_CUDA(cudaMalloc(&d, sizeof(double)));
+    const int blocks = prop.multiProcessorCount * 16, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    JB_CUDA(cudaEventCreate(&e0));
+    JB_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        JB_CUDA(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1.0e-9);
+        JB_CUDA(cudaEventRecord(e1));
+        JB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        JB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return JB_OK;
+}
+

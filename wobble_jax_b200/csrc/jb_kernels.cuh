@@ -1014,8 +1014,10 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
     for (int c = 0; c < a.n_comp + a.has_norm; ++c) {
         const bool is_norm = c == a.n_comp;
         const int M = is_norm ? a.n_norm_keys * a.norm_knots : a.comp[c].n_knots;
-        if (i < M) {
-            if (is_norm) {   // control point k of key: sum over the key's rows, in row order
+        const int Mp = (M + 31) & ~31;              // every segment is padded to whole warps
+        if (i < Mp) {
+            if (is_norm) {
+                if (i >= M) return;   // control point k of key: sum over the key's rows, in row order
                 const int key = (int)(i / a.norm_knots), k = (int)(i % a.norm_knots);
                 double s = 0.0;
                 for (int e = a.norm_rowptr[key]; e < a.norm_rowptr[key + 1]; ++e)
@@ -1027,16 +1029,30 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
             const int NT = a.n_tiles;
             const int* __restrict__ rng = a.tile_rng + 2 * c * NT;
             const double* __restrict__ tp = a.tilepart + (int64_t)c * NT * a.max_knots + i;
+            // the warp's 32 knots share the scan of the tiles: every lane tests one tile per round, the
+            // tiles whose range meets the warp's knots are then added in tile order (the segments of this
+            // kernel's index space are padded to 32, so a warp never straddles two of them)
+            const int lane = threadIdx.x & 31;
+            const int i0 = (int)i & ~31;
             double s = 0.0;
-            for (int t = 0; t < NT; ++t) {
-                const int2 r = *reinterpret_cast<const int2*>(rng + 2 * t);
-                if ((int)i >= r.x && (int)i < r.y) s += tp[(int64_t)t * a.max_knots];
+            for (int t0 = 0; t0 < NT; t0 += 32) {
+                int2 r = make_int2(0, 0);
+                if (t0 + lane < NT) r = *reinterpret_cast<const int2*>(rng + 2 * (t0 + lane));
+                unsigned m = __ballot_sync(0xffffffffu, r.y > r.x && r.x < i0 + 32 && r.y > i0);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int rx = __shfl_sync(0xffffffffu, r.x, b), ry = __shfl_sync(0xffffffffu, r.y, b);
+                    if ((int)i >= rx && (int)i < ry && i < M) s += tp[(int64_t)(t0 + b) * a.max_knots];
+                }
             }
+            if (i >= M) return;
             a.grad_all[a.ctrl_off[c] + i] = -a.coef * s;
             return;
         }
-        i -= M;
-        if (i < a.n_shift[c]) {
+        i -= Mp;
+        if (i < ((a.n_shift[c] + 31) & ~31)) {
+            if (i >= a.n_shift[c]) return;
             double gs = 0.0, fs = 0.0;
             const int qg = a.rq[c][0], qf = a.rq[c][2];
             for (int e = a.shift_rowptr[c][i]; e < a.shift_rowptr[c][i + 1]; ++e) {
@@ -1049,8 +1065,9 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
             if (!is_norm) a.fisher_all[a.shift_off[c] + i] = sc * sc * fs;
             return;
         }
-        i -= a.n_shift[c];
-        if (i < a.n_stretch[c]) {
+        i -= (a.n_shift[c] + 31) & ~31;
+        if (i < ((a.n_stretch[c] + 31) & ~31)) {
+            if (i >= a.n_stretch[c]) return;
             double gs = 0.0;
             const int qs = a.rq[c][1];
             for (int e = a.stretch_rowptr[c][i]; e < a.stretch_rowptr[c][i + 1]; ++e)
@@ -1058,7 +1075,7 @@ __global__ void k_reduce_stage2(const ReduceParams* __restrict__ arr, const int*
             a.grad_all[a.stretch_off[c] + i] = -a.coef * gs;
             return;
         }
-        i -= a.n_stretch[c];
+        i -= (a.n_stretch[c] + 31) & ~31;
     }
 }
 

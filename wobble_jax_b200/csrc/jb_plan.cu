@@ -240,6 +240,7 @@ int alloc_scratch(jb_plan* pl) {
 }
 
 constexpr int kStripWin = 64;      // doubles per published gradient window of a k_strip task (>= kStripWs + p_val + 1)
+constexpr int kStripRedThreads = 128;   // threads per block of k_reduce_stage1 for k_strip plans (a strip's windows span ~70 knots)
 
 // Does the model shape suit k_strip at all?
 bool strip_shape_ok(const jb_plan* pl) {
@@ -580,15 +581,17 @@ int refresh_pack(jb_plan* pl) {
     }
     rp.nq = NQ;
     rp.nb_ctrl = pl->n_glob * rp.n_tiles;
-    rp.nb_stage1_rows = (int)((pl->E * NQ + 255) / 256);
-    int64_t n2 = 0;
+    const int red_threads = strip ? kStripRedThreads : jb::kRedSlab;      // k_reduce_stage1's block: one thread per knot of a tile's window union
+    rp.nb_stage1_rows = (int)((pl->E * NQ + red_threads - 1) / red_threads);
+    int64_t n2 = 0;       // k_reduce_stage2: one thread per differentiated parameter, every segment padded to whole warps
+    auto pad32 = [](int64_t v) { return (v + 31) & ~(int64_t)31; };
     for (int c = 0; c < pl->n_comp; ++c)
-        n2 += (c < pl->n_glob ? pl->comp[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys) + rp.n_shift[c] + rp.n_stretch[c];
+        n2 += pad32(c < pl->n_glob ? pl->comp[c].n_knots : pl->desc[c].n_knots * pl->desc[c].n_ctrl_keys) + pad32(rp.n_shift[c]) + pad32(rp.n_stretch[c]);
     pl->nb[K_SCATTER] = (int)std::max<int64_t>(1, (pl->n_fit + 255) / 256);
     pl->nb[K_PREPARE] = strip ? (pl->s_nblocks + 3) / 4 : (int)((pl->E + 127) / 128);
     pl->nb[K_FUSED] = strip ? (int)((pl->s_ntasks + jb::kStripWarps - 1) / jb::kStripWarps)
                             : (int)((pl->n_tasks + jb::kWarpsPerBlock - 1) / jb::kWarpsPerBlock);
-    pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + 255) / 256) : 0);
+    pl->nb[K_STAGE1] = rp.nb_ctrl + rp.nb_stage1_rows + (pl->has_norm ? (int)((pl->E * pl->norm_stride + red_threads - 1) / red_threads) : 0);
     pl->nb[K_STAGE2] = (int)((n2 + 255) / 256);
     pl->nb[K_FINISH] = (int)(1 + (pl->n_fit + 1023) / 1024);
     int off[K_COUNT][2];
@@ -604,7 +607,7 @@ int refresh_pack(jb_plan* pl) {
 struct LaunchSet {
     const jb::ScatterParams* sc; const jb::PrepareParams* pr; const jb::FusedParams* fu; const jb::ReduceParams* re;
     const jb::StripParams* st; const jb::StripPrepParams* sp;
-    int strip_K;             // rows per block of the k_strip plans of the launch (its shared-memory layout)
+    int strip_K;             // longest block (rows) among the k_strip plans of the launch: its shared-memory layout
     const int* off[K_COUNT]; // n+1 block offsets per kernel
     int total[K_COUNT];
     int n;
@@ -695,7 +698,7 @@ int launch_strip_t(const LaunchSet& L, cudaStream_t st) {
     using Lay = jb::StripLay<NC, PV, FL>;
     const size_t smem = Lay::launch_bytes(L.strip_K);
     JB_CUDA(cudaFuncSetAttribute(jb::k_strip<NC, PV, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jb::k_strip<NC, PV, FL><<<(unsigned)L.total[K_FUSED], jb::kStripWarps * 32, smem, st>>>(L.st, L.off[K_FUSED], L.n);
+    jb::k_strip<NC, PV, FL><<<(unsigned)L.total[K_FUSED], jb::kStripWarps * 32, smem, st>>>(L.st, L.off[K_FUSED], L.n, L.strip_K);
     JB_CUDA(cudaGetLastError());
     return JB_OK;
 }
@@ -785,7 +788,7 @@ int launch_all(const LaunchSet& L, cudaStream_t st, const double* p_fit_override
         prof->prof_used++;
         prof->prof_stream = st;
     }
-    jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], jb::kRedSlab, 0, st>>>(L.re, L.off[K_STAGE1], L.n);
+    jb::k_reduce_stage1<<<(unsigned)L.total[K_STAGE1], strip ? kStripRedThreads : jb::kRedSlab, 0, st>>>(L.re, L.off[K_STAGE1], L.n);
     jb::k_reduce_stage2<<<(unsigned)L.total[K_STAGE2], 256, 0, st>>>(L.re, L.off[K_STAGE2], L.n);
     jb::k_finish<<<(unsigned)L.total[K_FINISH], 1024, 0, st>>>(L.re, L.off[K_FINISH], L.n, out_override);
     JB_CUDA(cudaGetLastError());
@@ -1750,33 +1753,18 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     bool regroup = b->dirty;
     for (jb_plan* pl : b->plans)
         if (pl->sort_dirty) { if ((rc = resort_rows(pl))) return rc; }
-    {   // one launch -> one kernel: plans that disagree on k_strip (its variant or its rows per block)
-        // all leave it; plans that then still disagree on the variant all take the general kernel
+    {   // one launch -> one kernel: plans that disagree on k_strip all leave it (their rows per block may
+        // differ: the launch sizes its shared memory for the longest); plans that then still disagree on the variant all take the general kernel
         auto all_same = [&]() {
             bool same = true;
             for (jb_plan* pl : b->plans) {
                 const int v = plan_variant(pl), v0 = plan_variant(b->plans[0]);
-                same = same && v == v0 && (!(v >= 0 && (v & 128)) || pl->sK == b->plans[0]->sK);
+                same = same && v == v0;
             }
             return same;
         };
         std::vector<std::pair<bool, bool>> old;
         for (jb_plan* pl : b->plans) { old.emplace_back(pl->force_nostrip, pl->force_v1); pl->force_nostrip = pl->force_v1 = false; }
-        {   // k_strip plans that differ only in their rows per block: all take the smallest
-            int kmin = INT_MAX, kmax = 0;
-            bool all_strip = true;
-            for (jb_plan* pl : b->plans) {
-                const int v = plan_variant(pl);
-                all_strip = all_strip && v >= 0 && (v & 128);
-                kmin = std::min(kmin, pl->sK); kmax = std::max(kmax, pl->sK);
-            }
-            if (all_strip && kmin != kmax)
-                for (jb_plan* pl : b->plans)
-                    if (pl->sK != kmin) {
-                        pl->sK_force = kmin;
-                        if ((rc = resort_rows(pl))) return rc;
-                    }
-        }
         bool want_nostrip = false, want_v1 = false;
         if (!all_same()) {
             want_nostrip = true;
@@ -1834,7 +1822,8 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     }
     LaunchSet L;
     L.sc = b->d_sc; L.pr = b->d_pr; L.fu = b->d_fu; L.re = b->d_re; L.st = b->d_st; L.sp = b->d_sp;
-    L.strip_K = b->plans[0]->sK;
+    L.strip_K = 0;
+    for (jb_plan* q : b->plans) L.strip_K = std::max(L.strip_K, q->sK);
     for (int q = 0; q < K_COUNT; ++q) { L.off[q] = b->d_off + (size_t)q * (n + 1); L.total[q] = b->total[q]; }
     L.n = n; L.n_comp = b->plans[0]->n_glob; L.p_val = b->plans[0]->desc[0].p_val; L.wincap = b->plans[0]->wincap;
     L.pvn = b->plans[0]->has_norm ? b->plans[0]->desc[b->plans[0]->n_glob].p_val : 0;

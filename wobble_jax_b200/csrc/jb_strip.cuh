@@ -346,7 +346,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr int kStripIlp = JB_STRIP_ILP;       // rows of a stage computed as independent streams (divides kStageRows)
 
 template <int NC, int PV, int FL>
-__global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const StripParams* __restrict__ arr, const int* __restrict__ off, int n) {
+__global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const StripParams* __restrict__ arr, const int* __restrict__ off, int n, int kmax) {
     // No static shared memory in this kernel: the dynamic block then starts at a 1 KB boundary, which
     // the XOR-addressed row-term tile relies on (256 bytes; checked below).  The plan's parameters
     // are read from global memory (constant for the launch, L1-resident).
@@ -369,12 +369,13 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     const int nrow = (int)min((int64_t)nblk * K, a.n_rows - row0);
     const int nstage = (nrow + kStageRows - 1) / kStageRows;
 
-    unsigned char* wb = strip_smem + (size_t)warp * Lay::total(K);
+    // (kmax: the longest block among the plans of the launch -- they share one shared-memory layout)
+    unsigned char* wb = strip_smem + (size_t)warp * Lay::total(kmax);
     const uint32_t wb32 = smem_u32(wb);
     if ((wb32 & 255u) != 0) { if (lane == 0) atomicOr(a.status, kStatBounds); return; }     // never: see above
-    const uint32_t bar0 = wb32 + Lay::bars(K);                  // stage barriers, then the two header barriers
+    const uint32_t bar0 = wb32 + Lay::bars(kmax);               // stage barriers, then the two header barriers
     const uint32_t hbar0 = bar0 + 8 * kStripStages;
-    const uint32_t hslot = Lay::hdr_slot(K);
+    const uint32_t hslot = Lay::hdr_slot(kmax);
     double* cwin = reinterpret_cast<double*>(wb + Lay::cwin);
     double* mtab = reinterpret_cast<double*>(wb + Lay::mtab);
 
