@@ -59,7 +59,7 @@ __global__ void k_fold(FoldP a) {
         const int b = a.base[c * a.n_tasks + t];
         if (b != INT_MAX && a.part[i] != 0.0) atomicAdd(a.g[c] + b + k, a.part[i]);
     }
-    if (i < a.E * a.n_strips * 4) { const int64_t r = i / (a.n_strips * 4); const int q = i % 4; atomicAdd(a.rows + r * 4 + q, a.rowpart[i]); }
+    if (i < a.E * a.n_strips * 3) { const int64_t r = i / (a.n_strips * 3); const int q = i % 3; atomicAdd(a.rows + r * 4 + q, a.rowpart[i]); }
     if (i < a.n_tasks) atomicAdd(a.loss, a.losspart[i]);
 }
 
@@ -147,7 +147,7 @@ int main(int argc, char** argv) {
         s.comp[0].shift = d_params + 2 * M; s.comp[0].shift_key = d_key;
         s.comp[1].stretch = d_params + 2 * M + E; s.comp[1].stretch_key = d_key;
         CK(cudaMalloc(&s.part, 2 * n_tasks * W * 8)); CK(cudaMalloc(&s.part_base, 2 * n_tasks * 4));
-        CK(cudaMalloc(&s.rowpart, E * n_strips * 4 * 8)); CK(cudaMalloc(&s.losspart, n_tasks * 8));
+        CK(cudaMalloc(&s.rowpart, E * n_strips * 3 * 8)); CK(cudaMalloc(&s.losspart, n_tasks * 8));
         s.status = d_status;
         StripPrepParams& q = pp[i]; memset(&q, 0, sizeof q);
         q.rowid = d_rowid; q.xref = d_xref; q.rowc = rowc; q.blk = blk; q.n_rows = E; q.K = K; q.n_blocks = n_blocks; q.n_comp = 2;

@@ -982,14 +982,20 @@ __global__ void k_reduce_stage1(const ReduceParams* __restrict__ arr, const int*
             if (k < k_hi) dst[k] = s;
         }
     } else if (blk < nb_ctrl + a.nb_stage1_rows) {
-        const int64_t i = (int64_t)(blk - nb_ctrl) * blockDim.x + threadIdx.x;
-        if (i >= a.n_rows * NQ) return;
-        const int64_t r = i / NQ;
-        const int q = (int)(i - r * NQ);
-        double s = 0.0;
-#pragma unroll 8
-        for (int t = 0; t < a.n_tiles; ++t) s += a.rowpart[(r * a.n_tiles + t) * NQ + q];
-        a.rowsum[(a.row_of_pos ? (int64_t)a.row_of_pos[r] : r) * NQ + q] = s;       // k_strip numbers the rows in sorted order
+        // per-row sums over the tiles: one WARP per row, lane l adds the tiles l, l + 32, .. in tile order,
+        // then the lanes are added in a fixed butterfly (the same tree for every row and every run)
+        const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+        const int64_t r = (int64_t)(blk - nb_ctrl) * warps_per_block + (threadIdx.x >> 5);
+        if (r >= a.n_rows) return;
+        const int64_t rr = a.row_of_pos ? (int64_t)a.row_of_pos[r] : r;       // k_strip numbers the rows in sorted order
+        const double* __restrict__ src = a.rowpart + r * a.n_tiles * NQ;
+        for (int q = 0; q < NQ; ++q) {
+            double s = 0.0;
+            for (int t = lane; t < a.n_tiles; t += 32) s += src[(int64_t)t * NQ + q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) a.rowsum[rr * NQ + q] = s;
+        }
     } else {   // normalisation control points: per row, sum of the tile partials
         const int64_t i = (int64_t)(blk - nb_ctrl - a.nb_stage1_rows) * blockDim.x + threadIdx.x;
         if (i >= a.n_rows * a.norm_stride) return;

@@ -575,14 +575,14 @@ int refresh_pack(jb_plan* pl) {
         if (pl->has_norm) { rp.rq[pl->n_glob][0] = pl->n_glob * jb::kRowQ; rp.rq[pl->n_glob][1] = pl->n_glob * jb::kRowQ + 1; }
     } else {
         const int fl = pl->variant & 15;       // bit 6 marks the float32 tier, bit 7 k_strip
-        NQ = jb::f2_pad(jb::f2_nsums(pl->n_glob, fl));
+        NQ = strip ? std::max(1, jb::f2_nsums(pl->n_glob, fl)) : jb::f2_pad(jb::f2_nsums(pl->n_glob, fl));     // k_strip does not pad its records
         for (int c = 0; c < pl->n_glob; ++c)
             for (int q = 0; q < 3; ++q) rp.rq[c][q] = jb::f2_slot(pl->n_glob, fl, c, q);
     }
     rp.nq = NQ;
     rp.nb_ctrl = pl->n_glob * rp.n_tiles;
     const int red_threads = strip ? kStripRedThreads : jb::kRedSlab;      // k_reduce_stage1's block: one thread per knot of a tile's window union
-    rp.nb_stage1_rows = (int)((pl->E * NQ + red_threads - 1) / red_threads);
+    rp.nb_stage1_rows = (int)((pl->E + red_threads / 32 - 1) / (red_threads / 32));     // a warp per row
     int64_t n2 = 0;       // k_reduce_stage2: one thread per differentiated parameter, every segment padded to whole warps
     auto pad32 = [](int64_t v) { return (v + 31) & ~(int64_t)31; };
     for (int c = 0; c < pl->n_comp; ++c)

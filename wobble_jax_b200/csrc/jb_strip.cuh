@@ -88,7 +88,7 @@ struct StripParams {
     CompDev comp[kMaxComp];
     double* part;            // [n_comp][n_tasks][wincap]
     int* part_base;          // [n_comp][n_tasks]
-    double* rowpart;         // [E][n_strips][NSP], rows in SORTED order (k_reduce_stage1 maps them back through rowid)
+    double* rowpart;         // [E][n_strips][NS] (NS = f2_nsums, not padded), rows in SORTED order (k_reduce_stage1 maps them back through rowid)
     double* losspart;        // [n_tasks]
     int* status;
 };
@@ -468,8 +468,8 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     if (empty || err_window) {
         // nothing weighted (or an error): the row sums of this strip are zero
         if (NS > 0)
-            for (int i = lane; i < nrow * NSP; i += 32)
-                a.rowpart[((row0 + i / NSP) * a.n_strips + strip) * NSP + i % NSP] = 0.0;
+            for (int i = lane; i < nrow * NS; i += 32)
+                a.rowpart[((row0 + i / (NS > 0 ? NS : 1)) * a.n_strips + strip) * NS + i % (NS > 0 ? NS : 1)] = 0.0;
         // copies are in flight into this warp's shared memory: let them land before leaving
         mbar_wait(hbar0, 0);
         if (nblk > 1) mbar_wait(hbar0 + 8, 0);
@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(kStripWarps * 32, JB_STRIP_MINB) k_strip(const
     const uint32_t rd_addr = tile32 + (uint32_t)(vsel * 256 + (lane & 1) * 16 + rsel * 32);
     const uint32_t park_addr = tile32 + (uint32_t)(lane * 8);
     // where this lane stores the sum it adds up (v0 = 0 round; later rounds 16 / kStageRows sums further), per stage
-    double* rowpart_p = a.rowpart + ((row0 + rsel) * a.n_strips + strip) * NSP + vsel / kStageRows;
-    const int64_t rowpart_step = (int64_t)kStageRows * a.n_strips * NSP;
+    double* rowpart_p = a.rowpart + ((row0 + rsel) * a.n_strips + strip) * NS + vsel / kStageRows;
+    const int64_t rowpart_step = (int64_t)kStageRows * a.n_strips * NS;
     // scale of that sum: the reducers expect S' / PV (jb_fused2.cuh); a stretched component's derivative
     // sums carry the row's stretch (only then does the scale depend on the row)
     constexpr bool kRowScale = (f2_der(FL, 0) && f2_str(FL, 0)) || (NC > 1 && f2_der(FL, 1) && f2_str(FL, 1));
