@@ -501,6 +501,9 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         out["epoch_sharded"] = epoch_sharded_leg(args, rank, world, local_rank, dist, args.es_epochs, args.es_pixels,
                                                  args.steps, args.warmup)
+    out["api"] = None
+    if rank == 0 and world == 1 and not args.no_extra_legs and not args.float32:
+        out["api"] = api_leg(args, local_rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
         ch, model, p, rows, cores = cpu_baseline(args, args.cpu_seconds)
@@ -520,6 +523,61 @@ def run_b200(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def api_leg(args, local_rank):
+    """The reference-facing Python API, timed: Model.optimize on one chunk (what a notebook calls per
+    order, jabble/model.py:195-238) and model.optimize_many on several (the Pool over orders,
+    notebooks/02-51peg.py:66-78), templates in fit mode, a fixed number of L-BFGS-B iterations.  Everything
+    the call does is inside the clock: blockify, the upload into a plan (first call only: the second call
+    finds the resident block, engine.get_plan), scipy, every evaluation's H2D / D2H copies."""
+    import copy
+    import wobble_jax_b200 as jabble
+    from wobble_jax_b200 import engine, synth
+    from wobble_jax_b200.dataset import Data
+
+    def chunk(c):
+        ch = synth.make_chunk(c, n_epochs=args.epochs, n_pix=args.pixels, p_val=args.p_val, as_block=True)
+        db = ch.datablock
+        data = Data.from_lists(list(db["xs"]), list(db["ys"]), list(db["yivar"]), list(db["mask"]))
+        m = ch.model
+        m.fix(); m.fit(0, 1); m.fit(1, 1)
+        return data, m
+
+    loss = jabble.loss.ChiSquare()
+    px = args.epochs * args.pixels
+    out = {}
+    engine.clear_plan_cache()
+    data, model = chunk(0)
+    res = []
+    for it in range(2):           # first call uploads the block, the second finds it resident
+        m = copy.deepcopy(model)
+        t0 = time.perf_counter()
+        x, f, d = m.optimize(loss, data, options={"maxiter": 20})
+        dt = time.perf_counter() - t0
+        res.append({"wall_s": dt, "funcalls": int(d["funcalls"]), "nit": int(d["nit"]),
+                    "ms_per_eval": dt * 1e3 / d["funcalls"], "ms_per_iteration": dt * 1e3 / max(d["nit"], 1),
+                    "value": px * d["funcalls"] / dt / 1e9})
+    out["optimize"] = {"workload": f"1 chunk of {args.epochs} x {args.pixels}, templates in fit mode ({len(x)} parameters), maxiter 20",
+                       "unit": UNIT + " of evaluations performed", "first_call": res[0], "second_call_block_resident": res[1]}
+    engine.clear_plan_cache()
+    n = 8
+    pairs = [chunk(c) for c in range(n)]
+    engine.PLAN_CACHE_SIZE = max(engine.PLAN_CACHE_SIZE, n)
+    many = []
+    for it in range(2):           # first call uploads the blocks, the second finds them resident
+        models = [copy.deepcopy(m) for _, m in pairs]
+        t0 = time.perf_counter()
+        outs = jabble.model.optimize_many(models, loss, [dt_ for dt_, _ in pairs], options={"maxiter": 10})
+        dt = time.perf_counter() - t0
+        calls = sum(int(o[2]["funcalls"]) for o in outs)
+        rounds = max(int(o[2]["funcalls"]) for o in outs)
+        many.append({"wall_s": dt, "funcalls_total": calls, "lockstep_rounds": rounds, "ms_per_round": dt * 1e3 / rounds,
+                     "value": px * calls / dt / 1e9})
+    out["optimize_many"] = {"workload": f"{n} chunks of {args.epochs} x {args.pixels} at once, templates in fit mode, maxiter 10",
+                            "unit": UNIT + " of evaluations performed", "first_call": many[0], "second_call_blocks_resident": many[1]}
+    engine.clear_plan_cache()
+    return out
 
 
 def epoch_sharded_leg(args, rank, world, local_rank, dist, epochs, pixels, steps, warmup):

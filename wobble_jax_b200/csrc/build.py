@@ -18,7 +18,7 @@ SOURCES = ["jb_plan.cu"]
 DEPS = ["jb_plan.cu", "jb_kernels.cuh", "jb_fused2.cuh", "jb_fused32.cuh", "jb_strip.cuh", "jb_group.cuh", "jb_device.cuh", os.path.join(ROOT, "include", "jabble_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--shared", "-cudart", "shared", "-ldl"]
+         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "--shared", "-cudart", "shared", "-ldl", "-lgomp"]
 
 
 def source_hash():

@@ -90,6 +90,7 @@ struct jb_plan {
     std::vector<int64_t> h_fit_map;   // host copy of the fit map (jb_group: which outputs are sums over all rows)
     double *d_params = nullptr, *d_grad_all = nullptr, *d_fisher_all = nullptr;
     std::vector<double> h_params;
+    std::vector<double> sorted_params;   // the parameters the rows were last sorted for
     bool params_set = false, sort_dirty = true;
     bool fit_shift[jb::kMaxComp] = {false, false, false};   // some shift of the component is in fit mode
     bool force_der = false;    // jb_plan_fisher: derivative sums whatever the fit flags say
@@ -450,6 +451,7 @@ int resort_rows(jb_plan* pl) {
     JB_CUDA(cudaMemcpyAsync(pl->d_tinfo, tinfo.data(), tinfo.size() * sizeof(jb::TileInfo), cudaMemcpyHostToDevice, pl->stream));
     JB_CUDA(cudaStreamSynchronize(pl->stream));
     pl->sort_dirty = false;
+    pl->sorted_params = pl->h_params;
     if (pl->params_set) {
         int rc = strip_build(pl, perm);
         if (rc) return rc;
@@ -990,6 +992,10 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     double any_x = 0.0;
     for (int64_t i = 0; i < E * P && any_x == 0.0; ++i)
         if ((!d->mask || !d->mask[i]) && std::isfinite(d->xs[i])) any_x = d->xs[i];
+    // (rows are independent: the loop runs on all host cores)
+    bool norm_smooth_all = true, f2_ok_all = true;
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, bad_row = -1, bad_pix = -1;
+#pragma omp parallel for schedule(dynamic, 8) reduction(&& : norm_smooth_all, f2_ok_all) reduction(+ : tk0, tk1, tk2, tk3)
     for (int64_t r = 0; r < E; ++r) {
         const double* xr = d->xs + r * P;
         const uint8_t* mr = d->mask ? d->mask + r * P : nullptr;
@@ -1018,7 +1024,10 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             const bool w = p < P && weighted(src);
             if (p < P) hx[(size_t)r * ppad + p] = std::isfinite(xr[src]) ? xr[src] : 0.0;
             if (w) {
-                if (!std::isfinite(xr[src])) return fail(JB_ERR_BAD_ARG, "row %lld pixel %lld: unmasked x is not finite", (long long)r, (long long)src);
+                if (!std::isfinite(xr[src])) {
+#pragma omp critical
+                    if (bad_row < 0) { bad_row = r; bad_pix = src; }
+                }
                 fill = xr[src];
                 if (pl->has_data) { rec[jb::kTile] = d->ys[r * P + src]; rec[2 * jb::kTile] = d->yivar[r * P + src]; }
                 pl->h_xfirst[r] = std::min(pl->h_xfirst[r], fill);
@@ -1055,7 +1064,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                     if (j > 0 && !(hxf[i] >= hxf[i - 1] && hxf[i] - hxf[i - 1] < smooth)) lane_jumpy = true;
                 }
                 jumpy |= lane_jumpy;
-                if (any_w && !(lmax - lmin < norm_dx)) pl->norm_smooth = false;
+                if (any_w && !(lmax - lmin < norm_dx)) norm_smooth_all = false;
                 double& cm = cmax[l % jb::kClasses];
                 if (!(lmin - cm >= need)) bad = true;   // also catches non-monotone rows
                 cm = std::max(cm, lmax);
@@ -1070,14 +1079,19 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                 txmax[ti] = std::max(txmax[ti], lmax);
             }
             live[ti] = lv;
-            if (lv && (bad2 || jumpy2)) pl->f2_ok = false;
+            if (lv && (bad2 || jumpy2)) f2_ok_all = false;
             // flags: 1 = lanes of a class may collide (walk lane by lane), 2 = nothing weighted (skip),
             //        4 = consecutive pixels a knot or more apart somewhere (general per-pixel path)
             dense[ti] = !any_w ? 2 : ((bad ? 1 : 0) | (jumpy ? 4 : 0));
             if (!any_w) { txmin[ti] = INFINITY; txmax[ti] = -INFINITY; }
-            pl->tiles_kind[!any_w ? 3 : bad ? 2 : jumpy ? 1 : 0]++;
+            const int kind = !any_w ? 3 : bad ? 2 : jumpy ? 1 : 0;
+            tk0 += kind == 0; tk1 += kind == 1; tk2 += kind == 2; tk3 += kind == 3;
         }
     }
+    if (bad_row >= 0) return fail(JB_ERR_BAD_ARG, "row %lld pixel %lld: unmasked x is not finite", bad_row, bad_pix);
+    pl->norm_smooth = pl->norm_smooth && norm_smooth_all;
+    pl->f2_ok = pl->f2_ok && f2_ok_all;
+    pl->tiles_kind[0] += tk0; pl->tiles_kind[1] += tk1; pl->tiles_kind[2] += tk2; pl->tiles_kind[3] += tk3;
     // Position of every row relative to one reference row (k_strip, jb_strip.cuh): x[r][p] - x[ref][p]
     // at the row's first weighted pixel whose reference pixel carries an x of its own.  Unlike the
     // first weighted x this does not jump by a pixel when a row's first pixel is masked.
@@ -1264,8 +1278,21 @@ int jb_plan_set_params(jb_plan* pl, const double* params_all, int64_t n) {
     pl->h_params.assign(params_all, params_all + n);
     JB_CUDA(cudaMemcpyAsync(pl->d_params, pl->h_params.data(), n * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
     JB_CUDA(cudaStreamSynchronize(pl->stream));
+    // The rows stay in the order (and the strip layout) they were sorted into: that order only has to keep
+    // the rows of a group near one another, and an evaluation says so when it no longer does (the knot
+    // window overflows: eval_sync / batch_settle re-sort with the parameters of the moment).  The first
+    // upload, and one that moves a shift by more than half a knot, sort right away.
+    bool moved = !pl->params_set;
+    if (!moved)
+        for (int c = 0; c < pl->n_comp && !moved; ++c) {
+            const jb_component_desc& cd = pl->desc[c];
+            if (cd.shift_offset < 0) continue;
+            for (int64_t i = 0; i < cd.n_shift && !moved; ++i)
+                if ((int64_t)pl->sorted_params.size() != n ||
+                    std::fabs(params_all[cd.shift_offset + i] - pl->sorted_params[cd.shift_offset + i]) > 0.5 * cd.dx) moved = true;
+        }
     pl->params_set = true;
-    pl->sort_dirty = true;
+    if (moved) pl->sort_dirty = true;
     return JB_OK;
 }
 

@@ -112,7 +112,8 @@ class TreeSpec:
         for comp in self.components:
             sp = comp["spline"]
             inner = sp.model if isinstance(sp, M.NormalizationModel) else sp
-            sig.append((type(sp).__name__, inner.p_val, id(inner.xs), inner.xs.shape,
+            grid = np.asarray(inner.xs, dtype=np.float64).reshape(-1)
+            sig.append((type(sp).__name__, inner.p_val, float(grid[0]), float(grid[1] - grid[0]) if grid.size > 1 else 0.0, grid.size,
                         None if comp["shift"] is None else (comp["shift"].which_key, comp["shift"].p.size),
                         None if comp["stretch"] is None else (comp["stretch"].which_key, comp["stretch"].p.size),
                         getattr(sp, "which_key", None), getattr(sp, "size", None)))
