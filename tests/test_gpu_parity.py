@@ -744,3 +744,122 @@ def test_reducer_with_windows_wider_than_a_block():
         assert abs(val - oval) <= TOL * abs(oval)
         _check_grad(model, grad, ograd)
         plan.close()
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY.md section 8d "small parity configs", as named there (not look-alikes), against the C oracle.
+
+def _c_oracle():
+    import os, subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")])
+    from oracle import c_oracle
+    return c_oracle
+
+
+@pytest.mark.parametrize("p_val", [1, 2, 3])
+def test_survey_config1_30_epochs_8192_px_on_the_R20000_grid(p_val):
+    """configs[0] analogue: E = 30, P = 8192, knot grid of R = 20,000 (dx = 2.5e-5: nine HARPS pixels per
+    knot -- where the lanes of a class share knots and the plan has to walk tiles lane by lane)."""
+    co = _c_oracle()
+    ch = synth.make_chunk(chunk=1, n_epochs=30, n_pix=8192, p_val=p_val, n_lines=40, resolution=20000.0)
+    assert abs((ch.grid[1] - ch.grid[0]) / np.log(1 + 1 / 40000.0) - 1) < 1e-3          # dx = 2.5e-5
+    model = synth.fit_all(ch.model)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, ofisher, _ = co.evaluate(p, dbd, mbd, model)
+    plan = engine.build_plan(model, db, mb)
+    val, grad = plan.eval(p)
+    info = plan.info()
+    assert info["tiles_serial"] + info["tiles_general"] + info["tiles_smooth"] > 0
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    assert rel_err(plan.fisher(0), ofisher[:30]) < TOL
+    plan.close()
+
+
+def test_survey_config2_60_epochs_three_descending_chips_of_2048_px():
+    """configs[1] analogue (hat-p-20: 60 rows x 6144 px, H band, stored red to blue): three independent
+    2048-pixel chunks with descending x."""
+    co = _c_oracle()
+    for chip in range(3):
+        ch = synth.make_chunk(chunk=10 + chip, n_epochs=60, n_pix=2048, p_val=3, n_lines=30, descending=True)
+        model = synth.fit_all(ch.model)
+        db, mb, dbd, mbd = _blocks(ch.data)
+        assert db["xs"][0, 0] > db["xs"][0, -1]
+        p = np.asarray(model.get_parameters())
+        oval, ograd, ofisher, _ = co.evaluate(p, dbd, mbd, model)
+        plan = engine.build_plan(model, db, mb)
+        val, grad = plan.eval(p)
+        assert abs(val - oval) <= TOL * abs(oval)
+        _check_grad(model, grad, ograd)
+        assert rel_err(plan.fisher(0), ofisher[:60]) < TOL
+        fwd = plan.forward(p)
+        keep = ~db["mask"]
+        assert np.all(np.isfinite(fwd[keep]))
+        plan.close()
+
+
+def test_survey_config3_apogee_like_rows_with_normalisation():
+    """configs[2] analogue (APOGEE cframes, 07-apogee-cframes.ipynb cell 14): rows = frames x 3 chips of
+    2048 px, p_val = 3, R = 30,000, 60 km/s padding, plus a NormalizationModel (norm_p_val = 2,
+    norm_pts = 4 -> 7 control points per row)."""
+    co = _c_oracle()
+    import wobble_jax_b200.synth as S
+    frames, chips, P = 12, 3, 2048
+    old_pad = S.VEL_PADDING
+    S.VEL_PADDING = 60e3
+    try:
+        parts = [synth.make_chunk(chunk=20 + c, n_epochs=frames, n_pix=P, p_val=3, n_lines=25, resolution=30000.0,
+                                  pixel_step=np.log(1 + 1 / 90000.0)) for c in range(1)]
+    finally:
+        S.VEL_PADDING = old_pad
+    ch = parts[0]
+    # three "chips" per frame = three rows per epoch key
+    xs, ys, ivs, ms, times = [], [], [], [], []
+    for e in range(frames):
+        fr = ch.data[e]
+        for c in range(chips):
+            sl = slice(c * (P // chips), (c + 1) * (P // chips))
+            xs.append(fr.xs[sl]); ys.append(fr.ys[sl]); ivs.append(fr.yivar[sl]); ms.append(fr.mask[sl]); times.append(e)
+    data = jabble.dataset.Data.from_lists(xs, ys, ivs, ms)
+    data.metadata["times"] = np.asarray(times, dtype=float)
+    airmass = np.asarray(ch.model[1][2].p)
+    model = jabble.quickplay.get_wobble_model(np.zeros(frames), airmass, ch.grid, 3, which_key="times") + \
+        jabble.quickplay.get_normalization_model(data, 2, 4)
+    model[0][0].p = np.asarray(ch.model[0][0].p).copy()
+    model[0][1].p = np.asarray(ch.model[0][1].p).copy()
+    model[1][1].p = np.asarray(ch.model[1][1].p).copy()
+    rng = np.random.default_rng(3)
+    model[2][1].p = rng.normal(0, 0.01, np.asarray(model[2][1].p).shape)
+    assert np.asarray(model[2][1].p).size == frames * chips * 7
+    model.fix(); model.fit(0, 0); model.fit(0, 1); model.fit(1, 1); model.fit(1, 2); model.fit(2, 1)
+    db, mb, dbd, mbd = _blocks(data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, ofisher, _ = co.evaluate(p, dbd, mbd, model)
+    plan = engine.build_plan(model, db, mb)
+    val, grad = plan.eval(p)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    assert rel_err(plan.fisher(0), ofisher[:frames]) < TOL
+    plan.close()
+
+
+def test_full_size_fisher_of_both_components():
+    """The RV Fisher information of the stellar AND the telluric shift on a whole chunk of configs[3]."""
+    co = _c_oracle()
+    E = 2000
+    ch = synth.make_chunk(chunk=5, n_epochs=E, n_pix=4096, p_val=3)
+    model = ch.model
+    model.fix(); model.fit(0, 0); model.fit(1, 0)
+    db, mb, dbd, mbd = _blocks(ch.data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, ofisher, _ = co.evaluate(p, dbd, mbd, model)
+    plan = engine.build_plan(model, db, mb)
+    val, grad = plan.eval(p)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    spec = engine.TreeSpec(model)
+    off = {id(lf.node): lf.offset for lf in spec.leaves}
+    for comp, node in ((0, model[0][0]), (1, model[1][0])):
+        assert rel_err(plan.fisher(comp), ofisher[off[id(node)]:off[id(node)] + E]) < TOL
+    plan.close()

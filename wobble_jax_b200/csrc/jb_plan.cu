@@ -386,9 +386,11 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     int bpt;
     if (pl->s_hint > 0) bpt = 12;       // a batch keeps every warp slot busy anyway: long tasks (their set-up is ~15 % of a 120-row task)
     else {
-        const int64_t groups_wanted = (148LL * 16 + n_strips - 1) / n_strips;
-        bpt = (int)std::max<int64_t>(1, n_blocks / std::max<int64_t>(groups_wanted, 1));
-        bpt = std::min(bpt, std::max(1, 128 / K));
+        // as many row groups as fill the warp slots ONCE: a lone plan is one wave of equal tasks, and a few
+        // tasks spilling into a second wave would double its time
+        const int64_t slots = 148LL * 16;
+        const int64_t groups_fit = std::max<int64_t>(1, slots / n_strips);
+        bpt = (int)std::max<int64_t>(1, (n_blocks + groups_fit - 1) / groups_fit);
     }
     bpt = std::min(bpt, bpt_fit);
     pl->sK = K; pl->sBPT = bpt; pl->s_nblocks = n_blocks; pl->s_nstrips = n_strips; pl->s_ncls = ncls;

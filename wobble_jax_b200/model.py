@@ -60,8 +60,11 @@ def cardinal_vmap_model(x, xp, ap, basis, a=None):
     """model.py:951-989 -- ``y(x) = sum_k ap[idx - k] * basis(frac + k)`` on the evenly spaced knots
     ``xp``: the CUDA forward kernel on a one-row plan (``jb_plan_forward``).  ``basis`` is a
     ``CardinalSplineKernel`` (or its degree); ``a`` (half the support) follows from the degree and
-    is accepted for the reference's signature.  An ``x`` whose taps leave the knot grid raises
-    ``ValueError`` where the reference clamps the gather (model.py:985)."""
+    is accepted for the reference's signature.  An ``x`` whose non-zero taps leave the knot grid comes
+    back NaN (the forward kernel marks the pixel; the fused loss / gradient evaluation raises
+    ``ValueError`` for it, JB_ERR_OUT_OF_RANGE) where the reference clamps the gather silently
+    (model.py:985).  The usable range ends (p_val + 1) / 2 knots inside the last knot: the test is on
+    the knots of the pixel's whole support, zero-weight taps included."""
     p_val = int(getattr(basis, "n", basis))
     x = np.asarray(x, dtype=np.float64)
     flat = x.reshape(-1)
