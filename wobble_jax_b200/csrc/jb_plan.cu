@@ -936,6 +936,15 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     if (ndev <= 0) return fail(JB_ERR_CUDA, "no CUDA device: this library has no CPU path");
     if (d->device < 0 || d->device >= ndev) return fail(JB_ERR_BAD_ARG, "device %d of %d", d->device, ndev);
     JB_CUDA(cudaSetDevice(d->device));
+    {   // the stream-ordered allocations of forward / grid search / curvature keep their memory between
+        // calls (the default pool hands it back to the driver at every synchronisation: milliseconds per call)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
 
     jb_plan* pl = new jb_plan;
     struct Guard { jb_plan* p; ~Guard() { if (p) jb_plan_destroy(p); } } guard{pl};
