@@ -171,3 +171,58 @@ def test_strip_plans_in_one_batched_launch():
     batch.close()
     for plan in plans:
         plan.close()
+
+
+def test_strip_kernel_with_several_rows_per_epoch_key_and_a_narrow_block(c_oracle):
+    """Rows = frames x 2 chips sharing one epoch key (which_key = 'times': shift, airmass and Fisher sums
+    are per key, summed over the key's rows in row order), on a block only 40 pixels wide per row (most of
+    its second strip is padding) and with a row count that is not a multiple of the 4-row stages."""
+    frames, chips, width = 1601, 2, 40
+    ch = synth.make_chunk(chunk=4, n_epochs=frames, n_pix=chips * width, p_val=3, n_lines=6)
+    xs, ys, ivs, ms, times = [], [], [], [], []
+    for e in range(frames):
+        fr = ch.data[e]
+        for c in range(chips):
+            sl = slice(c * width, (c + 1) * width)
+            xs.append(fr.xs[sl]); ys.append(fr.ys[sl]); ivs.append(fr.yivar[sl]); ms.append(fr.mask[sl]); times.append(float(e))
+    data = jabble.dataset.Data.from_lists(xs, ys, ivs, ms)
+    data.metadata["times"] = np.asarray(times)
+    model = jabble.quickplay.get_wobble_model(np.zeros(frames), np.asarray(ch.model[1][2].p), ch.grid, 3, which_key="times")
+    model[0][0].p = np.asarray(ch.model[0][0].p).copy()
+    model[0][1].p = np.asarray(ch.model[0][1].p).copy()
+    model[1][1].p = np.asarray(ch.model[1][1].p).copy()
+    synth.fit_all(model)
+    db, mb, dbd, mbd = _blocks(data)
+    p = np.asarray(model.get_parameters())
+    oval, ograd, ofisher, _ = c_oracle.evaluate(p, dbd, mbd, model)
+    # the two chips of a frame sit 40 pixels (25 knots) apart: sorted by position they form two families,
+    # each with its own column offsets -- blocks that mix them are not separable, and the plan says so
+    plan = engine.build_plan(model, db, mb)
+    val, grad = plan.eval(p)
+    info = plan.info()
+    assert (info["fused_variant"] & STRIP) or info["strip_reason"] in (2, 3)
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model, grad, ograd)
+    assert rel_err(plan.fisher(0), ofisher[:frames]) < TOL
+    plan.close()
+    # one chip per row but keyed epochs (two exposures per night share a key): k_strip serves it
+    ch2 = _chunk(3, n_epochs=1601, n_pix=70)
+    nights = np.arange(1601) // 2
+    data2 = ch2.data
+    data2.metadata["times"] = nights.astype(float)
+    nk = nights.max() + 1
+    model2 = jabble.quickplay.get_wobble_model(np.zeros(nk), np.asarray(ch2.model[1][2].p)[::2][:nk], ch2.grid, 3, which_key="times")
+    model2[0][0].p = np.asarray(ch2.model[0][0].p)[::2][:nk].copy()
+    model2[0][1].p = np.asarray(ch2.model[0][1].p).copy()
+    model2[1][1].p = np.asarray(ch2.model[1][1].p).copy()
+    synth.fit_all(model2)
+    db, mb, dbd, mbd = _blocks(data2)
+    p = np.asarray(model2.get_parameters())
+    oval, ograd, ofisher, _ = c_oracle.evaluate(p, dbd, mbd, model2)
+    plan = engine.build_plan(model2, db, mb)
+    val, grad = plan.eval(p)
+    assert plan.info()["fused_variant"] & STRIP
+    assert abs(val - oval) <= TOL * abs(oval)
+    _check_grad(model2, grad, ograd)
+    assert rel_err(plan.fisher(0), ofisher[:nk]) < TOL
+    plan.close()
