@@ -286,6 +286,51 @@ int jb_group_eval_device_checked(jb_group *group, void *stream);
 int jb_group_info(const jb_group *group, int64_t *n_shared, int64_t *collective_bytes, int32_t *world);
 int64_t jb_group_launches(const jb_group *group);
 
+/*
+ * L-BFGS-B for many independent chunks at once, every vector on the device: the optimiser of
+ * Model.optimize (jabble/model.py:226-232: scipy.optimize.fmin_l_bfgs_b(func, x0, fprime, **options),
+ * no bounds) and of the per-order process pool of notebooks/02-51peg.py:66-78.  One round = one batched
+ * evaluation of every chunk still iterating (as jb_batch_eval_device_checked) + one launch that takes
+ * each chunk's new [loss, gradient] through its own state machine (More'-Thuente search, BFGS update,
+ * two-loop recursion, next trial point); the host reads back one int per chunk per round.
+ * Options and results have scipy's meaning: m, factr, pgtol, maxiter, maxfun, maxls; warnflag 0 =
+ * converged, 1 = maxiter / maxfun reached, 2 = other; (task, task_msg) index scipy's status_messages /
+ * task_messages tables (4/401 "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 4/402 "... RELATIVE
+ * REDUCTION OF F <= FACTR*EPSMCH", 5/504 "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT", 5/502 "... F,G
+ * EVALUATIONS EXCEEDS LIMIT", 8/0 "ABNORMAL: "); task 7 / task_msg 799: the STARTING point puts an
+ * unmasked pixel outside a knot grid (a later trial point that does so is a large loss without slope,
+ * counted in n_out_of_range).
+ * Regularisers of the loss tree (jabble/loss.py:187-222) are parameter-only terms added on the device:
+ * kind 0: weight * 0.5 * sum (x[i] - constant)^2, kind 1: weight * sum |x[i] - constant| over `indices`
+ * into the fit vector (weight = coefficient * rows of the block: the reference evaluates a regulariser
+ * once per row, loss.py:61-74).
+ */
+typedef struct jb_lbfgs jb_lbfgs;
+typedef struct {
+    int32_t m;          /* pairs kept (scipy: m = 10) */
+    int32_t maxls;      /* trial points per line search (20) */
+    int64_t maxiter;    /* 15000 */
+    int64_t maxfun;     /* 15000 */
+    double factr;       /* 1e7 */
+    double pgtol;       /* 1e-5 */
+} jb_lbfgs_options;
+typedef struct {
+    double f;           /* loss at x */
+    double pg_norm;     /* max |g_i| at the last accepted iterate */
+    int64_t nit, funcalls;
+    int32_t warnflag, task, task_msg;
+    int32_t n_out_of_range, n_skipped, n_restarts;   /* trial points off a knot grid; BFGS pairs skipped; memory resets */
+} jb_lbfgs_result;
+int jb_lbfgs_create(jb_plan *const *plans, int32_t n_plans, const jb_lbfgs_options *options, jb_lbfgs **out);
+void jb_lbfgs_destroy(jb_lbfgs *opt);         /* not the plans */
+int jb_lbfgs_add_reg(jb_lbfgs *opt, int32_t chunk, int32_t kind, double weight, double constant,
+                     const int64_t *indices, int64_t n_indices);
+/* x0[i], x[i] (and grad[i], when grad and grad[i] are not NULL): host vectors of plan i's n_fit doubles.
+ * The plans keep the fit state and the fixed parameters they have (jb_plan_set_params / _set_fit). */
+int jb_lbfgs_run(jb_lbfgs *opt, const double *const *x0, double *const *x, double *const *grad,
+                 jb_lbfgs_result *results);
+int64_t jb_lbfgs_rounds(const jb_lbfgs *opt); /* batched evaluations so far */
+
 /* The device's measured FP64 FMA throughput (TFLOP/s: a register-resident DFMA kernel, best of 3):
  * in float64 the fused kernels sit at the roofline ridge, so benchmarks quote the FP64 pipe next to HBM. */
 int jb_double_peak(int32_t device, double *tflops);

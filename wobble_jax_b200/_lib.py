@@ -47,6 +47,19 @@ class PlanDesc(C.Structure):
     ]
 
 
+class LbfgsOptions(C.Structure):
+    """jb_lbfgs_options (include/jabble_b200.h): scipy's fmin_l_bfgs_b options."""
+    _fields_ = [("m", C.c_int32), ("maxls", C.c_int32), ("maxiter", C.c_int64), ("maxfun", C.c_int64),
+                ("factr", C.c_double), ("pgtol", C.c_double)]
+
+
+class LbfgsResult(C.Structure):
+    """jb_lbfgs_result."""
+    _fields_ = [("f", C.c_double), ("pg_norm", C.c_double), ("nit", C.c_int64), ("funcalls", C.c_int64),
+                ("warnflag", C.c_int32), ("task", C.c_int32), ("task_msg", C.c_int32),
+                ("n_out_of_range", C.c_int32), ("n_skipped", C.c_int32), ("n_restarts", C.c_int32)]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_rows", "n_pix", "n_pix_padded", "n_params", "n_fit", "n_tasks")] + \
                [("rows_per_group", C.c_int32), ("tile_pixels", C.c_int32)] + \
@@ -100,6 +113,11 @@ SYMBOLS = [
     ("jb_group_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("jb_group_launches", C.c_int64, [C.c_void_p]),
     ("jb_double_peak", C.c_int, [C.c_int32, c_f64p]),
+    ("jb_lbfgs_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(LbfgsOptions), C.POINTER(C.c_void_p)]),
+    ("jb_lbfgs_destroy", None, [C.c_void_p]),
+    ("jb_lbfgs_add_reg", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, c_i64p, C.c_int64]),
+    ("jb_lbfgs_run", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(LbfgsResult)]),
+    ("jb_lbfgs_rounds", C.c_int64, [C.c_void_p]),
     ("jb_plan_stream", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("jb_plan_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("jb_plan_profile_read", C.c_int, [C.c_void_p, c_f64p, c_i64p]),

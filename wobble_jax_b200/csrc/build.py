@@ -15,7 +15,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libjabble_b200.so")
 SOURCES = ["jb_plan.cu"]
-DEPS = ["jb_plan.cu", "jb_kernels.cuh", "jb_fused2.cuh", "jb_fused32.cuh", "jb_strip.cuh", "jb_group.cuh", "jb_device.cuh", os.path.join(ROOT, "include", "jabble_b200.h")]
+DEPS = ["jb_plan.cu", "jb_kernels.cuh", "jb_fused2.cuh", "jb_fused32.cuh", "jb_strip.cuh", "jb_group.cuh", "jb_lbfgs.cuh", "jb_device.cuh", os.path.join(ROOT, "include", "jabble_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "--shared", "-cudart", "shared", "-ldl", "-lgomp"]

@@ -1,0 +1,581 @@
+// jb_lbfgs: L-BFGS-B for many independent chunks at once, with every vector on the device.
+// Included at the end of jb_plan.cu.
+//
+// The reference fits a chunk with scipy.optimize.fmin_l_bfgs_b(func, x0, fprime, **options)
+// (jabble/model.py:226-232) and echelle orders in a multiprocessing.Pool, one optimiser per process
+// (notebooks/02-51peg.py:66-78).  No bounds are ever passed, so what runs is the unconstrained
+// branch of L-BFGS-B 3.0 (Zhu, Byrd, Lu, Nocedal 1997; Morales, Nocedal 2011): the quasi-Newton
+// direction -H g of the limited-memory BFGS matrix with H0 = (s'y / y'y) I, then the
+// More'-Thuente line search (MINPACK-2 dcsrch / dcstep, ftol 1e-3, gtol 0.9, xtol 0.1), the first
+// step of a fit scaled to 1 / |d|, at most maxls trial points per search, a BFGS pair skipped when
+// s'y <= eps * (-g'd * stp), the memory dropped and the iteration restarted from steepest descent when
+// a search fails, and the two stopping tests  max|g| <= pgtol  and
+// (f_k - f_k+1) / max(|f_k|, |f_k+1|, 1) <= factr * eps  -- restated here from the published
+// algorithm with scipy's status codes, so that a caller gets the (x, f, d) it got from scipy.
+//
+// One round = ONE batched evaluation of every chunk still iterating (jb_batch: one launch per kernel
+// for all of them) followed by ONE launch of k_lbfgs_advance, a block per chunk, which takes the new
+// [loss, gradient] through that chunk's state machine (line search decision; on an accepted step the
+// BFGS update, the two-loop recursion over the stored pairs, the next trial point) and leaves the next
+// x in place.  The host reads back one int per chunk per round (who is done) and nothing else.
+//
+// Differences from scipy that a caller can see: the direction comes from the two-loop recursion
+// instead of the compact representation (same matrix, different rounding), so iterates agree to
+// rounding for the first iterations and then drift like any two builds of the same optimiser.
+#include <cfloat>
+
+namespace jb {
+
+constexpr int kLbfgsMaxM = 32;
+constexpr int kLbfgsThreads = 512;       // 128 registers per thread: the scalar state of the search lives in registers
+
+enum { kLbFirst = 0, kLbSearch = 1, kLbDone = 2 };
+// scipy/optimize/_lbfgsb_py.py: status_messages / task_messages
+enum { kLbTaskConvergence = 4, kLbTaskStop = 5, kLbTaskError = 7, kLbTaskAbnormal = 8 };
+enum { kLbMsgNone = 0, kLbMsgPgtol = 401, kLbMsgFactr = 402, kLbMsgMaxfun = 502, kLbMsgMaxiter = 504, kLbMsgOutOfRange = 799 };
+
+struct LbfgsState {
+    double f, fold, stp, dnorm, gd, gdold, theta, sbgnrm, f_inside;
+    double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;     // dcsrch
+    long long iter, funcalls;
+    int brackt, stage, col, head, ifun, iback, phase, task, msg, warnflag, n_oor, nskip, nrestart, pad_;
+};
+struct LbfgsReg { const long long* idx; long long n; double weight; double constant; int kind; int pad_; };   // kind 0: L2, 1: L1
+struct LbfgsProblem {
+    long long n;
+    double *x, *out, *xold, *gold, *d, *z, *S, *Y;     // out = [f, g[n]] of the evaluation; S, Y: [m][n]
+    LbfgsState* st;
+    double* rho;                                        // [m]: 1 / s'y of the stored pairs
+    const LbfgsReg* regs;
+    int n_regs, pad_;
+};
+struct LbfgsOpts { int m, maxls; long long maxiter, maxfun; double tol, pgtol; };
+
+struct LbfgsRed { double buf[2][32]; int par; };
+
+// Sum / max over the block in one fixed order; every thread gets the result.  One barrier per call
+// (two alternating buffers: the barrier of call k + 1 separates the reads of call k from the writes
+// of call k + 2).
+__device__ __forceinline__ double lb_sum(double v, LbfgsRed& r, int& par) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) r.buf[par][warp] = v;
+    __syncthreads();
+    double t = lane < (int)(blockDim.x >> 5) ? r.buf[par][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    par ^= 1;
+    return t;
+}
+__device__ __forceinline__ double lb_max(double v, LbfgsRed& r, int& par) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) r.buf[par][warp] = v;
+    __syncthreads();
+    double t = lane < (int)(blockDim.x >> 5) ? r.buf[par][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    par ^= 1;
+    return t;
+}
+
+// MINPACK-2 dcstep: the safeguarded cubic / quadratic step of the More'-Thuente search and the update
+// of the interval of uncertainty [stx, sty].
+__device__ inline void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
+                                 double fp, double dp, int& brackt, double stpmin, double stpmax) {
+    const double sgnd = dp * (dx / fabs(dx));
+    double stpf;
+    if (fp > fx) {                       // higher value: the minimum is bracketed
+        const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp < stx) gamma = -gamma;
+        const double p = (gamma - dx) + theta, q = ((gamma - dx) + gamma) + dp, r = p / q;
+        const double stpc = stx + r * (stp - stx);
+        const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+        stpf = fabs(stpc - stx) < fabs(stpq - stx) ? stpc : stpc + (stpq - stpc) / 2.0;
+        brackt = 1;
+    } else if (sgnd < 0.0) {             // lower value, derivatives of opposite sign: bracketed
+        const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp > stx) gamma = -gamma;
+        const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dx, r = p / q;
+        const double stpc = stp + r * (stx - stp);
+        const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        stpf = fabs(stpc - stp) > fabs(stpq - stp) ? stpc : stpq;
+        brackt = 1;
+    } else if (fabs(dp) < fabs(dx)) {    // lower value, same sign, the derivative shrinks
+        const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        double gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+        if (stp > stx) gamma = -gamma;
+        const double p = (gamma - dp) + theta, q = (gamma + (dx - dp)) + gamma, r = p / q;
+        double stpc;
+        if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+        else stpc = stp > stx ? stpmax : stpmin;
+        const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (brackt) {
+            stpf = fabs(stpc - stp) < fabs(stpq - stp) ? stpc : stpq;
+            if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+            else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+        } else {
+            stpf = fabs(stpc - stp) > fabs(stpq - stp) ? stpc : stpq;
+            stpf = fmin(stpmax, stpf);
+            stpf = fmax(stpmin, stpf);
+        }
+    } else {                             // lower value, same sign, the derivative does not shrink
+        if (brackt) {
+            const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+            const double s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
+            double gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+            if (stp > sty) gamma = -gamma;
+            const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dy, r = p / q;
+            stpf = stp + r * (sty - stp);
+        } else {
+            stpf = stp > stx ? stpmax : stpmin;
+        }
+    }
+    if (fp > fx) { sty = stp; fy = fp; dy = dp; }
+    else {
+        if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+        stx = stp; fx = fp; dx = dp;
+    }
+    stp = stpf;
+}
+
+constexpr double kLbFtol = 1.0e-3, kLbGtol = 0.9, kLbXtol = 0.1, kLbStpMin = 0.0, kLbStpMax = 1.0e10;
+
+__device__ inline void lb_dcsrch_start(LbfgsState& s, double f, double g) {
+    s.brackt = 0; s.stage = 1;
+    s.finit = f; s.ginit = g; s.gtest = kLbFtol * g;
+    s.width = kLbStpMax - kLbStpMin; s.width1 = s.width / 0.5;
+    s.stx = 0.0; s.fx = f; s.gx = g; s.sty = 0.0; s.fy = f; s.gy = g;
+    s.stmin = 0.0; s.stmax = s.stp + 4.0 * s.stp;
+}
+// One More'-Thuente step at the trial point (f, g = slope along d).  true: the search is over
+// (converged, or one of dcsrch's warnings -- L-BFGS-B treats both as "step accepted").
+__device__ inline bool lb_dcsrch(LbfgsState& s, double f, double g) {
+    double stp = s.stp;
+    const double ftest = s.finit + stp * s.gtest;
+    if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
+    bool over = false;
+    if (s.brackt && (stp <= s.stmin || stp >= s.stmax)) over = true;               // rounding errors prevent progress
+    if (s.brackt && s.stmax - s.stmin <= kLbXtol * s.stmax) over = true;           // xtol test satisfied
+    if (stp == kLbStpMax && f <= ftest && g <= s.gtest) over = true;
+    if (stp == kLbStpMin && (f > ftest || g >= s.gtest)) over = true;
+    if (f <= ftest && fabs(g) <= kLbGtol * -s.ginit) over = true;                  // strong Wolfe conditions hold
+    if (over) return true;
+    if (s.stage == 1 && f <= s.fx && f > ftest) {
+        // a lower value without sufficient decrease: step on the modified function psi
+        const double fm = f - stp * s.gtest;
+        double fxm = s.fx - s.stx * s.gtest, fym = s.fy - s.sty * s.gtest;
+        const double gm = g - s.gtest;
+        double gxm = s.gx - s.gtest, gym = s.gy - s.gtest;
+        lb_dcstep(s.stx, fxm, gxm, s.sty, fym, gym, stp, fm, gm, s.brackt, s.stmin, s.stmax);
+        s.fx = fxm + s.stx * s.gtest; s.fy = fym + s.sty * s.gtest;
+        s.gx = gxm + s.gtest; s.gy = gym + s.gtest;
+    } else {
+        lb_dcstep(s.stx, s.fx, s.gx, s.sty, s.fy, s.gy, stp, f, g, s.brackt, s.stmin, s.stmax);
+    }
+    if (s.brackt) {
+        if (fabs(s.sty - s.stx) >= 0.66 * s.width1) stp = s.stx + 0.5 * (s.sty - s.stx);
+        s.width1 = s.width;
+        s.width = fabs(s.sty - s.stx);
+    }
+    if (s.brackt) { s.stmin = fmin(s.stx, s.sty); s.stmax = fmax(s.stx, s.sty); }
+    else { s.stmin = stp + 1.1 * (stp - s.stx); s.stmax = stp + 4.0 * (stp - s.stx); }
+    stp = fmax(stp, kLbStpMin);
+    stp = fmin(stp, kLbStpMax);
+    if ((s.brackt && (stp <= s.stmin || stp >= s.stmax)) || (s.brackt && s.stmax - s.stmin <= kLbXtol * s.stmax)) stp = s.stx;
+    s.stp = stp;
+    return false;
+}
+
+// One block per chunk that is still iterating (active[blockIdx.x] names it).
+__global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProblem* __restrict__ probs, const int* __restrict__ active,
+                                                                 LbfgsOpts o, int* __restrict__ flags) {
+    __shared__ LbfgsRed red;
+    __shared__ double alpha[kLbfgsMaxM], rho[kLbfgsMaxM];
+    const int pid = active[blockIdx.x];
+    const LbfgsProblem P = probs[pid];
+    LbfgsState s = *P.st;                  // every thread carries the (identical) scalar state; thread 0 stores it
+    if (s.phase == kLbDone) return;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid < o.m) rho[tid] = P.rho[tid];
+    __syncthreads();
+    const long long n = P.n;
+    int par = 0;
+    double* g = P.out + 1;
+    const int m = o.m;
+
+    auto finish = [&](int task, int msg, int warn) {
+        s.phase = kLbDone; s.task = task; s.msg = msg; s.warnflag = warn;
+    };
+
+    // ---- the evaluation: [loss, gradient] of the data term, then the regularisers -------------------
+    double f = P.out[0];
+    if (!isfinite(f)) {
+        // the trial point carried an unmasked pixel off a knot grid (k_finish wrote NaN).  The reference's
+        // gather clamps there and scipy sees a large finite loss; here the search is told the same: a
+        // loss far above the last valid one, no slope.  At the starting point it is the caller's error.
+        if (s.phase == kLbFirst) {
+            finish(kLbTaskError, kLbMsgOutOfRange, 2);
+            if (tid == 0) { *P.st = s; flags[pid] = kLbDone; }
+            return;
+        }
+        f = 1.0e8 * fmax(fabs(s.f_inside), 1.0);
+        for (long long i = tid; i < n; i += T) g[i] = 0.0;
+        s.n_oor++;
+    } else {
+        s.f_inside = f;
+    }
+    if (P.n_regs) __syncthreads();
+    for (int r = 0; r < P.n_regs; ++r) {
+        const LbfgsReg R = P.regs[r];
+        double part = 0.0;
+        for (long long j = tid; j < R.n; j += T) {
+            const long long i = R.idx[j];
+            const double dl = P.x[i] - R.constant;
+            if (R.kind == 0) { part += dl * dl; g[i] += R.weight * dl; }
+            else { part += fabs(dl); g[i] += R.weight * (dl > 0.0 ? 1.0 : (dl < 0.0 ? -1.0 : 0.0)); }
+        }
+        const double tot = lb_sum(part, red, par);
+        f += R.kind == 0 ? R.weight * 0.5 * tot : R.weight * tot;
+    }
+    if (P.n_regs) __syncthreads();
+    s.funcalls++;
+
+    bool start = false;          // begin a new iteration (direction + first trial point) from (x, f, g)
+    if (s.phase == kLbFirst) {
+        double mx = 0.0;
+        for (long long i = tid; i < n; i += T) mx = fmax(mx, fabs(g[i]));
+        s.sbgnrm = lb_max(mx, red, par);
+        s.f = f;
+        if (s.sbgnrm <= o.pgtol) finish(kLbTaskConvergence, kLbMsgPgtol, 0);
+        else start = true;
+    } else {
+        double part = 0.0;
+        for (long long i = tid; i < n; i += T) part += g[i] * P.d[i];
+        const double gd = lb_sum(part, red, par);
+        s.gd = gd;
+        if (!lb_dcsrch(s, f, gd)) {
+            // another trial point, unless the search has used up its evaluations
+            s.ifun++; s.iback = s.ifun - 1;
+            if (s.iback >= o.maxls) {
+                // give up the search: back to the iterate it started from
+                for (long long i = tid; i < n; i += T) { P.x[i] = P.xold[i]; g[i] = P.gold[i]; }
+                f = s.fold; s.f = f;
+                if (s.col == 0) { s.iter++; finish(kLbTaskAbnormal, kLbMsgNone, 2); }
+                else { s.col = 0; s.head = 0; s.theta = 1.0; s.nrestart++; start = true; }
+            } else {
+                const double stp = s.stp;
+                for (long long i = tid; i < n; i += T) P.x[i] = stp * P.d[i] + P.xold[i];
+            }
+        } else {
+            // the step is accepted: x is the new iterate
+            s.iter++;
+            s.f = f;
+            double mx = 0.0;
+            for (long long i = tid; i < n; i += T) mx = fmax(mx, fabs(g[i]));
+            s.sbgnrm = lb_max(mx, red, par);
+            const double dmax = fmax(fmax(fabs(s.fold), fabs(f)), 1.0);
+            if (s.iter >= o.maxiter) finish(kLbTaskStop, kLbMsgMaxiter, 1);
+            else if (s.funcalls > o.maxfun) finish(kLbTaskStop, kLbMsgMaxfun, 1);
+            else if (s.sbgnrm <= o.pgtol) finish(kLbTaskConvergence, kLbMsgPgtol, 0);
+            else if (s.fold - f <= o.tol * dmax) finish(kLbTaskConvergence, kLbMsgFactr, 0);
+            else {
+                // BFGS pair: s = stp d, y = g - g_old (left in gold); s'y from the search's slopes
+                double rr = 0.0;
+                for (long long i = tid; i < n; i += T) { const double y = g[i] - P.gold[i]; P.gold[i] = y; rr += y * y; }
+                rr = lb_sum(rr, red, par);
+                double dr, ddum;
+                if (s.stp == 1.0) { dr = gd - s.gdold; ddum = -s.gdold; }
+                else { dr = (gd - s.gdold) * s.stp; ddum = -s.gdold * s.stp; }
+                if (dr <= DBL_EPSILON * ddum) {
+                    s.nskip++;
+                } else {
+                    int slot;
+                    if (s.col < m) { slot = (s.head + s.col) % m; s.col++; }
+                    else { slot = s.head; s.head = (s.head + 1) % m; }
+                    double* Ss = P.S + (long long)slot * n;
+                    double* Ys = P.Y + (long long)slot * n;
+                    const double stp = s.stp;
+                    for (long long i = tid; i < n; i += T) { Ss[i] = stp * P.d[i]; Ys[i] = P.gold[i]; }
+                    __syncthreads();
+                    if (tid == 0) { rho[slot] = 1.0 / dr; P.rho[slot] = 1.0 / dr; }
+                    __syncthreads();
+                    s.theta = rr / dr;
+                }
+                start = true;
+            }
+        }
+    }
+
+    // ---- a new iteration: direction, set-up of the search, first trial point --------------------------
+    while (start) {
+        start = false;
+        const int col = s.col;
+        double* q = P.d;
+        if (col == 0) {
+            for (long long i = tid; i < n; i += T) q[i] = -g[i];
+        } else {
+            // two-loop recursion; every thread owns the elements i = tid (mod T) of q, so only the
+            // dot products cross threads.  The axpy of one pair is fused with the dot of the next.
+            double part = 0.0;
+            {
+                const double* Sj = P.S + (long long)((s.head + col - 1) % m) * n;
+                for (long long i = tid; i < n; i += T) { const double v = g[i]; q[i] = v; part += Sj[i] * v; }
+            }
+            for (int k = col - 1; k >= 0; --k) {
+                const int j = (s.head + k) % m;
+                const double a = rho[j] * lb_sum(part, red, par);
+                if (tid == 0) alpha[k] = a;
+                const double* Yj = P.Y + (long long)j * n;
+                part = 0.0;
+                if (k > 0) {
+                    const double* Sn = P.S + (long long)((s.head + k - 1) % m) * n;
+                    for (long long i = tid; i < n; i += T) { const double v = q[i] - a * Yj[i]; q[i] = v; part += Sn[i] * v; }
+                } else {
+                    // r = H0 q, and the first dot of the second loop
+                    const double gamma = 1.0 / s.theta;
+                    for (long long i = tid; i < n; i += T) { const double v = (q[i] - a * Yj[i]) * gamma; q[i] = v; part += Yj[i] * v; }
+                }
+            }
+            __syncthreads();      // alpha[]
+            for (int k = 0; k < col; ++k) {
+                const int j = (s.head + k) % m;
+                const double b = rho[j] * lb_sum(part, red, par);
+                const double c = alpha[k] - b;
+                const double* Sj = P.S + (long long)j * n;
+                part = 0.0;
+                if (k + 1 < col) {
+                    const double* Yn = P.Y + (long long)((s.head + k + 1) % m) * n;
+                    for (long long i = tid; i < n; i += T) { const double v = q[i] + c * Sj[i]; q[i] = v; part += Yn[i] * v; }
+                } else {
+                    for (long long i = tid; i < n; i += T) q[i] = -(q[i] + c * Sj[i]);
+                }
+            }
+        }
+        // L-BFGS-B forms the point z = x + direction and searches along d = z - x
+        double dtd = 0.0, gd = 0.0;
+        for (long long i = tid; i < n; i += T) {
+            const double xi = P.x[i], gi = g[i];
+            const double zi = xi + q[i];
+            const double di = zi - xi;
+            P.z[i] = zi; q[i] = di;
+            P.xold[i] = xi; P.gold[i] = gi;
+            dtd += di * di; gd += gi * di;
+        }
+        dtd = lb_sum(dtd, red, par);
+        gd = lb_sum(gd, red, par);
+        s.dnorm = sqrt(dtd);
+        s.stp = s.iter == 0 ? fmin(1.0 / s.dnorm, kLbStpMax) : 1.0;
+        s.fold = s.f;
+        s.ifun = 0; s.iback = 0;
+        s.gd = gd; s.gdold = gd;
+        if (!(gd < 0.0)) {
+            // not a descent direction (rounding in a nearly singular memory): drop the memory
+            if (col == 0) { s.iter++; finish(kLbTaskAbnormal, kLbMsgNone, 2); }
+            else { s.col = 0; s.head = 0; s.theta = 1.0; s.nrestart++; start = true; }
+            continue;
+        }
+        lb_dcsrch_start(s, s.f, gd);
+        s.ifun = 1; s.iback = 0;
+        const double stp = s.stp;
+        if (stp == 1.0) { for (long long i = tid; i < n; i += T) P.x[i] = P.z[i]; }
+        else { for (long long i = tid; i < n; i += T) P.x[i] = stp * q[i] + P.xold[i]; }
+        s.phase = kLbSearch;
+    }
+    if (tid == 0) { *P.st = s; flags[pid] = s.phase; }
+}
+
+}  // namespace jb
+
+struct jb_lbfgs {
+    std::vector<jb_plan*> plans;
+    int device = 0;
+    jb::LbfgsOpts opt{};
+    std::vector<jb::LbfgsProblem> probs;
+    std::vector<std::vector<jb::LbfgsReg>> regs;              // device index pointers inside
+    std::vector<void*> dev;                                    // everything cudaMalloc'ed here
+    jb::LbfgsProblem* d_probs = nullptr;
+    jb::LbfgsState* d_states = nullptr;
+    jb::LbfgsReg* d_regs = nullptr;
+    int *d_flags = nullptr, *d_active = nullptr, *h_flags = nullptr;
+    bool regs_dirty = true;
+    int64_t rounds = 0, launches = 0, batches_built = 0;
+};
+
+namespace {
+template <typename T>
+int lb_alloc(jb_lbfgs* h, T** out, size_t count) {
+    void* p = nullptr;
+    JB_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    h->dev.push_back(p);
+    *out = static_cast<T*>(p);
+    return JB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* opt, jb_lbfgs** out) {
+    if (!plans || n <= 0 || !opt || !out) return fail(JB_ERR_BAD_ARG, "bad arguments");
+    *out = nullptr;
+    if (opt->m <= 0 || opt->m > jb::kLbfgsMaxM) return fail(JB_ERR_BAD_ARG, "m must be in 1..%d", jb::kLbfgsMaxM);
+    if (opt->maxls <= 0) return fail(JB_ERR_BAD_ARG, "maxls must be positive");
+    if (opt->factr < 0 || opt->pgtol < 0) return fail(JB_ERR_BAD_ARG, "factr and pgtol must not be negative");
+    for (int i = 0; i < n; ++i) {
+        if (!plans[i]) return fail(JB_ERR_BAD_ARG, "null plan");
+        if (plans[i]->device != plans[0]->device) return fail(JB_ERR_BAD_ARG, "the plans must live on one device");
+        if (plans[i]->f32) return fail(JB_ERR_UNSUPPORTED, "the optimiser iterates in float64");
+        if (plans[i]->n_fit <= 0) return fail(JB_ERR_BAD_ARG, "plan %d has no parameter in fit mode", i);
+    }
+    JB_CUDA(cudaSetDevice(plans[0]->device));
+    std::unique_ptr<jb_lbfgs, void (*)(jb_lbfgs*)> h(new jb_lbfgs, jb_lbfgs_destroy);
+    h->plans.assign(plans, plans + n);
+    h->device = plans[0]->device;
+    h->opt.m = opt->m; h->opt.maxls = opt->maxls; h->opt.maxiter = opt->maxiter; h->opt.maxfun = opt->maxfun;
+    h->opt.tol = opt->factr * DBL_EPSILON; h->opt.pgtol = opt->pgtol;
+    h->probs.resize(n);
+    h->regs.resize(n);
+    int rc;
+    if ((rc = lb_alloc(h.get(), &h->d_states, (size_t)n))) return rc;
+    for (int i = 0; i < n; ++i) {
+        jb::LbfgsProblem& P = h->probs[i];
+        memset(&P, 0, sizeof P);
+        P.n = plans[i]->n_fit;
+        const size_t nn = (size_t)P.n;
+        double* base = nullptr;
+        // x | out (1 + n) | xold | gold | d | z | S (m n) | Y (m n)
+        if ((rc = lb_alloc(h.get(), &base, nn * (6 + 2 * (size_t)opt->m) + 2))) return rc;
+        P.x = base; P.out = base + nn; P.xold = P.out + nn + 1; P.gold = P.xold + nn; P.d = P.gold + nn; P.z = P.d + nn;
+        P.S = P.z + nn; P.Y = P.S + nn * opt->m;
+        P.st = h->d_states + i;
+        if ((rc = lb_alloc(h.get(), &P.rho, (size_t)jb::kLbfgsMaxM))) return rc;
+    }
+    if ((rc = lb_alloc(h.get(), &h->d_probs, (size_t)n))) return rc;
+    if ((rc = lb_alloc(h.get(), &h->d_flags, (size_t)n))) return rc;
+    if ((rc = lb_alloc(h.get(), &h->d_active, (size_t)n))) return rc;
+    JB_CUDA(cudaMallocHost(&h->h_flags, (size_t)n * sizeof(int)));
+    *out = h.release();
+    return JB_OK;
+}
+
+void jb_lbfgs_destroy(jb_lbfgs* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->dev) cudaFree(p);
+    if (h->d_regs) cudaFree(h->d_regs);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    delete h;
+}
+
+int jb_lbfgs_add_reg(jb_lbfgs* h, int32_t problem, int32_t kind, double weight, double constant, const int64_t* indices, int64_t n_indices) {
+    if (!h || problem < 0 || problem >= (int)h->plans.size() || (kind != 0 && kind != 1) || n_indices < 0 || (n_indices && !indices))
+        return fail(JB_ERR_BAD_ARG, "bad regulariser");
+    JB_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->probs[problem].n;
+    std::vector<long long> idx((size_t)n_indices);
+    for (int64_t j = 0; j < n_indices; ++j) {
+        if (indices[j] < 0 || indices[j] >= n) return fail(JB_ERR_BAD_ARG, "regulariser index %lld outside the fit vector (%lld)", (long long)indices[j], (long long)n);
+        idx[(size_t)j] = indices[j];
+    }
+    long long* d_idx = nullptr;
+    int rc = lb_alloc(h, &d_idx, idx.size());
+    if (rc) return rc;
+    if (!idx.empty()) JB_CUDA(cudaMemcpy(d_idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    jb::LbfgsReg R;
+    R.idx = d_idx; R.n = n_indices; R.weight = weight; R.constant = constant; R.kind = kind; R.pad_ = 0;
+    h->regs[problem].push_back(R);
+    h->regs_dirty = true;
+    return JB_OK;
+}
+
+int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, double* const* grad_out, jb_lbfgs_result* results) {
+    if (!h || !x0 || !x_out || !results) return fail(JB_ERR_BAD_ARG, "null argument");
+    JB_CUDA(cudaSetDevice(h->device));
+    const int n = (int)h->plans.size();
+    cudaStream_t st = h->plans[0]->stream;
+    int rc;
+    for (int i = 0; i < n; ++i) {
+        if (!x0[i] || !x_out[i]) return fail(JB_ERR_BAD_ARG, "null vector for chunk %d", i);
+        if (h->plans[i]->n_fit != h->probs[i].n) return fail(JB_ERR_BAD_ARG, "chunk %d: the fit vector changed size since jb_lbfgs_create", i);
+    }
+    if (h->regs_dirty) {
+        if (h->d_regs) { cudaFree(h->d_regs); h->d_regs = nullptr; }
+        std::vector<jb::LbfgsReg> flat;
+        for (int i = 0; i < n; ++i) flat.insert(flat.end(), h->regs[i].begin(), h->regs[i].end());
+        if (!flat.empty()) {
+            JB_CUDA(cudaMalloc(&h->d_regs, flat.size() * sizeof(jb::LbfgsReg)));
+            JB_CUDA(cudaMemcpy(h->d_regs, flat.data(), flat.size() * sizeof(jb::LbfgsReg), cudaMemcpyHostToDevice));
+        }
+        size_t o = 0;
+        for (int i = 0; i < n; ++i) {
+            h->probs[i].regs = h->d_regs ? h->d_regs + o : nullptr;
+            h->probs[i].n_regs = (int)h->regs[i].size();
+            o += h->regs[i].size();
+        }
+        JB_CUDA(cudaMemcpy(h->d_probs, h->probs.data(), (size_t)n * sizeof(jb::LbfgsProblem), cudaMemcpyHostToDevice));
+        h->regs_dirty = false;
+    }
+    // starting points and fresh states
+    std::vector<jb::LbfgsState> hs((size_t)n);
+    memset(hs.data(), 0, hs.size() * sizeof(jb::LbfgsState));
+    for (int i = 0; i < n; ++i) {
+        hs[i].theta = 1.0; hs[i].phase = jb::kLbFirst;
+        JB_CUDA(cudaMemcpyAsync(h->probs[i].x, x0[i], (size_t)h->probs[i].n * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    JB_CUDA(cudaMemcpyAsync(h->d_states, hs.data(), hs.size() * sizeof(jb::LbfgsState), cudaMemcpyHostToDevice, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+
+    std::vector<int> active((size_t)n);
+    for (int i = 0; i < n; ++i) active[i] = i;
+    jb_batch* batch = nullptr;
+    auto drop_batch = [&]() { if (batch) { jb_batch_destroy(batch); batch = nullptr; } };
+    rc = JB_OK;
+    while (!active.empty()) {
+        if (!batch) {
+            std::vector<jb_plan*> pl; std::vector<const double*> px; std::vector<double*> po;
+            for (int i : active) { pl.push_back(h->plans[i]); px.push_back(h->probs[i].x); po.push_back(h->probs[i].out); }
+            if ((rc = jb_batch_create(pl.data(), (int)pl.size(), &batch))) break;
+            if ((rc = jb_batch_bind(batch, px.data(), po.data()))) break;
+            jb_batch_soft_range(batch, 1);
+            if (cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(JB_ERR_CUDA, "cudaMemcpyAsync failed"); break; }
+            h->batches_built++;
+        }
+        if ((rc = jb_batch_eval_device_checked(batch, st))) break;
+        jb::k_lbfgs_advance<<<(unsigned)active.size(), jb::kLbfgsThreads, 0, st>>>(h->d_probs, h->d_active, h->opt, h->d_flags);
+        if (cudaMemcpyAsync(h->h_flags, h->d_flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = fail(JB_ERR_CUDA, "L-BFGS round failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        h->rounds++; h->launches += 1;
+        std::vector<int> next;
+        for (int i : active) if (h->h_flags[i] != jb::kLbDone) next.push_back(i);
+        if (next.size() != active.size()) { active.swap(next); drop_batch(); }
+    }
+    if (batch) h->launches += jb_batch_launches(batch);
+    drop_batch();
+    if (rc) return rc;
+    JB_CUDA(cudaMemcpy(hs.data(), h->d_states, hs.size() * sizeof(jb::LbfgsState), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const jb::LbfgsProblem& P = h->probs[i];
+        JB_CUDA(cudaMemcpy(x_out[i], P.x, (size_t)P.n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (grad_out && grad_out[i]) JB_CUDA(cudaMemcpy(grad_out[i], P.out + 1, (size_t)P.n * sizeof(double), cudaMemcpyDeviceToHost));
+        jb_lbfgs_result& R = results[i];
+        R.f = hs[i].f; R.pg_norm = hs[i].sbgnrm; R.nit = hs[i].iter; R.funcalls = hs[i].funcalls;
+        R.warnflag = hs[i].warnflag; R.task = hs[i].task; R.task_msg = hs[i].msg;
+        R.n_out_of_range = hs[i].n_oor; R.n_skipped = hs[i].nskip; R.n_restarts = hs[i].nrestart;
+    }
+    return JB_OK;
+}
+
+int64_t jb_lbfgs_rounds(const jb_lbfgs* h) { return h ? h->rounds : 0; }
+
+}  // extern "C"

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -1900,3 +1901,4 @@ int jb_plan_grad_all(jb_plan* pl, double* grad_all, int64_t n) {
 }  // extern "C"
 
 #include "jb_group.cuh"
+#include "jb_lbfgs.cuh"

@@ -656,6 +656,85 @@ class Objective:
         return self._eval(p)[1].copy()
 
 
+_LBFGS_STATUS = {4: "CONVERGENCE", 5: "STOP", 7: "ERROR", 8: "ABNORMAL"}      # scipy/optimize/_lbfgsb_py.py status_messages
+_LBFGS_TASK = {0: "", 401: "NORM OF PROJECTED GRADIENT <= PGTOL", 402: "RELATIVE REDUCTION OF F <= FACTR*EPSMCH",
+               502: "TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT", 504: "TOTAL NO. OF ITERATIONS REACHED LIMIT",
+               799: "STARTING POINT OUTSIDE THE KNOT GRID"}
+_LBFGS_DEFAULTS = {"m": 10, "factr": 1e7, "pgtol": 1e-5, "maxfun": 15000, "maxiter": 15000, "maxls": 20}
+
+
+def lbfgs_options_supported(options):
+    """Can the device optimiser take these ``fmin_l_bfgs_b`` keyword options?  (No bounds -- the
+    reference never passes any, model.py:226-232 --, no callback, analytic gradient.)"""
+    for k, v in options.items():
+        if k in _LBFGS_DEFAULTS:
+            continue
+        if k in ("bounds", "callback") and v is None:
+            continue
+        if k in ("approx_grad",) and not v:
+            continue
+        if k in ("args",) and tuple(v) == ():
+            continue
+        if k in ("epsilon",):
+            continue
+        return False
+    return 1 <= int(options.get("m", 10)) <= 32 and int(options.get("maxls", 20)) > 0
+
+
+def minimize_lbfgs(objectives, x0s, options=None):
+    """``scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)`` for every
+    objective at once, on the device (``jb_lbfgs``, include/jabble_b200.h): one batched evaluation per
+    round for all chunks still iterating, optimiser state and vectors in HBM.  Returns scipy's
+    ``(x, f, d)`` per objective, ``d`` = {grad, task, funcalls, nit, warnflag}."""
+    options = dict(options or {})
+    if not lbfgs_options_supported(options):
+        raise NotImplementedError(f"options {sorted(options)} need scipy's optimiser")
+    lib = _lib.load()
+    opt = _lib.LbfgsOptions()
+    for k, v in _LBFGS_DEFAULTS.items():
+        val = options.get(k, v)
+        setattr(opt, k, float(val) if k in ("factr", "pgtol") else int(val))
+    n = len(objectives)
+    for o in objectives:          # the plan carries this objective's fixed parameters and fit state
+        if o.plan._owner is not o:
+            o.plan.set_params(o._params_all)
+            o.plan.set_fit(o._fit_index)
+            o.plan._owner = o
+    handle = C.c_void_p()
+    plans = (C.c_void_p * n)(*[o.plan.handle for o in objectives])
+    _lib.check(lib.jb_lbfgs_create(plans, n, C.byref(opt), C.byref(handle)))
+    try:
+        for i, o in enumerate(objectives):
+            from . import loss as L
+            for r in o.regs:
+                idx = np.ascontiguousarray(np.asarray(r.indices, dtype=np.int64).reshape(-1))
+                _lib.check(lib.jb_lbfgs_add_reg(handle, i, 1 if isinstance(r, L.L1Reg) else 0, float(o.n_rows) * float(r.coefficient),
+                                                float(r.constant), idx.ctypes.data_as(_lib.c_i64p), idx.size))
+        x0 = [np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)) for x in x0s]
+        for o, x in zip(objectives, x0):
+            if x.size != o.plan.n_fit:
+                raise ValueError(f"x0 has {x.size} entries, the model has {o.plan.n_fit} parameters in fit mode")
+        xs = [np.empty_like(x) for x in x0]
+        gs = [np.empty_like(x) for x in x0]
+        res = (_lib.LbfgsResult * n)()
+        as_ptrs = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        _lib.check(lib.jb_lbfgs_run(handle, as_ptrs(x0), as_ptrs(xs), as_ptrs(gs), res))
+        rounds = int(lib.jb_lbfgs_rounds(handle))
+    finally:
+        lib.jb_lbfgs_destroy(handle)
+    out = []
+    for o, x, g, r in zip(objectives, xs, gs, res):
+        o.n_evals += int(r.funcalls)
+        o.n_out_of_range += int(r.n_out_of_range)
+        o.lbfgs_rounds = rounds
+        if r.task == 7:
+            raise ValueError("an unmasked warped pixel lies outside the knot grid of a spline component (at the starting point)")
+        d = {"grad": g, "task": _LBFGS_STATUS.get(int(r.task), "?") + ": " + _LBFGS_TASK.get(int(r.task_msg), ""),
+             "funcalls": int(r.funcalls), "nit": int(r.nit), "warnflag": int(r.warnflag)}
+        out.append((x, float(r.f), d))
+    return out
+
+
 class LockstepEvaluator:
     """Evaluations of several independent objectives (chunks / orders, each driven by its own scipy
     L-BFGS-B in its own thread) sent to the GPU together: a thread that asks for (loss, gradient)

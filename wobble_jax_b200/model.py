@@ -131,6 +131,13 @@ def save_rvs(filename, rv_inds, model, dataset, loss, time, device=None):
         hf.create_dataset("rv_error_2d_full", data=quickplay.get_RV_error_2d(model, dataset, loss, rv_inds, device))
 
 
+# Which L-BFGS-B runs the fits: "device" = jb_lbfgs (the library's batched optimiser: state and
+# vectors in HBM, one evaluation launch per round for all chunks), "scipy" = scipy.optimize.fmin_l_bfgs_b
+# on the host, one thread per chunk (always used for options the device optimiser does not take:
+# bounds, callback, approx_grad).
+OPTIMIZER = "device"
+
+
 def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_size=None, options={}):
     """``Model.optimize`` (model.py:195-238) for many independent models at once -- the echelle orders /
     chunks the reference fits in a ``multiprocessing.Pool(jax.device_count())``
@@ -153,6 +160,9 @@ def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_
         ls.ready_indices(model)
         x0s.append(np.asarray(model.get_parameters(), dtype=np.float64))
         objectives.append(engine.Objective(ls, model, datablock, metablock))
+    if OPTIMIZER == "device" and engine.lbfgs_options_supported(options):
+        out = engine.minimize_lbfgs(objectives, x0s, options)
+        return _record_many(models, losses, out)
     evaluator = engine.LockstepEvaluator(objectives)
     out, errors = [None] * len(models), [None] * len(models)
 
@@ -173,6 +183,10 @@ def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_
     for exc in errors:
         if exc is not None:
             raise exc
+    return _record_many(models, losses, out)
+
+
+def _record_many(models, losses, out):
     for model, ls, (x, f, d) in zip(models, losses, out):
         model.results = np.append(
             model.results,
@@ -231,7 +245,10 @@ class Model:
         objective = engine.Objective(loss, self, datablock, metablock)
         # func returns (loss, gradient): the pair the reference hands scipy as func / fprime
         # (model.py:226-229), from one fused evaluation and one callback
-        x, f, d = scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)
+        if OPTIMIZER == "device" and engine.lbfgs_options_supported(options):
+            x, f, d = engine.minimize_lbfgs([objective], [x0], options)[0]
+        else:
+            x, f, d = scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)
         self.results = np.append(
             self.results,
             np.array([(d["task"], d["funcalls"], d["nit"], d["warnflag"], f, repr(loss))],
