@@ -212,21 +212,27 @@ def run_b200(args, rank, world, local_rank):
     def make(c):
         # generated, canonicalised and uploaded on a host thread of its own (ctypes drops the GIL)
         torch.cuda.set_device(local_rank)
+        t0 = time.perf_counter()
         ch = synth.make_chunk(rank * args.chunks + c, n_epochs=args.epochs, n_pix=args.pixels,
                               p_val=args.p_val, as_block=True)
         model = synth.fit_all(ch.model)
+        t1 = time.perf_counter()
         plan = engine.Plan(engine.TreeSpec(model), ch.datablock["xs"], ch.datablock["ys"], ch.datablock["yivar"],
                            ch.datablock["mask"], ch.metablock, device=local_rank,
                            rows_per_group=rows_per_group, float32=args.float32)
         plan.sync_from_model()
-        return plan, np.asarray(model.get_parameters()).copy()
+        setup_split[0] += t1 - t0                     # synthetic data (numpy, host): the bench's own cost
+        setup_split[1] += time.perf_counter() - t1    # jb_plan_create: canonical block, upload, sort, strip layout
+        return plan, np.asarray(model.get_parameters()).copy(), model
 
-    plans, p_host = [], []
+    plans, p_host, models = [], [], []
+    setup_split = [0.0, 0.0]
     nworkers = max(1, min(8, len(os.sched_getaffinity(0)) // max(world, 1), args.chunks))
     with ThreadPoolExecutor(nworkers) as pool:
-        for plan, p in pool.map(make, range(args.chunks)):
+        for plan, p, model in pool.map(make, range(args.chunks)):
             plans.append(plan)
             p_host.append(p)
+            models.append(model)
     info = plans[0].info()
     n_fit = info["n_fit"]
     setup_s = time.perf_counter() - t_setup
@@ -485,9 +491,15 @@ def run_b200(args, rank, world, local_rank):
         "fp64": fp64_info,
         "plan": {k: info[k] for k in ("n_tasks", "rows_per_group", "tile_pixels", "device_bytes", "scratch_bytes", "n_fit")},
         "setup_s": setup_s,
+        "setup_split": {"host_threads": nworkers, "generate_synthetic_thread_s": setup_split[0], "plan_create_thread_s": setup_split[1],
+                        "plan_create_ms_per_chunk": 1e3 * setup_split[1] / max(len(plans), 1)},
         "loss_chunk0": losses[0],
     }
     out["strong_scaling"] = strong
+    # ---- the optimiser on the resident chunks: jb_lbfgs, all chunks in one optimiser -----------------
+    out["lbfgs"] = None
+    if rank == 0 and world == 1 and not args.no_extra_legs and not args.float32:
+        out["lbfgs"] = lbfgs_leg(args, plans, models, main)
     # ---- BASELINE.json configs[4]: one chunk, epochs sharded over the ranks, NCCL all-reduce ---------
     out["epoch_sharded"] = None
     if not args.no_extra_legs and not args.float32:
@@ -525,6 +537,56 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def lbfgs_leg(args, plans, models, stream, maxiter=10):
+    """Model.optimize for every resident chunk at once (jabble/model.py:195-238; the Pool over orders of
+    notebooks/02-51peg.py:66-78), through the library's device optimiser (jb_lbfgs): templates in fit
+    mode, a fixed number of L-BFGS-B iterations.  One round = one batched evaluation of all chunks + one
+    launch of the optimiser's kernel (a block per chunk) + one 4-byte-per-chunk readback; reported next to
+    the batched evaluation alone, timed with the same fit state."""
+    import torch
+    from wobble_jax_b200 import engine
+
+    x0s = []
+    for plan, model in zip(plans, models):
+        model.fix(); model.fit(0, 1); model.fit(1, 1)
+        plan.set_fit(engine.TreeSpec(model).fit_index())
+        x0s.append(np.asarray(model.get_parameters(), dtype=np.float64).copy())
+    n = len(plans)
+    # the batched evaluation alone, in this fit state
+    d_p = [torch.from_numpy(x).cuda() for x in x0s]
+    d_out = [torch.empty(len(x) + 1, dtype=torch.float64, device="cuda") for x in x0s]
+    batch = engine.Batch(plans)
+    batch.bind([t.data_ptr() for t in d_p], [t.data_ptr() for t in d_out])
+    for _ in range(3):
+        batch.eval_device(stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        batch.eval_device(stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    eval_ms = e0.elapsed_time(e1) / reps
+    batch.close()
+    runs = []
+    for it in range(2):
+        t0 = time.perf_counter()
+        res, info = engine.lbfgs_run(plans, x0s, {"maxiter": maxiter})
+        dt = time.perf_counter() - t0
+        calls = sum(d["funcalls"] for _, _, d in res)
+        runs.append({"wall_s": dt, "create_s": info["create_s"], "run_s": info["run_s"], "destroy_s": info["destroy_s"],
+                     "rounds": info["rounds"], "funcalls_total": calls, "ms_per_round": dt * 1e3 / info["rounds"],
+                     "value": args.epochs * args.pixels * calls / dt / 1e9})
+    best = min(runs, key=lambda r: r["wall_s"])
+    f0 = [float(o[0]) for o in d_out]
+    return {"workload": f"{n} chunks of {args.epochs} x {args.pixels} in ONE optimiser, templates in fit mode "
+                        f"({len(x0s[0])} parameters per chunk), maxiter {maxiter}, scipy's default m / factr / pgtol",
+            "unit": UNIT + " of evaluations performed", "runs": runs, "batched_eval_ms": eval_ms,
+            "round_over_eval": best["ms_per_round"] / eval_ms,
+            "loss_drop_chunk0": [f0[0], float(res[0][1])], "nit": [int(d["nit"]) for _, _, d in res][:4]}
+
+
 def api_leg(args, local_rank):
     """The reference-facing Python API, timed: Model.optimize on one chunk (what a notebook calls per
     order, jabble/model.py:195-238) and model.optimize_many on several (the Pool over orders,
@@ -559,7 +621,20 @@ def api_leg(args, local_rank):
                     "ms_per_eval": dt * 1e3 / d["funcalls"], "ms_per_iteration": dt * 1e3 / max(d["nit"], 1),
                     "value": px * d["funcalls"] / dt / 1e9})
     out["optimize"] = {"workload": f"1 chunk of {args.epochs} x {args.pixels}, templates in fit mode ({len(x)} parameters), maxiter 20",
+                       "optimizer": "jb_lbfgs (device)",
                        "unit": UNIT + " of evaluations performed", "first_call": res[0], "second_call_block_resident": res[1]}
+    # the same call with scipy's L-BFGS-B on the host (one callback, one H2D and one D2H per evaluation)
+    jabble.model.OPTIMIZER = "scipy"
+    try:
+        m = copy.deepcopy(model)
+        t0 = time.perf_counter()
+        x, f, d = m.optimize(loss, data, options={"maxiter": 20})
+        dt = time.perf_counter() - t0
+    finally:
+        jabble.model.OPTIMIZER = "device"
+    out["optimize"]["scipy_host_optimizer_block_resident"] = {
+        "wall_s": dt, "funcalls": int(d["funcalls"]), "nit": int(d["nit"]), "ms_per_eval": dt * 1e3 / d["funcalls"],
+        "value": px * d["funcalls"] / dt / 1e9}
     engine.clear_plan_cache()
     n = 8
     pairs = [chunk(c) for c in range(n)]
@@ -575,7 +650,21 @@ def api_leg(args, local_rank):
         many.append({"wall_s": dt, "funcalls_total": calls, "lockstep_rounds": rounds, "ms_per_round": dt * 1e3 / rounds,
                      "value": px * calls / dt / 1e9})
     out["optimize_many"] = {"workload": f"{n} chunks of {args.epochs} x {args.pixels} at once, templates in fit mode, maxiter 10",
+                            "optimizer": "jb_lbfgs (device)",
                             "unit": UNIT + " of evaluations performed", "first_call": many[0], "second_call_blocks_resident": many[1]}
+    jabble.model.OPTIMIZER = "scipy"
+    try:
+        models = [copy.deepcopy(m) for _, m in pairs]
+        t0 = time.perf_counter()
+        outs = jabble.model.optimize_many(models, loss, [dt_ for dt_, _ in pairs], options={"maxiter": 10})
+        dt = time.perf_counter() - t0
+    finally:
+        jabble.model.OPTIMIZER = "device"
+    calls = sum(int(o[2]["funcalls"]) for o in outs)
+    rounds = max(int(o[2]["funcalls"]) for o in outs)
+    out["optimize_many"]["scipy_host_optimizers_blocks_resident"] = {
+        "wall_s": dt, "funcalls_total": calls, "lockstep_rounds": rounds, "ms_per_round": dt * 1e3 / rounds,
+        "value": px * calls / dt / 1e9}
     engine.clear_plan_cache()
     return out
 

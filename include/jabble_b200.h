@@ -138,6 +138,10 @@ typedef struct {
 const char *jb_last_error(void);
 int jb_abi_version(void);
 int jb_device_count(void);   /* 0 when no CUDA device/driver is present */
+/* Host helper of the data-format side (jabble/dataset.py:118-160, Data.blockify): out[i] = 64-bit
+ * position-sensitive checksum of the nbytes[i] bytes at ptrs[i], for n host buffers (OpenMP over buffers).
+ * The host side reuses a resident block only while every frame array is the same object with the same checksum. */
+int jb_host_checksum(const void *const *ptrs, const int64_t *nbytes, int64_t n, uint64_t *out);
 
 int jb_plan_create(const jb_plan_desc *desc, jb_plan **out);
 void jb_plan_destroy(jb_plan *plan);

@@ -153,6 +153,31 @@ def test_trial_points_off_the_knot_grid_and_a_bad_start():
         engine.minimize_lbfgs([obj], [bad], {"maxiter": 5})
 
 
+def test_column_walk_plans_with_the_rvs_in_fit_mode():
+    """1600 epochs: the plan runs k_strip, whose row order and column layout belong to the shifts the plan
+    was built with.  With the RVs in fit mode the optimiser moves them (the first trial steps by whole
+    wavelengths); a knot-window overflow is settled inside the optimiser's round (rows re-sorted, the
+    chunk repeats the evaluation) and the fit proceeds as scipy's does on the same objective."""
+    ch = synth.make_chunk(chunk=3, n_epochs=1600, n_pix=330, p_val=3, n_lines=8)
+    model, obj, x0 = _objective(ch, ALL)
+    assert obj.plan.info()["fused_variant"] & 128
+    rng = np.random.default_rng(11)
+    x0 = x0.copy()
+    x0[:1600] += rng.normal(0.0, 2e-7, 1600)          # RVs off by ~60 m/s: something to fit
+    xs, fs, ds = _scipy(obj, x0, maxiter=6)
+    xd, fd, dd = engine.minimize_lbfgs([obj], [x0], {"maxiter": 6})[0]
+    assert dd["nit"] == ds["nit"] and dd["funcalls"] == ds["funcalls"]
+    assert abs(fd - fs) <= 1e-8 * abs(fs)
+    f_check, g_check = obj.value_and_gradient(xd)
+    assert abs(f_check - fd) <= 1e-11 * abs(fd)
+    # shifts that drift by knots between the rounds of one run
+    x1 = xd.copy()
+    x1[:1600] += rng.uniform(-3, 3, 1600) * (ch.grid[1] - ch.grid[0])
+    xs, fs, ds = _scipy(obj, x1, maxiter=4)
+    xd, fd, dd = engine.minimize_lbfgs([obj], [x1], {"maxiter": 4})[0]
+    assert dd["funcalls"] == ds["funcalls"] and abs(fd - fs) <= 1e-8 * abs(fs)
+
+
 def test_many_chunks_in_one_optimiser():
     """Chunks of different sizes that stop at different rounds: each gets exactly what it gets alone
     (the batched kernels are bit-identical to the per-plan ones, the optimiser state is per chunk)."""

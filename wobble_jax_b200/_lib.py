@@ -113,6 +113,7 @@ SYMBOLS = [
     ("jb_group_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("jb_group_launches", C.c_int64, [C.c_void_p]),
     ("jb_double_peak", C.c_int, [C.c_int32, c_f64p]),
+    ("jb_host_checksum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("jb_lbfgs_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(LbfgsOptions), C.POINTER(C.c_void_p)]),
     ("jb_lbfgs_destroy", None, [C.c_void_p]),
     ("jb_lbfgs_add_reg", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, c_i64p, C.c_int64]),

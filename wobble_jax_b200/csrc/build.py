@@ -35,10 +35,15 @@ def build(force=False, verbose=False):
     digest = source_hash()
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == digest:
         return OUT
-    cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT,
+    # built beside the target and moved into place: a reader (a snapshot of the tree, another process
+    # loading the library) never sees a half-written file
+    tmp = os.path.join(ROOT, "build", f"libjabble_b200.{os.getpid()}.so")
+    os.makedirs(os.path.dirname(tmp), exist_ok=True)
+    cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", tmp,
            *[os.path.join(HERE, s) for s in SOURCES]]
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     with open(stamp, "w") as f:
         f.write(digest)
     return OUT

@@ -29,7 +29,7 @@ namespace jb {
 constexpr int kLbfgsMaxM = 32;
 constexpr int kLbfgsThreads = 512;       // 128 registers per thread: the scalar state of the search lives in registers
 
-enum { kLbFirst = 0, kLbSearch = 1, kLbDone = 2 };
+enum { kLbFirst = 0, kLbSearch = 1, kLbDone = 2, kLbRepeat = 3 };
 // scipy/optimize/_lbfgsb_py.py: status_messages / task_messages
 enum { kLbTaskConvergence = 4, kLbTaskStop = 5, kLbTaskError = 7, kLbTaskAbnormal = 8 };
 enum { kLbMsgNone = 0, kLbMsgPgtol = 401, kLbMsgFactr = 402, kLbMsgMaxfun = 502, kLbMsgMaxiter = 504, kLbMsgOutOfRange = 799 };
@@ -195,15 +195,22 @@ __device__ inline bool lb_dcsrch(LbfgsState& s, double f, double g) {
 }
 
 // One block per chunk that is still iterating (active[blockIdx.x] names it).
+// status[b]: status words of the plan evaluated for block b (jb_plan: bit kStatOutOfRange = its loss is
+// NaN, handled below; any other bit = the evaluation is not valid -- knot window overflow: the host
+// re-sorts the plan's rows and the chunk repeats the evaluation next round).
 __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProblem* __restrict__ probs, const int* __restrict__ active,
-                                                                 LbfgsOpts o, int* __restrict__ flags) {
+                                                                 LbfgsOpts o, int* __restrict__ flags, int* const* __restrict__ status) {
     __shared__ LbfgsRed red;
     __shared__ double alpha[kLbfgsMaxM], rho[kLbfgsMaxM];
     const int pid = active[blockIdx.x];
     const LbfgsProblem P = probs[pid];
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (status[blockIdx.x][0] & ~kStatOutOfRange) {
+        if (tid == 0) flags[pid] = kLbRepeat;
+        return;
+    }
     LbfgsState s = *P.st;                  // every thread carries the (identical) scalar state; thread 0 stores it
     if (s.phase == kLbDone) return;
-    const int tid = threadIdx.x, T = blockDim.x;
     if (tid < o.m) rho[tid] = P.rho[tid];
     __syncthreads();
     const long long n = P.n;
@@ -444,18 +451,21 @@ int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* op
     h->regs.resize(n);
     int rc;
     if ((rc = lb_alloc(h.get(), &h->d_states, (size_t)n))) return rc;
+    // one allocation for every vector of every chunk:  x | out (1 + n) | xold | gold | d | z | S (m n) | Y (m n) | rho
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (size_t)plans[i]->n_fit * (6 + 2 * (size_t)opt->m) + 2 + jb::kLbfgsMaxM;
+    double* base = nullptr;
+    if ((rc = lb_alloc(h.get(), &base, total))) return rc;
     for (int i = 0; i < n; ++i) {
         jb::LbfgsProblem& P = h->probs[i];
         memset(&P, 0, sizeof P);
         P.n = plans[i]->n_fit;
         const size_t nn = (size_t)P.n;
-        double* base = nullptr;
-        // x | out (1 + n) | xold | gold | d | z | S (m n) | Y (m n)
-        if ((rc = lb_alloc(h.get(), &base, nn * (6 + 2 * (size_t)opt->m) + 2))) return rc;
         P.x = base; P.out = base + nn; P.xold = P.out + nn + 1; P.gold = P.xold + nn; P.d = P.gold + nn; P.z = P.d + nn;
         P.S = P.z + nn; P.Y = P.S + nn * opt->m;
+        P.rho = P.Y + nn * opt->m;
         P.st = h->d_states + i;
-        if ((rc = lb_alloc(h.get(), &P.rho, (size_t)jb::kLbfgsMaxM))) return rc;
+        base = P.rho + jb::kLbfgsMaxM + 1;
     }
     if ((rc = lb_alloc(h.get(), &h->d_probs, (size_t)n))) return rc;
     if ((rc = lb_alloc(h.get(), &h->d_flags, (size_t)n))) return rc;
@@ -538,6 +548,7 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
     jb_batch* batch = nullptr;
     auto drop_batch = [&]() { if (batch) { jb_batch_destroy(batch); batch = nullptr; } };
     rc = JB_OK;
+    std::vector<int> repeats((size_t)n, 0);
     while (!active.empty()) {
         if (!batch) {
             std::vector<jb_plan*> pl; std::vector<const double*> px; std::vector<double*> po;
@@ -545,17 +556,38 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
             if ((rc = jb_batch_create(pl.data(), (int)pl.size(), &batch))) break;
             if ((rc = jb_batch_bind(batch, px.data(), po.data()))) break;
             jb_batch_soft_range(batch, 1);
+            if ((rc = batch_status_buffers(batch))) break;
             if (cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(JB_ERR_CUDA, "cudaMemcpyAsync failed"); break; }
             h->batches_built++;
         }
-        if ((rc = jb_batch_eval_device_checked(batch, st))) break;
-        jb::k_lbfgs_advance<<<(unsigned)active.size(), jb::kLbfgsThreads, 0, st>>>(h->d_probs, h->d_active, h->opt, h->d_flags);
-        if (cudaMemcpyAsync(h->h_flags, h->d_flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        // one round, one wait: the evaluation, the optimiser's step, the status words and the flags
+        const size_t na = active.size();
+        if ((rc = jb_batch_eval_device(batch, st))) break;
+        jb::k_lbfgs_advance<<<(unsigned)na, jb::kLbfgsThreads, 0, st>>>(h->d_probs, h->d_active, h->opt, h->d_flags, batch->d_stat_ptrs);
+        jb::k_gather_status<<<(unsigned)((na + 127) / 128), 128, 0, st>>>(batch->d_stat_ptrs, (int)na, batch->d_stat_flat);
+        if (cudaMemcpyAsync(batch->h_stat_flat, batch->d_stat_flat, 2 * na * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h->h_flags, h->d_flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             rc = fail(JB_ERR_CUDA, "L-BFGS round failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        h->rounds++; h->launches += 1;
+        h->rounds++; h->launches += 2;
+        // plans that raised a status word: an off-grid trial point is the optimiser's business (its loss is
+        // NaN); a knot-window overflow is settled here (rows re-sorted with the current shifts, or the plan
+        // leaves k_strip) and the chunk, which did not advance, evaluates the same point again
+        for (size_t k = 0; k < na && !rc; ++k) {
+            if (!batch->h_stat_flat[2 * k] && !batch->h_stat_flat[2 * k + 1]) continue;
+            jb_plan* pl = h->plans[active[k]];
+            bool window = false;
+            const int rs = read_status(pl, st, &window);
+            if (rs == JB_OK || rs == JB_ERR_OUT_OF_RANGE) continue;
+            if (!window || repeats[active[k]] >= 14) { rc = rs; break; }
+            const std::string msg = g_err;
+            bool retry = false;
+            if ((rc = window_retry(pl, repeats[active[k]]++, &retry))) break;
+            if (!retry) { g_err = msg; rc = rs; break; }
+        }
+        if (rc) break;
         std::vector<int> next;
         for (int i : active) if (h->h_flags[i] != jb::kLbDone) next.push_back(i);
         if (next.size() != active.size()) { active.swap(next); drop_batch(); }

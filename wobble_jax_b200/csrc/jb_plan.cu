@@ -898,6 +898,29 @@ int jb_device_count(void) {
     return n;
 }
 
+// 64-bit position-sensitive checksums of n host buffers (OpenMP over the buffers): what
+// Data.blockify compares to notice an in-place edit of a frame before it reuses the resident block.
+int jb_host_checksum(const void* const* ptrs, const int64_t* nbytes, int64_t n, uint64_t* out) {
+    if (n < 0 || (n && (!ptrs || !nbytes || !out))) return fail(JB_ERR_BAD_ARG, "null argument");
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        const unsigned char* p = static_cast<const unsigned char*>(ptrs[i]);
+        const int64_t nb = nbytes[i] > 0 ? nbytes[i] : 0, nw = nb / 8;
+        uint64_t s1 = 0x9E3779B97F4A7C15ull, s2 = 0;
+        for (int64_t k = 0; k < nw; ++k) {
+            uint64_t w;
+            memcpy(&w, p + 8 * k, 8);
+            s1 += w;
+            s2 += w * (uint64_t)(2 * k + 1);
+        }
+        uint64_t tail = 0;
+        if (nb > 8 * nw) memcpy(&tail, p + 8 * nw, (size_t)(nb - 8 * nw));
+        s1 += tail; s2 += tail * (uint64_t)(2 * nw + 1);
+        out[i] = s1 ^ (s2 * 0xff51afd7ed558ccdull) ^ (uint64_t)nb;
+    }
+    return JB_OK;
+}
+
 void jb_plan_destroy(jb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);

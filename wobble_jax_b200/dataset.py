@@ -175,11 +175,30 @@ class Data:
         return out
 
     def _fingerprint(self):
-        parts = []
-        for f in self.dataframes:
-            for a in (f.xs, f.ys, f.yivar, f.mask):
-                arr = np.asarray(a)
-                parts.append((id(a), arr.shape, float(np.sum(arr, dtype=np.float64)) if arr.size else 0.0))
+        """Identity of every frame array + a checksum of its bytes.  The pointer table of the arrays is
+        kept while the array OBJECTS stay the same (then only the checksums are recomputed: one library
+        call, OpenMP over the arrays -- jb_host_checksum, include/jabble_b200.h)."""
+        import ctypes
+        from . import _lib
+        arrays = [a for f in self.dataframes for a in (f.xs, f.ys, f.yivar, f.mask)]
+        cache = getattr(self, "_fp_cache", None)
+        if cache is None or len(cache[0]) != len(arrays) or any(a is not b for a, b in zip(arrays, cache[0])):
+            keep, ptrs, nbytes, shapes = [], [], [], []
+            for a in arrays:
+                arr = a if isinstance(a, np.ndarray) and a.flags.c_contiguous else np.ascontiguousarray(a)
+                keep.append(arr)
+                ptrs.append(arr.ctypes.data if arr.size else 0)
+                nbytes.append(arr.nbytes)
+                shapes.append((id(a), arr.shape, arr.dtype.str))
+            direct = all(k is a for k, a in zip(keep, arrays))       # every frame array is a contiguous ndarray
+            cache = (arrays, np.asarray(ptrs, dtype=np.uint64), np.asarray(nbytes, dtype=np.int64), tuple(shapes), direct)
+            self._fp_cache = cache if direct else None               # copies were made: their pointers describe this call only
+        _, ptrs, nbytes, shapes, _ = cache
+        sums = np.empty(len(arrays), dtype=np.uint64)
+        if len(arrays):
+            _lib.check(_lib.load().jb_host_checksum(ctypes.c_void_p(ptrs.ctypes.data), ctypes.c_void_p(nbytes.ctypes.data),
+                                                    len(arrays), ctypes.c_void_p(sums.ctypes.data)))
+        parts = [shapes, sums.tobytes()]
         for key in sorted(self.metadata):
             arr = np.asarray(self.metadata[key])
             parts.append((key, id(self.metadata[key]), arr.shape, arr.tobytes() if arr.size <= 4096 else hash(arr.tobytes())))

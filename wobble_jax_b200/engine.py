@@ -681,11 +681,12 @@ def lbfgs_options_supported(options):
     return 1 <= int(options.get("m", 10)) <= 32 and int(options.get("maxls", 20)) > 0
 
 
-def minimize_lbfgs(objectives, x0s, options=None):
-    """``scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)`` for every
-    objective at once, on the device (``jb_lbfgs``, include/jabble_b200.h): one batched evaluation per
-    round for all chunks still iterating, optimiser state and vectors in HBM.  Returns scipy's
-    ``(x, f, d)`` per objective, ``d`` = {grad, task, funcalls, nit, warnflag}."""
+def lbfgs_run(plans, x0s, options=None, regs=None):
+    """``jb_lbfgs`` on plans whose fit state and fixed parameters are set: L-BFGS-B from ``x0s[i]`` for
+    every plan at once.  ``regs[i]``: list of (kind, weight, constant, indices) parameter-only terms
+    (kind 0: weight * 0.5 * sum (x[indices] - constant)^2, 1: weight * sum |x[indices] - constant|).
+    Returns ([(x, f, d)], info): scipy's ``fmin_l_bfgs_b`` triple per plan, and {rounds, results} with
+    the number of batched evaluations and the raw ``jb_lbfgs_result`` fields."""
     options = dict(options or {})
     if not lbfgs_options_supported(options):
         raise NotImplementedError(f"options {sorted(options)} need scipy's optimiser")
@@ -694,44 +695,67 @@ def minimize_lbfgs(objectives, x0s, options=None):
     for k, v in _LBFGS_DEFAULTS.items():
         val = options.get(k, v)
         setattr(opt, k, float(val) if k in ("factr", "pgtol") else int(val))
-    n = len(objectives)
+    n = len(plans)
+    handle = C.c_void_p()
+    arr = (C.c_void_p * n)(*[p.handle for p in plans])
+    import time
+    t_create = time.perf_counter()
+    _lib.check(lib.jb_lbfgs_create(arr, n, C.byref(opt), C.byref(handle)))
+    t_create = time.perf_counter() - t_create
+    t_run = 0.0
+    try:
+        for i, terms in enumerate(regs or []):
+            for kind, weight, constant, indices in terms:
+                idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64).reshape(-1))
+                _lib.check(lib.jb_lbfgs_add_reg(handle, i, int(kind), float(weight), float(constant),
+                                                idx.ctypes.data_as(_lib.c_i64p), idx.size))
+        x0 = [np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)) for x in x0s]
+        for p, x in zip(plans, x0):
+            if x.size != p.n_fit:
+                raise ValueError(f"x0 has {x.size} entries, the model has {p.n_fit} parameters in fit mode")
+        xs = [np.empty_like(x) for x in x0]
+        gs = [np.empty_like(x) for x in x0]
+        res = (_lib.LbfgsResult * n)()
+        as_ptrs = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        t_run = time.perf_counter()
+        _lib.check(lib.jb_lbfgs_run(handle, as_ptrs(x0), as_ptrs(xs), as_ptrs(gs), res))
+        t_run = time.perf_counter() - t_run
+        rounds = int(lib.jb_lbfgs_rounds(handle))
+    finally:
+        t_destroy = time.perf_counter()
+        lib.jb_lbfgs_destroy(handle)
+        t_destroy = time.perf_counter() - t_destroy
+    out, raw = [], []
+    for x, g, r in zip(xs, gs, res):
+        d = {"grad": g, "task": _LBFGS_STATUS.get(int(r.task), "?") + ": " + _LBFGS_TASK.get(int(r.task_msg), ""),
+             "funcalls": int(r.funcalls), "nit": int(r.nit), "warnflag": int(r.warnflag)}
+        out.append((x, float(r.f), d))
+        raw.append({k: getattr(r, k) for k, _ in _lib.LbfgsResult._fields_})
+    return out, {"rounds": rounds, "results": raw, "create_s": t_create, "run_s": t_run, "destroy_s": t_destroy}
+
+
+def minimize_lbfgs(objectives, x0s, options=None):
+    """``scipy.optimize.fmin_l_bfgs_b(func=objective.value_and_gradient, x0=x0, **options)`` for every
+    objective at once, on the device (``jb_lbfgs``, include/jabble_b200.h): one batched evaluation per
+    round for all chunks still iterating, optimiser state and vectors in HBM.  Returns scipy's
+    ``(x, f, d)`` per objective, ``d`` = {grad, task, funcalls, nit, warnflag}."""
+    from . import loss as L
     for o in objectives:          # the plan carries this objective's fixed parameters and fit state
         if o.plan._owner is not o:
             o.plan.set_params(o._params_all)
             o.plan.set_fit(o._fit_index)
             o.plan._owner = o
-    handle = C.c_void_p()
-    plans = (C.c_void_p * n)(*[o.plan.handle for o in objectives])
-    _lib.check(lib.jb_lbfgs_create(plans, n, C.byref(opt), C.byref(handle)))
-    try:
-        for i, o in enumerate(objectives):
-            from . import loss as L
-            for r in o.regs:
-                idx = np.ascontiguousarray(np.asarray(r.indices, dtype=np.int64).reshape(-1))
-                _lib.check(lib.jb_lbfgs_add_reg(handle, i, 1 if isinstance(r, L.L1Reg) else 0, float(o.n_rows) * float(r.coefficient),
-                                                float(r.constant), idx.ctypes.data_as(_lib.c_i64p), idx.size))
-        x0 = [np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)) for x in x0s]
-        for o, x in zip(objectives, x0):
-            if x.size != o.plan.n_fit:
-                raise ValueError(f"x0 has {x.size} entries, the model has {o.plan.n_fit} parameters in fit mode")
-        xs = [np.empty_like(x) for x in x0]
-        gs = [np.empty_like(x) for x in x0]
-        res = (_lib.LbfgsResult * n)()
-        as_ptrs = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
-        _lib.check(lib.jb_lbfgs_run(handle, as_ptrs(x0), as_ptrs(xs), as_ptrs(gs), res))
-        rounds = int(lib.jb_lbfgs_rounds(handle))
-    finally:
-        lib.jb_lbfgs_destroy(handle)
-    out = []
-    for o, x, g, r in zip(objectives, xs, gs, res):
-        o.n_evals += int(r.funcalls)
-        o.n_out_of_range += int(r.n_out_of_range)
-        o.lbfgs_rounds = rounds
-        if r.task == 7:
+    # the reference's loss_all evaluates a regulariser inside the vmap over rows (loss.py:61-74): its
+    # value and gradient count once per row of the block
+    regs = [[(1 if isinstance(r, L.L1Reg) else 0, float(o.n_rows) * float(r.coefficient), float(r.constant), r.indices)
+             for r in o.regs] for o in objectives]
+    out, info = lbfgs_run([o.plan for o in objectives], x0s, options, regs)
+    for o, r in zip(objectives, info["results"]):
+        o.n_evals += int(r["funcalls"])
+        o.n_out_of_range += int(r["n_out_of_range"])
+        o.lbfgs_rounds = info["rounds"]
+        if r["task"] == 7:
             raise ValueError("an unmasked warped pixel lies outside the knot grid of a spline component (at the starting point)")
-        d = {"grad": g, "task": _LBFGS_STATUS.get(int(r.task), "?") + ": " + _LBFGS_TASK.get(int(r.task_msg), ""),
-             "funcalls": int(r.funcalls), "nit": int(r.nit), "warnflag": int(r.warnflag)}
-        out.append((x, float(r.f), d))
     return out
 
 
