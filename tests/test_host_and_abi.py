@@ -102,6 +102,45 @@ def test_blockify_padding_and_keys():
     assert len(db) == 3 and db.ele(1)["xs"].shape == (5,)
 
 
+def test_blockify_keeps_the_block_until_a_frame_changes():
+    """Data.blockify hands back the same block objects while the frames are unchanged (the resident copy in
+    HBM is keyed on them) and notices every in-place edit: jb_host_checksum (position-sensitive, so a swap of
+    two pixels counts) over the arrays, plus the identity of the array objects."""
+    rng = np.random.default_rng(3)
+    frames = [jabble.dataset.DataFrame(np.sort(rng.normal(size=n)), rng.normal(size=n), np.ones(n), np.zeros(n, dtype=bool))
+              for n in (50, 64, 57)]
+    data = jabble.dataset.Data(frames)
+    a = data.blockify()
+    b = data.blockify()
+    assert a[0] is b[0] and a[1] is b[1]
+    data[1].mask[7] = True                                  # one bit
+    c = data.blockify()
+    assert c[0] is not a[0] and c[0]["mask"][1, 7]
+    data[2].ys[[3, 4]] = data[2].ys[[4, 3]]                 # a swap: same sum, different order
+    d = data.blockify()
+    assert d[0] is not c[0] and d[0]["ys"][2, 3] == data[2].ys[3]
+    data[0].yivar = data[0].yivar.copy()                    # a new array object with equal contents
+    e = data.blockify()
+    assert e[0] is not d[0] and np.array_equal(e[0]["yivar"], d[0]["yivar"])
+    data[0].xs = list(data[0].xs)                           # not an ndarray: checksummed through a copy
+    f = data.blockify()
+    assert np.array_equal(f[0]["xs"], e[0]["xs"])
+    assert data.blockify()[0] is not None
+
+
+def test_which_fmin_l_bfgs_b_options_the_device_optimiser_takes():
+    """Model.optimize hands its ``options`` to scipy.optimize.fmin_l_bfgs_b (jabble/model.py:226-232); the
+    device optimiser takes scipy's numeric options, everything else (bounds, callback, numerical
+    gradients) stays with scipy."""
+    from wobble_jax_b200 import engine
+    ok = engine.lbfgs_options_supported
+    assert ok({}) and ok({"maxiter": 64}) and ok({"m": 5, "factr": 10.0, "pgtol": 1e-8, "maxfun": 100, "maxls": 30})
+    assert ok({"bounds": None, "callback": None, "approx_grad": 0, "args": ()})
+    assert not ok({"bounds": [(0, 1)]}) and not ok({"callback": print}) and not ok({"approx_grad": True})
+    assert not ok({"m": 0}) and not ok({"m": 33}) and not ok({"maxls": 0}) and not ok({"iprint": 1})
+    assert jabble.model.OPTIMIZER == "device"
+
+
 def test_save_load_round_trip(tmp_path):
     """jabble.model.save / load and Data.save / load (model.py:35-71, dataset.py:239-277): the tree,
     every leaf's parameters, the metadata and the group / dataset names of the reference's HDF5 layout

@@ -195,9 +195,9 @@ __device__ inline bool lb_dcsrch(LbfgsState& s, double f, double g) {
 }
 
 // One block per chunk that is still iterating (active[blockIdx.x] names it).
-// status[b]: status words of the plan evaluated for block b (jb_plan: bit kStatOutOfRange = its loss is
-// NaN, handled below; any other bit = the evaluation is not valid -- knot window overflow: the host
-// re-sorts the plan's rows and the chunk repeats the evaluation next round).
+// status[b]: status words of the plan evaluated for block b (jb_plan: bit kStatOutOfRange = the point is
+// off a knot grid, its loss is NaN, handled below; otherwise any bit = the evaluation is not valid --
+// knot window overflow: the host re-sorts the plan's rows and the chunk repeats the evaluation next round).
 __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProblem* __restrict__ probs, const int* __restrict__ active,
                                                                  LbfgsOpts o, int* __restrict__ flags, int* const* __restrict__ status) {
     __shared__ LbfgsRed red;
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
     const int pid = active[blockIdx.x];
     const LbfgsProblem P = probs[pid];
     const int tid = threadIdx.x, T = blockDim.x;
-    if (status[blockIdx.x][0] & ~kStatOutOfRange) {
+    const int bits = status[blockIdx.x][0];
+    if (bits && !(bits & kStatOutOfRange)) {       // (off the grid wins, as in read_status: the point is refused, not repeated)
         if (tid == 0) flags[pid] = kLbRepeat;
         return;
     }
@@ -576,11 +577,18 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
         // NaN); a knot-window overflow is settled here (rows re-sorted with the current shifts, or the plan
         // leaves k_strip) and the chunk, which did not advance, evaluates the same point again
         for (size_t k = 0; k < na && !rc; ++k) {
-            if (!batch->h_stat_flat[2 * k] && !batch->h_stat_flat[2 * k + 1]) continue;
+            const bool repeat = h->h_flags[active[k]] == jb::kLbRepeat;
+            if (!batch->h_stat_flat[2 * k] && !batch->h_stat_flat[2 * k + 1]) {
+                if (repeat) rc = fail(JB_ERR_CUDA, "chunk %d: evaluation refused without a status word", active[k]);
+                continue;
+            }
             jb_plan* pl = h->plans[active[k]];
             bool window = false;
             const int rs = read_status(pl, st, &window);
-            if (rs == JB_OK || rs == JB_ERR_OUT_OF_RANGE) continue;
+            if (rs == JB_OK || rs == JB_ERR_OUT_OF_RANGE) {
+                if (repeat) rc = fail(JB_ERR_CUDA, "chunk %d: evaluation refused with status %d", active[k], batch->h_stat_flat[2 * k]);
+                continue;
+            }
             if (!window || repeats[active[k]] >= 14) { rc = rs; break; }
             const std::string msg = g_err;
             bool retry = false;

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <numeric>
 #include <string>
@@ -29,6 +30,15 @@
 namespace {
 
 thread_local std::string g_err;
+
+// JB_TIMING=1: phases of plan creation on stderr (milliseconds)
+struct PhaseTimer {
+    bool on; double t0; const char* what;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit PhaseTimer(const char* w) : on(getenv("JB_TIMING") != nullptr), t0(on ? now() : 0.0), what(w) {}
+    void lap(const char* next) { if (on) { const double t = now(); fprintf(stderr, "[jb timing] %-28s %8.2f ms\n", what, t - t0); t0 = t; what = next; } }
+    ~PhaseTimer() { lap(""); }
+};
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -189,6 +199,32 @@ int dev_alloc(jb_plan* pl, T** out, size_t count, bool scratch = false) {
     pl->device_bytes += (int64_t)b.bytes;
     if (scratch) pl->scratch_bytes += (int64_t)b.bytes;
     *out = static_cast<T*>(b.p);
+    return JB_OK;
+}
+
+// uninitialised host memory for the canonical copy of a block (hundreds of MB: the loop that fills it
+// writes every element, in parallel -- no single-threaded zero fill, pages first touched by their writer)
+template <typename T>
+struct HostBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit HostBuf(size_t n_) : p(static_cast<T*>(malloc(std::max<size_t>(n_ * sizeof(T), 16)))), n(n_) {}
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { free(p); }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
+template <typename T>
+int dev_upload(jb_plan* pl, T** out, const HostBuf<T>& h) {
+    int rc = dev_alloc(pl, out, h.size());
+    if (rc) return rc;
+    if (!h.empty()) JB_CUDA(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return JB_OK;
 }
 
@@ -428,6 +464,7 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
 // Sort rows by (smallest unmasked x) - (shift of the first component that has one), so that the
 // rows of a group land on nearly the same knots and the on-chip window stays small.
 int resort_rows(jb_plan* pl) {
+    PhaseTimer phase_all("resort: sort, tile info");
     std::vector<double> key(pl->E);
     const jb_component_desc* sc = nullptr;
     for (int c = 0; c < pl->n_comp; ++c)
@@ -456,6 +493,7 @@ int resort_rows(jb_plan* pl) {
     pl->sort_dirty = false;
     pl->sorted_params = pl->h_params;
     if (pl->params_set) {
+        PhaseTimer phase("resort: strip layout");
         int rc = strip_build(pl, perm);
         if (rc) return rc;
     }
@@ -1008,10 +1046,12 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     // leading ones), so it is evaluated on knots the data already touch and contributes exactly
     // zero -- ChiSquare's where(~mask, ., 0), loss.py:168-173, for value and cotangent.
     const int NT = pl->n_tiles;
-    std::vector<double> hdata((size_t)E * NT * jb::kTileDoubles, 0.0);
-    std::vector<double> hx((size_t)E * ppad, 0.0);    // original x, canonical orientation
-    std::vector<double> hxf((size_t)E * ppad, 0.0);   // filled x (what the fused kernel sees)
-    std::vector<uint8_t> hm((size_t)E * ppad, 1);     // 1 = carries no weight
+    PhaseTimer phase("create: host staging alloc");
+    HostBuf<double> hdata((size_t)E * NT * jb::kTileDoubles);
+    HostBuf<double> hx((size_t)E * ppad);     // original x, canonical orientation
+    HostBuf<double> hxf((size_t)E * ppad);    // filled x (what the fused kernel sees)
+    HostBuf<uint8_t> hm((size_t)E * ppad);    // 1 = carries no weight
+    if (!hdata.data() || !hx.data() || !hxf.data() || !hm.data()) return fail(JB_ERR_BAD_ARG, "out of host memory for the canonical block");
     pl->h_row_rev.assign(E, 0);
     pl->h_xfirst.assign(E, INFINITY);
     std::vector<double> txmin((size_t)E * NT, INFINITY), txmax((size_t)E * NT, -INFINITY);
@@ -1028,6 +1068,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     for (int64_t i = 0; i < E * P && any_x == 0.0; ++i)
         if ((!d->mask || !d->mask[i]) && std::isfinite(d->xs[i])) any_x = d->xs[i];
     // (rows are independent: the loop runs on all host cores)
+    phase.lap("create: canonical rows");
     bool norm_smooth_all = true, f2_ok_all = true;
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, bad_row = -1, bad_pix = -1;
 #pragma omp parallel for schedule(dynamic, 8) reduction(&& : norm_smooth_all, f2_ok_all) reduction(+ : tk0, tk1, tk2, tk3)
@@ -1057,7 +1098,9 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
             double* rec = hdata.data() + ((size_t)r * NT + t) * jb::kTileDoubles +
                           (pt % jb::kPixPerLane) * 32 + pt / jb::kPixPerLane;
             const bool w = p < P && weighted(src);
-            if (p < P) hx[(size_t)r * ppad + p] = std::isfinite(xr[src]) ? xr[src] : 0.0;
+            hx[(size_t)r * ppad + p] = (p < P && std::isfinite(xr[src])) ? xr[src] : 0.0;
+            hm[(size_t)r * ppad + p] = w ? 0 : 1;
+            rec[jb::kTile] = 0.0; rec[2 * jb::kTile] = 0.0;
             if (w) {
                 if (!std::isfinite(xr[src])) {
 #pragma omp critical
@@ -1066,7 +1109,6 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
                 fill = xr[src];
                 if (pl->has_data) { rec[jb::kTile] = d->ys[r * P + src]; rec[2 * jb::kTile] = d->yivar[r * P + src]; }
                 pl->h_xfirst[r] = std::min(pl->h_xfirst[r], fill);
-                hm[(size_t)r * ppad + p] = 0;
             }
             else if (p < P && std::isfinite(xr[src]) && xr[src] >= fill && xr[src] <= nextw[p] && std::isfinite(nextw[p]))
                 fill = xr[src];   // an interior masked pixel keeps its own x when it sits between its weighted neighbours
@@ -1127,6 +1169,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     pl->norm_smooth = pl->norm_smooth && norm_smooth_all;
     pl->f2_ok = pl->f2_ok && f2_ok_all;
     pl->tiles_kind[0] += tk0; pl->tiles_kind[1] += tk1; pl->tiles_kind[2] += tk2; pl->tiles_kind[3] += tk3;
+    phase.lap("create: row offsets");
     // Position of every row relative to one reference row (k_strip, jb_strip.cuh): x[r][p] - x[ref][p]
     // at the row's first weighted pixel whose reference pixel carries an x of its own.  Unlike the
     // first weighted x this does not jump by a pixel when a row's first pixel is masked.
@@ -1149,6 +1192,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     }
     int rc;
     pl->h_txmin = txmin; pl->h_txmax = txmax; pl->h_flags = dense; pl->h_live = live;
+    phase.lap("create: uploads");
     if ((rc = dev_alloc(pl, &pl->d_tinfo, (size_t)NT * E))) return rc;
     {
         char* rec = nullptr;
@@ -1193,6 +1237,7 @@ int jb_plan_create(const jb_plan_desc* d, jb_plan** out) {
     if ((rc = dev_upload(pl, &pl->d_row_perm, perm))) return rc;
 
     // ---- components ---------------------------------------------------------------------------
+    phase.lap("create: components, scratch");
     if ((rc = dev_alloc(pl, &pl->d_params, (size_t)d->n_params))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_grad_all, (size_t)d->n_params))) return rc;
     if ((rc = dev_alloc(pl, &pl->d_fisher_all, (size_t)d->n_params))) return rc;
