@@ -212,6 +212,8 @@ def run_b200(args, rank, world, local_rank):
     def make(c):
         # generated, canonicalised and uploaded on a host thread of its own (ctypes drops the GIL)
         torch.cuda.set_device(local_rank)
+        if gomp is not None:
+            gomp.omp_set_num_threads(omp_inner)
         t0 = time.perf_counter()
         ch = synth.make_chunk(rank * args.chunks + c, n_epochs=args.epochs, n_pix=args.pixels,
                               p_val=args.p_val, as_block=True)
@@ -227,7 +229,17 @@ def run_b200(args, rank, world, local_rank):
 
     plans, p_host, models = [], [], []
     setup_split = [0.0, 0.0]
-    nworkers = max(1, min(8, len(os.sched_getaffinity(0)) // max(world, 1), args.chunks))
+    # one host thread per core of this rank, each generating and uploading its chunks; the library's own
+    # OpenMP loop (row canonicalisation in jb_plan_create) is kept to one thread meanwhile, or the
+    # worker threads x OpenMP threads oversubscribe the cores
+    cores_here = max(1, len(os.sched_getaffinity(0)) // max(world, 1))
+    nworkers = max(1, min(cores_here, args.chunks))
+    try:
+        import ctypes
+        gomp = ctypes.CDLL("libgomp.so.1")          # (the ICV is per calling thread: every worker sets its own)
+    except OSError:
+        gomp = None
+    omp_inner = max(1, cores_here // nworkers)
     with ThreadPoolExecutor(nworkers) as pool:
         for plan, p, model in pool.map(make, range(args.chunks)):
             plans.append(plan)
