@@ -19,9 +19,16 @@
 // BFGS update, the two-loop recursion over the stored pairs, the next trial point) and leaves the next
 // x in place.  The host reads back one int per chunk per round (who is done) and nothing else.
 //
-// Differences from scipy that a caller can see: the direction comes from the two-loop recursion
-// instead of the compact representation (same matrix, different rounding), so iterates agree to
-// rounding for the first iterations and then drift like any two builds of the same optimiser.
+// The direction -H g comes from the compact representation of the inverse L-BFGS matrix (Byrd, Nocedal,
+// Schnabel 1994): H = gamma I + [S gamma Y] [[R^-T (D + gamma Y'Y) R^-1, -R^-T], [-R^-1, 0]] [S gamma Y]',
+// R = upper triangle of S'Y, so that a block reads the stored pairs in TWO passes of independent loads
+// (all 2 m dot products S'g, Y'g at once -- fused with the dots S'y, Y'y that extend R and Y'Y by the new
+// pair --, then the combination) instead of the 2 m dependent passes of the two-loop recursion; the m x m
+// algebra in between is one thread's work.
+//
+// Differences from scipy that a caller can see: L-BFGS-B applies the compact form of B and a subspace
+// step where this applies the compact form of H (the same matrix, different rounding), so iterates agree
+// to rounding for the first iterations and then drift like any two builds of the same optimiser.
 #include <cfloat>
 
 namespace jb {
@@ -45,7 +52,8 @@ struct LbfgsProblem {
     long long n;
     double *x, *out, *xold, *gold, *d, *z, *S, *Y;     // out = [f, g[n]] of the evaluation; S, Y: [m][n]
     LbfgsState* st;
-    double* rho;                                        // [m]: 1 / s'y of the stored pairs
+    double* sy;                                         // [m][m] by slot: sy[i][j] = s_i'y_j (used for i not newer than j), then
+                                                        // [m][m]: yy[i][j] = y_i'y_j
     const LbfgsReg* regs;
     int n_regs, pad_;
 };
@@ -201,7 +209,10 @@ __device__ inline bool lb_dcsrch(LbfgsState& s, double f, double g) {
 __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProblem* __restrict__ probs, const int* __restrict__ active,
                                                                  LbfgsOpts o, int* __restrict__ flags, int* const* __restrict__ status) {
     __shared__ LbfgsRed red;
-    __shared__ double alpha[kLbfgsMaxM], rho[kLbfgsMaxM];
+    __shared__ double sy[kLbfgsMaxM * kLbfgsMaxM], yy[kLbfgsMaxM * kLbfgsMaxM];     // by slot, row stride m
+    __shared__ double dots[4][kLbfgsMaxM];          // S'y, Y'y, S'g, Y'g by age (0 = oldest pair)
+    __shared__ double coef[2][kLbfgsMaxM];          // what multiplies S_k and gamma Y_k in H g
+    __shared__ double wred[kLbfgsThreads / 32][16];
     const int pid = active[blockIdx.x];
     const LbfgsProblem P = probs[pid];
     const int tid = threadIdx.x, T = blockDim.x;
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
     }
     LbfgsState s = *P.st;                  // every thread carries the (identical) scalar state; thread 0 stores it
     if (s.phase == kLbDone) return;
-    if (tid < o.m) rho[tid] = P.rho[tid];
+    for (int i = tid; i < o.m * o.m; i += T) { sy[i] = P.sy[i]; yy[i] = P.sy[o.m * o.m + i]; }
     __syncthreads();
     const long long n = P.n;
     int par = 0;
@@ -257,6 +268,8 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
     s.funcalls++;
 
     bool start = false;          // begin a new iteration (direction + first trial point) from (x, f, g)
+    int new_slot = -1;           // a pair was stored in this slot: its column of S'Y and Y'Y is formed with the direction
+    double new_dr = 0.0;
     if (s.phase == kLbFirst) {
         double mx = 0.0;
         for (long long i = tid; i < n; i += T) mx = fmax(mx, fabs(g[i]));
@@ -296,27 +309,28 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
             else if (s.fold - f <= o.tol * dmax) finish(kLbTaskConvergence, kLbMsgFactr, 0);
             else {
                 // BFGS pair: s = stp d, y = g - g_old (left in gold); s'y from the search's slopes
-                double rr = 0.0;
-                for (long long i = tid; i < n; i += T) { const double y = g[i] - P.gold[i]; P.gold[i] = y; rr += y * y; }
-                rr = lb_sum(rr, red, par);
                 double dr, ddum;
                 if (s.stp == 1.0) { dr = gd - s.gdold; ddum = -s.gdold; }
                 else { dr = (gd - s.gdold) * s.stp; ddum = -s.gdold * s.stp; }
-                if (dr <= DBL_EPSILON * ddum) {
-                    s.nskip++;
-                } else {
-                    int slot;
+                const bool upd = !(dr <= DBL_EPSILON * ddum);
+                int slot = 0;
+                if (upd) {
                     if (s.col < m) { slot = (s.head + s.col) % m; s.col++; }
                     else { slot = s.head; s.head = (s.head + 1) % m; }
-                    double* Ss = P.S + (long long)slot * n;
-                    double* Ys = P.Y + (long long)slot * n;
-                    const double stp = s.stp;
-                    for (long long i = tid; i < n; i += T) { Ss[i] = stp * P.d[i]; Ys[i] = P.gold[i]; }
-                    __syncthreads();
-                    if (tid == 0) { rho[slot] = 1.0 / dr; P.rho[slot] = 1.0 / dr; }
-                    __syncthreads();
-                    s.theta = rr / dr;
+                } else {
+                    s.nskip++;
                 }
+                double* Ss = P.S + (long long)slot * n;
+                double* Ys = P.Y + (long long)slot * n;
+                const double stp = s.stp;
+                double rr = 0.0;
+                for (long long i = tid; i < n; i += T) {
+                    const double y = g[i] - P.gold[i];
+                    P.gold[i] = y; rr += y * y;
+                    if (upd) { Ss[i] = stp * P.d[i]; Ys[i] = y; }
+                }
+                rr = lb_sum(rr, red, par);
+                if (upd) { s.theta = rr / dr; new_slot = slot; new_dr = dr; }
                 start = true;
             }
         }
@@ -330,42 +344,98 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
         if (col == 0) {
             for (long long i = tid; i < n; i += T) q[i] = -g[i];
         } else {
-            // two-loop recursion; every thread owns the elements i = tid (mod T) of q, so only the
-            // dot products cross threads.  The axpy of one pair is fused with the dot of the next.
-            double part = 0.0;
-            {
-                const double* Sj = P.S + (long long)((s.head + col - 1) % m) * n;
-                for (long long i = tid; i < n; i += T) { const double v = g[i]; q[i] = v; part += Sj[i] * v; }
+            // (1) every dot product with the stored pairs in one sweep, four pairs (16 sums) at a time; a
+            // thread owns the elements i = tid (mod T) of every vector, so only the sums cross threads
+            for (int k0 = 0; k0 < col; k0 += 4) {
+                const int np = col - k0 < 4 ? col - k0 : 4;
+                const double *Sp[4], *Yp[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int slot = (s.head + k0 + (k < np ? k : 0)) % m;
+                    Sp[k] = P.S + (long long)slot * n; Yp[k] = P.Y + (long long)slot * n;
+                }
+                double acc[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+                for (long long i = tid; i < n; i += T) {
+                    const double gi = g[i], yi = P.gold[i];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < np) {
+                            const double sv = Sp[k][i], yv = Yp[k][i];
+                            acc[4 * k] = __fma_rn(sv, yi, acc[4 * k]); acc[4 * k + 1] = __fma_rn(yv, yi, acc[4 * k + 1]);
+                            acc[4 * k + 2] = __fma_rn(sv, gi, acc[4 * k + 2]); acc[4 * k + 3] = __fma_rn(yv, gi, acc[4 * k + 3]);
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    double v = acc[k];
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+                    if ((tid & 31) == 0) wred[tid >> 5][k] = v;
+                }
+                __syncthreads();
+                if (tid < 4 * np) {
+                    double t = 0.0;
+                    for (int w = 0; w < (T >> 5); ++w) t += wred[w][tid];
+                    dots[tid & 3][k0 + (tid >> 2)] = t;
+                }
+                __syncthreads();
             }
-            for (int k = col - 1; k >= 0; --k) {
-                const int j = (s.head + k) % m;
-                const double a = rho[j] * lb_sum(part, red, par);
-                if (tid == 0) alpha[k] = a;
-                const double* Yj = P.Y + (long long)j * n;
-                part = 0.0;
-                if (k > 0) {
-                    const double* Sn = P.S + (long long)((s.head + k - 1) % m) * n;
-                    for (long long i = tid; i < n; i += T) { const double v = q[i] - a * Yj[i]; q[i] = v; part += Sn[i] * v; }
-                } else {
-                    // r = H0 q, and the first dot of the second loop
-                    const double gamma = 1.0 / s.theta;
-                    for (long long i = tid; i < n; i += T) { const double v = (q[i] - a * Yj[i]) * gamma; q[i] = v; part += Yj[i] * v; }
+            // (2) the m x m algebra, one thread: the new pair's column of S'Y and Y'Y, then
+            //   u = R^-1 S'g,  w = (D + gamma Y'Y) u - gamma Y'g,  H g = gamma g + S R^-T w - gamma Y u
+            if (tid == 0) {
+                const double gamma = 1.0 / s.theta;
+                auto slot_of = [&](int k) { return (s.head + k) % m; };
+                if (new_slot >= 0) {
+                    for (int k = 0; k < col; ++k) {
+                        const int sk = slot_of(k);
+                        sy[sk * m + new_slot] = dots[0][k];
+                        yy[sk * m + new_slot] = dots[1][k]; yy[new_slot * m + sk] = dots[1][k];
+                    }
+                    sy[new_slot * m + new_slot] = new_dr;          // s'y of the newest pair as the search measured it (L-BFGS-B's D)
+                }
+                double* u = coef[1];
+                double* w = coef[0];
+                for (int i = col - 1; i >= 0; --i) {
+                    double t = dots[2][i];
+                    for (int j = i + 1; j < col; ++j) t -= sy[slot_of(i) * m + slot_of(j)] * u[j];
+                    u[i] = t / sy[slot_of(i) * m + slot_of(i)];
+                }
+                for (int i = 0; i < col; ++i) {
+                    double t = 0.0;
+                    for (int j = 0; j < col; ++j) t += yy[slot_of(i) * m + slot_of(j)] * u[j];
+                    w[i] = sy[slot_of(i) * m + slot_of(i)] * u[i] + gamma * t - gamma * dots[3][i];
+                }
+                for (int i = 0; i < col; ++i) {
+                    double t = w[i];
+                    for (int j = 0; j < i; ++j) t -= sy[slot_of(j) * m + slot_of(i)] * w[j];
+                    w[i] = t / sy[slot_of(i) * m + slot_of(i)];          // in place: w[j < i] already hold R^-T w
+                }
+                for (int i = 0; i < col; ++i) u[i] = -gamma * u[i];
+            }
+            __syncthreads();
+            // (3) direction = -H g
+            const double gamma = 1.0 / s.theta;
+            for (int k0 = 0; k0 < col; k0 += 4) {
+                const int np = col - k0 < 4 ? col - k0 : 4;
+                const double *Sp[4], *Yp[4];
+                double c1[4], c2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int slot = (s.head + k0 + (k < np ? k : 0)) % m;
+                    Sp[k] = P.S + (long long)slot * n; Yp[k] = P.Y + (long long)slot * n;
+                    c1[k] = k < np ? coef[0][k0 + k] : 0.0; c2[k] = k < np ? coef[1][k0 + k] : 0.0;
+                }
+                for (long long i = tid; i < n; i += T) {
+                    double a = k0 == 0 ? gamma * g[i] : -q[i];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < np) a = __fma_rn(Sp[k][i], c1[k], __fma_rn(Yp[k][i], c2[k], a));
+                    q[i] = -a;
                 }
             }
-            __syncthreads();      // alpha[]
-            for (int k = 0; k < col; ++k) {
-                const int j = (s.head + k) % m;
-                const double b = rho[j] * lb_sum(part, red, par);
-                const double c = alpha[k] - b;
-                const double* Sj = P.S + (long long)j * n;
-                part = 0.0;
-                if (k + 1 < col) {
-                    const double* Yn = P.Y + (long long)((s.head + k + 1) % m) * n;
-                    for (long long i = tid; i < n; i += T) { const double v = q[i] + c * Sj[i]; q[i] = v; part += Yn[i] * v; }
-                } else {
-                    for (long long i = tid; i < n; i += T) q[i] = -(q[i] + c * Sj[i]);
-                }
-            }
+            new_slot = -1;
         }
         // L-BFGS-B forms the point z = x + direction and searches along d = z - x
         double dtd = 0.0, gd = 0.0;
@@ -397,6 +467,8 @@ __global__ void __launch_bounds__(kLbfgsThreads) k_lbfgs_advance(const LbfgsProb
         else { for (long long i = tid; i < n; i += T) P.x[i] = stp * q[i] + P.xold[i]; }
         s.phase = kLbSearch;
     }
+    __syncthreads();
+    for (int i = tid; i < o.m * o.m; i += T) { P.sy[i] = sy[i]; P.sy[o.m * o.m + i] = yy[i]; }
     if (tid == 0) { *P.st = s; flags[pid] = s.phase; }
 }
 
@@ -413,6 +485,9 @@ struct jb_lbfgs {
     jb::LbfgsState* d_states = nullptr;
     jb::LbfgsReg* d_regs = nullptr;
     int *d_flags = nullptr, *d_active = nullptr, *h_flags = nullptr;
+    double *d_x = nullptr, *d_out = nullptr;                  // all chunks' x / [f, g], contiguous
+    size_t n_x = 0, n_out = 0;
+    std::vector<double> h_x, h_out;
     bool regs_dirty = true;
     int64_t rounds = 0, launches = 0, batches_built = 0;
 };
@@ -452,22 +527,36 @@ int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* op
     h->regs.resize(n);
     int rc;
     if ((rc = lb_alloc(h.get(), &h->d_states, (size_t)n))) return rc;
-    // one allocation for every vector of every chunk:  x | out (1 + n) | xold | gold | d | z | S (m n) | Y (m n) | rho
-    size_t total = 0;
-    for (int i = 0; i < n; ++i) total += (size_t)plans[i]->n_fit * (6 + 2 * (size_t)opt->m) + 2 + jb::kLbfgsMaxM;
+    // one allocation for every vector of every chunk: all x | all out (1 + n each) -- so that starting
+    // points go up and results come down in one copy each -- then per chunk
+    // xold | gold | d | z | S (m n) | Y (m n) | S'Y, Y'Y (2 m m)
+    size_t total = 0, nx = 0, nout = 0;
+    for (int i = 0; i < n; ++i) {
+        const size_t nn = (size_t)plans[i]->n_fit;
+        nx += nn; nout += nn + 1;
+        total += nn * (4 + 2 * (size_t)opt->m) + 2 * (size_t)opt->m * opt->m;
+    }
+    h->n_x = nx; h->n_out = nout;
     double* base = nullptr;
-    if ((rc = lb_alloc(h.get(), &base, total))) return rc;
+    if ((rc = lb_alloc(h.get(), &base, nx + nout + total))) return rc;
+    h->d_x = base; h->d_out = base + nx;
+    double* px = h->d_x;
+    double* po = h->d_out;
+    base += nx + nout;
     for (int i = 0; i < n; ++i) {
         jb::LbfgsProblem& P = h->probs[i];
         memset(&P, 0, sizeof P);
         P.n = plans[i]->n_fit;
         const size_t nn = (size_t)P.n;
-        P.x = base; P.out = base + nn; P.xold = P.out + nn + 1; P.gold = P.xold + nn; P.d = P.gold + nn; P.z = P.d + nn;
+        P.x = px; px += nn;
+        P.out = po; po += nn + 1;
+        P.xold = base; P.gold = P.xold + nn; P.d = P.gold + nn; P.z = P.d + nn;
         P.S = P.z + nn; P.Y = P.S + nn * opt->m;
-        P.rho = P.Y + nn * opt->m;
+        P.sy = P.Y + nn * opt->m;
         P.st = h->d_states + i;
-        base = P.rho + jb::kLbfgsMaxM + 1;
+        base = P.sy + 2 * (size_t)opt->m * opt->m;
     }
+    h->h_x.resize(nx); h->h_out.resize(nout);
     if ((rc = lb_alloc(h.get(), &h->d_probs, (size_t)n))) return rc;
     if ((rc = lb_alloc(h.get(), &h->d_flags, (size_t)n))) return rc;
     if ((rc = lb_alloc(h.get(), &h->d_active, (size_t)n))) return rc;
@@ -539,8 +628,9 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
     memset(hs.data(), 0, hs.size() * sizeof(jb::LbfgsState));
     for (int i = 0; i < n; ++i) {
         hs[i].theta = 1.0; hs[i].phase = jb::kLbFirst;
-        JB_CUDA(cudaMemcpyAsync(h->probs[i].x, x0[i], (size_t)h->probs[i].n * sizeof(double), cudaMemcpyHostToDevice, st));
+        memcpy(h->h_x.data() + (h->probs[i].x - h->d_x), x0[i], (size_t)h->probs[i].n * sizeof(double));
     }
+    JB_CUDA(cudaMemcpyAsync(h->d_x, h->h_x.data(), h->n_x * sizeof(double), cudaMemcpyHostToDevice, st));
     JB_CUDA(cudaMemcpyAsync(h->d_states, hs.data(), hs.size() * sizeof(jb::LbfgsState), cudaMemcpyHostToDevice, st));
     JB_CUDA(cudaStreamSynchronize(st));
 
@@ -604,10 +694,12 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
     drop_batch();
     if (rc) return rc;
     JB_CUDA(cudaMemcpy(hs.data(), h->d_states, hs.size() * sizeof(jb::LbfgsState), cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpy(h->h_x.data(), h->d_x, h->n_x * sizeof(double), cudaMemcpyDeviceToHost));
+    if (grad_out) JB_CUDA(cudaMemcpy(h->h_out.data(), h->d_out, h->n_out * sizeof(double), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {
         const jb::LbfgsProblem& P = h->probs[i];
-        JB_CUDA(cudaMemcpy(x_out[i], P.x, (size_t)P.n * sizeof(double), cudaMemcpyDeviceToHost));
-        if (grad_out && grad_out[i]) JB_CUDA(cudaMemcpy(grad_out[i], P.out + 1, (size_t)P.n * sizeof(double), cudaMemcpyDeviceToHost));
+        memcpy(x_out[i], h->h_x.data() + (P.x - h->d_x), (size_t)P.n * sizeof(double));
+        if (grad_out && grad_out[i]) memcpy(grad_out[i], h->h_out.data() + (P.out - h->d_out) + 1, (size_t)P.n * sizeof(double));
         jb_lbfgs_result& R = results[i];
         R.f = hs[i].f; R.pg_norm = hs[i].sbgnrm; R.nit = hs[i].iter; R.funcalls = hs[i].funcalls;
         R.warnflag = hs[i].warnflag; R.task = hs[i].task; R.task_msg = hs[i].msg;
