@@ -89,6 +89,13 @@ struct jb_group {
     double* d_red = nullptr;             // [1 + n_shared]
     bool layout_dirty = true;
     int64_t evals = 0;
+    // the whole step (the plans' kernels, gather, all-reduce, scatter) as one CUDA graph once two calls in a
+    // row enqueue the same thing: the host then issues ONE launch per step, and a rank whose host thread
+    // is late by a few launches no longer holds the other ranks' all-reduce up
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t gstream = nullptr;
+    int steady = 0;
+    bool graphs_ok = true;
 };
 
 namespace {
@@ -209,6 +216,8 @@ void jb_group_destroy(jb_group* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->batch && g->batch->stream) cudaStreamSynchronize(g->batch->stream);
+    if (g->gstream) cudaStreamSynchronize(g->gstream);
+    drop_graph(g->gexec);
     if (g->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(g->comm); }
     if (g->d_pos) cudaFree(g->d_pos);
     if (g->d_red) cudaFree(g->d_red);
@@ -234,6 +243,35 @@ int jb_group_eval_device(jb_group* g, void* stream) {
     bool stale = g->layout_dirty || g->fit_sizes.size() != g->batch->plans.size();
     for (size_t i = 0; !stale && i < g->fit_sizes.size(); ++i) stale = g->fit_sizes[i] != g->batch->plans[i]->n_fit;
     if (stale && (rc = group_layout(g))) return rc;
+    static const bool group_graphs = [] { const char* e = getenv("JB_GROUP_GRAPH"); return !(e && e[0] == '0'); }();
+    if (graphs_enabled() && group_graphs && g->graphs_ok && !stale && batch_is_clean(g->batch) && !stream_is_capturing(st)) {
+        if (g->gexec && g->gstream != st) { JB_CUDA(cudaStreamSynchronize(g->gstream)); drop_graph(g->gexec); g->steady = 0; }
+        if (!g->gexec && ++g->steady >= 2) {
+            int rrc = JB_OK;
+            const int64_t launches0 = g->batch->launches, evals0 = g->evals;
+            std::vector<int64_t> ev0;
+            for (jb_plan* pl : g->batch->plans) ev0.push_back(pl->evaluations);
+            const bool ok = record_graph(st, &g->gexec, &rrc, [&] {
+                int r = jb_batch_eval_device(g->batch, st);
+                return r ? r : group_exchange(g, st);
+            });
+            // (recording counted a step that has not run yet)
+            g->batch->launches = launches0; g->evals = evals0;
+            for (size_t i = 0; i < ev0.size(); ++i) g->batch->plans[i]->evaluations = ev0[i];
+            if (!ok || rrc) { g->graphs_ok = false; drop_graph(g->gexec); }
+            else g->gstream = st;
+        }
+        if (g->gexec) {
+            JB_CUDA(cudaGraphLaunch(g->gexec, st));
+            g->batch->launches += (g->batch->p_fit.empty() ? 5 : 6) + 2;
+            g->evals++;
+            for (jb_plan* pl : g->batch->plans) pl->evaluations++;
+            return JB_OK;
+        }
+    } else if (!batch_is_clean(g->batch) || stale) {
+        if (g->gexec) { JB_CUDA(cudaStreamSynchronize(g->gstream)); drop_graph(g->gexec); }
+        g->steady = 0;
+    }
     if ((rc = jb_batch_eval_device(g->batch, st))) return rc;
     return group_exchange(g, st);
 }

@@ -637,7 +637,14 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
     std::vector<int> active((size_t)n);
     for (int i = 0; i < n; ++i) active[i] = i;
     jb_batch* batch = nullptr;
-    auto drop_batch = [&]() { if (batch) { jb_batch_destroy(batch); batch = nullptr; } };
+    cudaGraphExec_t round_exec = nullptr;
+    int steady = 0;
+    bool round_graphs_ok = true;
+    auto drop_batch = [&]() {
+        if (round_exec) { cudaStreamSynchronize(st); drop_graph(round_exec); }
+        steady = 0;
+        if (batch) { jb_batch_destroy(batch); batch = nullptr; }
+    };
     rc = JB_OK;
     std::vector<int> repeats((size_t)n, 0);
     while (!active.empty()) {
@@ -651,14 +658,43 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
             if (cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(JB_ERR_CUDA, "cudaMemcpyAsync failed"); break; }
             h->batches_built++;
         }
-        // one round, one wait: the evaluation, the optimiser's step, the status words and the flags
+        // one round, one wait: the evaluation, the optimiser's step, the status words and the flags --
+        // recorded as ONE CUDA graph once two rounds in a row enqueue the same thing (same chunks still
+        // iterating, no plan re-laid out), replayed until that changes
         const size_t na = active.size();
-        if ((rc = jb_batch_eval_device(batch, st))) break;
-        jb::k_lbfgs_advance<<<(unsigned)na, jb::kLbfgsThreads, 0, st>>>(h->d_probs, h->d_active, h->opt, h->d_flags, batch->d_stat_ptrs);
-        jb::k_gather_status<<<(unsigned)((na + 127) / 128), 128, 0, st>>>(batch->d_stat_ptrs, (int)na, batch->d_stat_flat);
-        if (cudaMemcpyAsync(batch->h_stat_flat, batch->d_stat_flat, 2 * na * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(h->h_flags, h->d_flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) {
+        auto enqueue_round = [&]() -> int {
+            int r = jb_batch_eval_device(batch, st);
+            if (r) return r;
+            jb::k_lbfgs_advance<<<(unsigned)na, jb::kLbfgsThreads, 0, st>>>(h->d_probs, h->d_active, h->opt, h->d_flags, batch->d_stat_ptrs);
+            jb::k_gather_status<<<(unsigned)((na + 127) / 128), 128, 0, st>>>(batch->d_stat_ptrs, (int)na, batch->d_stat_flat);
+            if (cudaMemcpyAsync(batch->h_stat_flat, batch->d_stat_flat, 2 * na * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaMemcpyAsync(h->h_flags, h->d_flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                return fail(JB_ERR_CUDA, "L-BFGS round: %s", cudaGetErrorString(cudaGetLastError()));
+            return JB_OK;
+        };
+        bool replayed = false;
+        if (graphs_enabled() && round_graphs_ok && batch_is_clean(batch)) {
+            if (!round_exec && ++steady >= 2) {
+                const int64_t launches0 = batch->launches;
+                std::vector<int64_t> ev0;
+                for (jb_plan* pl : batch->plans) ev0.push_back(pl->evaluations);
+                int rrc = JB_OK;
+                if (!record_graph(st, &round_exec, &rrc, enqueue_round) || rrc) { round_graphs_ok = false; drop_graph(round_exec); }
+                batch->launches = launches0;
+                for (size_t i = 0; i < ev0.size(); ++i) batch->plans[i]->evaluations = ev0[i];
+            }
+            if (round_exec) {
+                if (cudaGraphLaunch(round_exec, st) != cudaSuccess) { rc = fail(JB_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError())); break; }
+                batch->launches += batch->p_fit.empty() ? 5 : 6;
+                for (jb_plan* pl : batch->plans) pl->evaluations++;
+                replayed = true;
+            }
+        } else {
+            if (round_exec) { cudaStreamSynchronize(st); drop_graph(round_exec); }
+            steady = 0;
+        }
+        if (!replayed && (rc = enqueue_round())) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
             rc = fail(JB_ERR_CUDA, "L-BFGS round failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }

@@ -186,6 +186,12 @@ struct jb_batch {
     int** d_stat_ptrs = nullptr; int* d_stat_flat = nullptr; int* h_stat_flat = nullptr;
     bool host_bound = false, host_pending = false;
     bool soft_range = false;   // jb_batch_soft_range: an out-of-range plan yields a NaN loss instead of an error
+    // The launch sequence of an evaluation recorded as a CUDA graph once nothing changes between two calls
+    // (same packs, same stream) and replayed from then on: one launch per evaluation instead of six.
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t gstream = nullptr;
+    int steady = 0;
+    bool graphs_ok = true;
 };
 
 namespace {
@@ -925,6 +931,37 @@ int eval_sync(jb_plan* pl, const double* d_p_fit) {
 }  // namespace
 
 // ================================================================================ C ABI
+namespace {
+// JB_GRAPHS=0 turns the recorded launch sequences off (plain stream launches everywhere)
+bool graphs_enabled() {
+    static const bool on = [] { const char* e = getenv("JB_GRAPHS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+void drop_graph(cudaGraphExec_t& g) {
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
+// Record what `enqueue` puts on `st` and instantiate it.  false: recording is not possible here (the work
+// was NOT done: the caller enqueues it the plain way); rc carries an error of `enqueue` itself.
+template <typename F>
+bool record_graph(cudaStream_t st, cudaGraphExec_t* exec, int* rc, F enqueue) {
+    *rc = JB_OK;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    *rc = enqueue();
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    bool ok = *rc == JB_OK && e == cudaSuccess && g != nullptr;
+    if (ok && cudaGraphInstantiate(exec, g, 0) != cudaSuccess) { *exec = nullptr; ok = false; }
+    if (g) cudaGraphDestroy(g);
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+}  // namespace
+
 extern "C" {
 
 const char* jb_last_error(void) { return g_err.c_str(); }
@@ -1606,6 +1643,14 @@ int jb_plan_profile_read(jb_plan* pl, double* fused_ms_total, int64_t* n_launche
     return JB_OK;
 }
 
+// would an evaluation of this batch enqueue exactly what the previous one did?
+static bool batch_is_clean(const jb_batch* b) {
+    if (b->dirty || b->plans.empty()) return false;
+    for (const jb_plan* pl : b->plans)
+        if (pl->sort_dirty || pl->pack_dirty || pl->profiling || pl->wincap != b->plans[0]->wincap) return false;
+    return true;
+}
+
 int jb_batch_create(jb_plan* const* plans, int32_t n, jb_batch** out) {
     if (!plans || n <= 0 || !out) return fail(JB_ERR_BAD_ARG, "bad batch");
     *out = nullptr;
@@ -1636,6 +1681,8 @@ void jb_batch_destroy(jb_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->gstream) cudaStreamSynchronize(b->gstream);
+    drop_graph(b->gexec);
     for (void* q : b->dev) cudaFree(q);
     if (b->d_flat_p) cudaFree(b->d_flat_p);
     if (b->d_flat_out) cudaFree(b->d_flat_out);
@@ -1897,6 +1944,9 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     }
     if (regroup) {
         JB_CUDA(cudaStreamSynchronize(st));
+        if (b->gstream && b->gstream != st) JB_CUDA(cudaStreamSynchronize(b->gstream));
+        drop_graph(b->gexec);
+        b->steady = 0;
         for (void* q : b->dev) cudaFree(q);
         b->dev.clear();
         std::vector<jb::ScatterParams> sc(n); std::vector<jb::PrepareParams> pr(n);
@@ -1938,7 +1988,18 @@ int jb_batch_eval_device(jb_batch* b, void* stream) {
     for (jb_plan* q : b->plans) L.max_knots = std::max(L.max_knots, q->max_knots);
     L.variant = b->plans[0]->variant;
     L.scatter = !b->p_fit.empty();
-    if ((rc = launch_all(L, st, nullptr, nullptr, b->plans[0]))) return rc;
+    bool replayed = false;
+    if (graphs_enabled() && b->graphs_ok && !b->plans[0]->profiling && !stream_is_capturing(st)) {
+        if (b->gexec && b->gstream != st) { JB_CUDA(cudaStreamSynchronize(b->gstream)); drop_graph(b->gexec); b->steady = 0; }
+        if (!b->gexec && ++b->steady >= 2) {
+            // nothing changed since the previous call: record the sequence, replay it from now on
+            if (!record_graph(st, &b->gexec, &rc, [&] { return launch_all(L, st, nullptr, nullptr, nullptr); })) b->graphs_ok = false;
+            if (rc) return rc;
+            b->gstream = st;
+        }
+        if (b->gexec) { JB_CUDA(cudaGraphLaunch(b->gexec, st)); replayed = true; }
+    }
+    if (!replayed && (rc = launch_all(L, st, nullptr, nullptr, b->plans[0]))) return rc;
     b->launches += L.scatter ? 6 : 5;
     for (jb_plan* pl : b->plans) pl->evaluations++;
     return JB_OK;
