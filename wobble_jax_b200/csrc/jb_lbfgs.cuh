@@ -30,6 +30,7 @@
 // step where this applies the compact form of H (the same matrix, different rounding), so iterates agree
 // to rounding for the first iterations and then drift like any two builds of the same optimiser.
 #include <cfloat>
+#include <mutex>
 
 namespace jb {
 
@@ -493,13 +494,37 @@ struct jb_lbfgs {
 };
 
 namespace {
+// device memory from the stream-ordered pool (the plans keep its release threshold at "never": a second
+// optimiser finds the first one's memory there -- no driver call, nothing shared with other processes)
 template <typename T>
 int lb_alloc(jb_lbfgs* h, T** out, size_t count) {
     void* p = nullptr;
-    JB_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    JB_CUDA(cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16), h->plans[0]->stream));
     h->dev.push_back(p);
     *out = static_cast<T*>(p);
     return JB_OK;
+}
+// page-locked flag buffers of finished optimisers, kept for the next one
+std::mutex g_lb_pinned_mutex;
+std::vector<std::pair<int*, size_t>> g_lb_pinned;
+int* lb_pinned_get(size_t n) {
+    {
+        std::lock_guard<std::mutex> lock(g_lb_pinned_mutex);
+        for (size_t i = 0; i < g_lb_pinned.size(); ++i)
+            if (g_lb_pinned[i].second >= n) {
+                int* p = g_lb_pinned[i].first;
+                g_lb_pinned.erase(g_lb_pinned.begin() + i);
+                return p;
+            }
+    }
+    int* p = nullptr;
+    if (cudaMallocHost(&p, std::max<size_t>(n, 256) * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void lb_pinned_put(int* p, size_t n) {
+    std::lock_guard<std::mutex> lock(g_lb_pinned_mutex);
+    if (g_lb_pinned.size() < 8) g_lb_pinned.emplace_back(p, std::max<size_t>(n, 256));
+    else cudaFreeHost(p);
 }
 }  // namespace
 
@@ -560,7 +585,8 @@ int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* op
     if ((rc = lb_alloc(h.get(), &h->d_probs, (size_t)n))) return rc;
     if ((rc = lb_alloc(h.get(), &h->d_flags, (size_t)n))) return rc;
     if ((rc = lb_alloc(h.get(), &h->d_active, (size_t)n))) return rc;
-    JB_CUDA(cudaMallocHost(&h->h_flags, (size_t)n * sizeof(int)));
+    h->h_flags = lb_pinned_get((size_t)n);
+    if (!h->h_flags) return fail(JB_ERR_CUDA, "no page-locked memory for the optimiser's flags");
     *out = h.release();
     return JB_OK;
 }
@@ -568,10 +594,11 @@ int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* op
 void jb_lbfgs_destroy(jb_lbfgs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaDeviceSynchronize();
-    for (void* p : h->dev) cudaFree(p);
-    if (h->d_regs) cudaFree(h->d_regs);
-    if (h->h_flags) cudaFreeHost(h->h_flags);
+    cudaStream_t st = h->plans.empty() ? nullptr : h->plans[0]->stream;
+    for (void* p : h->dev) cudaFreeAsync(p, st);
+    if (h->d_regs) cudaFreeAsync(h->d_regs, st);
+    cudaStreamSynchronize(st);
+    if (h->h_flags) lb_pinned_put(h->h_flags, h->plans.size());
     delete h;
 }
 
@@ -588,7 +615,10 @@ int jb_lbfgs_add_reg(jb_lbfgs* h, int32_t problem, int32_t kind, double weight, 
     long long* d_idx = nullptr;
     int rc = lb_alloc(h, &d_idx, idx.size());
     if (rc) return rc;
-    if (!idx.empty()) JB_CUDA(cudaMemcpy(d_idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    if (!idx.empty()) {
+        JB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice, h->plans[0]->stream));
+        JB_CUDA(cudaStreamSynchronize(h->plans[0]->stream));
+    }
     jb::LbfgsReg R;
     R.idx = d_idx; R.n = n_indices; R.weight = weight; R.constant = constant; R.kind = kind; R.pad_ = 0;
     h->regs[problem].push_back(R);
@@ -607,12 +637,13 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
         if (h->plans[i]->n_fit != h->probs[i].n) return fail(JB_ERR_BAD_ARG, "chunk %d: the fit vector changed size since jb_lbfgs_create", i);
     }
     if (h->regs_dirty) {
-        if (h->d_regs) { cudaFree(h->d_regs); h->d_regs = nullptr; }
+        if (h->d_regs) { cudaFreeAsync(h->d_regs, st); h->d_regs = nullptr; }
         std::vector<jb::LbfgsReg> flat;
         for (int i = 0; i < n; ++i) flat.insert(flat.end(), h->regs[i].begin(), h->regs[i].end());
         if (!flat.empty()) {
-            JB_CUDA(cudaMalloc(&h->d_regs, flat.size() * sizeof(jb::LbfgsReg)));
-            JB_CUDA(cudaMemcpy(h->d_regs, flat.data(), flat.size() * sizeof(jb::LbfgsReg), cudaMemcpyHostToDevice));
+            JB_CUDA(cudaMallocAsync(&h->d_regs, flat.size() * sizeof(jb::LbfgsReg), st));
+            JB_CUDA(cudaMemcpyAsync(h->d_regs, flat.data(), flat.size() * sizeof(jb::LbfgsReg), cudaMemcpyHostToDevice, st));
+            JB_CUDA(cudaStreamSynchronize(st));
         }
         size_t o = 0;
         for (int i = 0; i < n; ++i) {
@@ -620,7 +651,8 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
             h->probs[i].n_regs = (int)h->regs[i].size();
             o += h->regs[i].size();
         }
-        JB_CUDA(cudaMemcpy(h->d_probs, h->probs.data(), (size_t)n * sizeof(jb::LbfgsProblem), cudaMemcpyHostToDevice));
+        JB_CUDA(cudaMemcpyAsync(h->d_probs, h->probs.data(), (size_t)n * sizeof(jb::LbfgsProblem), cudaMemcpyHostToDevice, st));
+        JB_CUDA(cudaStreamSynchronize(st));
         h->regs_dirty = false;
     }
     // starting points and fresh states
@@ -729,9 +761,10 @@ int jb_lbfgs_run(jb_lbfgs* h, const double* const* x0, double* const* x_out, dou
     if (batch) h->launches += jb_batch_launches(batch);
     drop_batch();
     if (rc) return rc;
-    JB_CUDA(cudaMemcpy(hs.data(), h->d_states, hs.size() * sizeof(jb::LbfgsState), cudaMemcpyDeviceToHost));
-    JB_CUDA(cudaMemcpy(h->h_x.data(), h->d_x, h->n_x * sizeof(double), cudaMemcpyDeviceToHost));
-    if (grad_out) JB_CUDA(cudaMemcpy(h->h_out.data(), h->d_out, h->n_out * sizeof(double), cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpyAsync(hs.data(), h->d_states, hs.size() * sizeof(jb::LbfgsState), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaMemcpyAsync(h->h_x.data(), h->d_x, h->n_x * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad_out) JB_CUDA(cudaMemcpyAsync(h->h_out.data(), h->d_out, h->n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i) {
         const jb::LbfgsProblem& P = h->probs[i];
         memcpy(x_out[i], h->h_x.data() + (P.x - h->d_x), (size_t)P.n * sizeof(double));
