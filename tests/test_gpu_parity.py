@@ -863,3 +863,39 @@ def test_full_size_fisher_of_both_components():
     for comp, node in ((0, model[0][0]), (1, model[1][0])):
         assert rel_err(plan.fisher(comp), ofisher[off[id(node)]:off[id(node)] + E]) < TOL
     plan.close()
+
+
+def test_the_x64_switch_selects_the_float32_tier():
+    """``jabble.config.update("jax_enable_x64", False)`` -- the reference's global precision switch
+    (notebooks/01-testdata.ipynb cell 0 sets it True) -- puts loss_all / grad_all / optimize / f_info on the
+    float32 tier (k_fused32; 1e-5 of float64, BASELINE.json north_star); grid search and curvature stay in
+    float64; a tree the tier does not cover says so."""
+    import copy
+    ch = synth.make_chunk(chunk=3, n_epochs=40, n_pix=1500, p_val=3, n_lines=20)
+    model = ch.model
+    model.fix(); model.fit(0, 1); model.fit(1, 1)
+    loss = jabble.loss.ChiSquare()
+    db, mb = ch.data.blockify()
+    p = np.asarray(model.get_parameters())
+    f64, g64 = loss.loss_all(p, db, mb, model), np.asarray(loss.grad_all(p, db, mb, model))
+    m64 = copy.deepcopy(model)
+    x64, fo64, d64 = m64.optimize(loss, ch.data, options={"maxiter": 15})
+    assert jabble.config.jax_enable_x64
+    try:
+        jabble.config.update("jax_enable_x64", False)
+        f32, g32 = loss.loss_all(p, db, mb, model), np.asarray(loss.grad_all(p, db, mb, model))
+        plan = engine.get_plan(model, db, mb)
+        assert plan.info()["fused_variant"] >= 64 and plan.info()["algorithmic_bytes"] < 14 * 40 * 1500 + 10 ** 6
+        assert f32 != f64 and abs(f32 - f64) <= TOL32 * abs(f64)
+        _check_grad(model, g32, g64, tol=TOL32)
+        m32 = copy.deepcopy(model)
+        x32, fo32, d32 = m32.optimize(loss, ch.data, options={"maxiter": 15})      # the device optimiser on a float32 plan
+        assert fo32 < f32 and abs(fo32 - fo64) <= 1e-2 * abs(fo64) and d32["nit"] == d64["nit"]
+        # float64-only paths ignore the switch
+        gs = engine.grid_search(model, model[0][0], db, mb, np.zeros((40, 3)) + np.array([-1e-6, 0.0, 1e-6]))
+        assert np.all(np.isfinite(gs))
+        with pytest.raises(AttributeError):
+            jabble.config.update("jax_debug_nans", True)
+    finally:
+        jabble.config.update("jax_enable_x64", True)
+    assert loss.loss_all(p, db, mb, model) == f64

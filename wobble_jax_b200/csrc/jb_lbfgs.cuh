@@ -539,7 +539,6 @@ int jb_lbfgs_create(jb_plan* const* plans, int32_t n, const jb_lbfgs_options* op
     for (int i = 0; i < n; ++i) {
         if (!plans[i]) return fail(JB_ERR_BAD_ARG, "null plan");
         if (plans[i]->device != plans[0]->device) return fail(JB_ERR_BAD_ARG, "the plans must live on one device");
-        if (plans[i]->f32) return fail(JB_ERR_UNSUPPORTED, "the optimiser iterates in float64");
         if (plans[i]->n_fit <= 0) return fail(JB_ERR_BAD_ARG, "plan %d has no parameter in fit mode", i);
     }
     JB_CUDA(cudaSetDevice(plans[0]->device));

@@ -520,12 +520,16 @@ def clear_plan_cache():
     del _PLAN_CACHE[:]
 
 
-def get_plan(model, datablock, metablock, coefficient=1.0, device=0, unit_weights=None):
+def get_plan(model, datablock, metablock, coefficient=1.0, device=0, unit_weights=None, float32=None):
     """The cached Plan of (data block, tree structure, data term), synchronised with the model's
     current parameter values and fit flags.  ``unit_weights``: a constant that replaces ``yivar``
-    (L2Loss).  The plan belongs to the cache: do not close it."""
+    (L2Loss).  ``float32``: the float32 tier; None = what ``jabble.config`` says (``jax_enable_x64``
+    False -> float32).  The plan belongs to the cache: do not close it."""
+    if float32 is None:
+        from . import config
+        float32 = not config.jax_enable_x64
     spec = TreeSpec(model)
-    key = (id(datablock), id(metablock), spec.signature(), float(coefficient), unit_weights, int(device))
+    key = (id(datablock), id(metablock), spec.signature(), float(coefficient), unit_weights, int(device), bool(float32))
     for i, (k, db, mb, plan) in enumerate(_PLAN_CACHE):
         if k == key and db is datablock and mb is metablock and plan.handle:
             _PLAN_CACHE.append(_PLAN_CACHE.pop(i))
@@ -537,7 +541,7 @@ def get_plan(model, datablock, metablock, coefficient=1.0, device=0, unit_weight
     if unit_weights is not None and datablock["ys"] is not None:
         yivar = np.full_like(np.asarray(datablock["ys"], dtype=np.float64), float(unit_weights))
     plan = Plan(spec, datablock["xs"], datablock["ys"], yivar, datablock["mask"], metablock,
-                coefficient=coefficient, device=device)
+                coefficient=coefficient, device=device, float32=bool(float32))
     plan.sync_from_model()
     _PLAN_CACHE.append((key, datablock, metablock, plan))
     while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
@@ -605,7 +609,8 @@ class Objective:
         loss_all / grad_all calls: scipy's func and fprime then share one fused evaluation."""
         spec = TreeSpec(model)
         fit = tuple(bool(lf.node._fit) for lf in spec.leaves)
-        key = (id(datablock), id(metablock), id(model), _loss_key(loss), spec.signature(), fit)
+        from . import config
+        key = (id(datablock), id(metablock), id(model), _loss_key(loss), spec.signature(), fit, config.jax_enable_x64)
         obj = cls._cache.get(key)
         if obj is not None and obj._db is datablock and np.array_equal(obj._params_all[~obj._fit_mask], spec.params_all()[~obj._fit_mask]):
             return obj
@@ -872,7 +877,7 @@ def shift_curvature(model, shift_model, datablock, metablock, coefficient=1.0, d
             comp = i
     if comp is None:
         raise NotImplementedError("the curvature runs on the CUDA path for the ShiftingModel of an additive component only")
-    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device).curvature(comp)
+    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device, float32=False).curvature(comp)
 
 
 def grid_search(model, shift_model, datablock, metablock, grid, coefficient=1.0, device=0):
@@ -884,7 +889,7 @@ def grid_search(model, shift_model, datablock, metablock, grid, coefficient=1.0,
             comp = i
     if comp is None:
         raise NotImplementedError("grid_search runs on the CUDA path for the ShiftingModel of an additive component only")
-    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device).grid_search(comp, grid)
+    return get_plan(model, datablock, metablock, coefficient=coefficient, device=device, float32=False).grid_search(comp, grid)
 
 
 def fisher_information(model, rv_model, datablock, metablock, device=0):

@@ -236,7 +236,7 @@ def train_norm(model, dataset, loss, device_store=None, device_op=None, batch_si
         print(res1)
         model.fix()
         datablock, metablock = dataset.blockify(device_op)
-        fwd = engine.get_plan(model, datablock, metablock, coefficient=getattr(loss, "coefficient", 1.0)).forward()
+        fwd = engine.get_plan(model, datablock, metablock, coefficient=getattr(loss, "coefficient", 1.0), float32=False).forward()
         for data_epoch in range(len(dataset)):
             frame = dataset[data_epoch]
             mask = np.asarray(frame.mask, dtype=bool)
@@ -320,7 +320,7 @@ def get_loss_array(model, datablock, metablock, loss, device=None):
     if not isinstance(loss, L.ChiSquare):
         raise NotImplementedError("get_loss_array runs on the CUDA path for ChiSquare only")
     loss.ready_indices(model)
-    fwd = engine.get_plan(model, datablock, metablock, coefficient=loss.coefficient).forward(
+    fwd = engine.get_plan(model, datablock, metablock, coefficient=loss.coefficient, float32=False).forward(
         np.asarray(model.get_parameters(), dtype=np.float64))
     mask = np.asarray(datablock["mask"], dtype=bool)
     with np.errstate(invalid="ignore"):
