@@ -147,13 +147,16 @@ class Data:
         if memo is not None and memo[0] == fp:
             return memo[1], memo[2]
         E = len(self)
-        max_ind = int(np.max([len(f.xs) for f in self.dataframes]))
-        xs = np.zeros((E, max_ind))
-        ys = np.zeros((E, max_ind))
-        yivar = np.zeros((E, max_ind))
-        mask = np.ones((E, max_ind), dtype=bool)
+        lens = [len(f.xs) for f in self.dataframes]
+        max_ind = int(np.max(lens))
+        full = min(lens) == max_ind       # rows of one length (the usual case): nothing to pad, no fill pass
+        make = np.empty if full else np.zeros
+        xs = make((E, max_ind))
+        ys = make((E, max_ind))
+        yivar = make((E, max_ind))
+        mask = np.empty((E, max_ind), dtype=bool) if full else np.ones((E, max_ind), dtype=bool)
         for i, f in enumerate(self.dataframes):
-            n = len(f.xs)
+            n = lens[i]
             xs[i, :n] = f.xs
             ys[i, :n] = f.ys
             yivar[i, :n] = f.yivar
