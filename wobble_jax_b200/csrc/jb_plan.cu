@@ -389,6 +389,21 @@ int strip_build(jb_plan* pl, const std::vector<int>& perm) {
     }
     pl->strip_reason = 2;
     if (K == 0) return JB_OK;      // rows too far apart for the column walk: k_fused2 / k_fused
+    if (pl->s_hint <= 0 && !pl->sK_force) {
+        // a lone plan runs as ONE wave of equal tasks of whole blocks: its time is the longest task's, rows
+        // plus ~4 rows' worth of checkpoint per block.  A shorter block can cut the rows per task finer
+        // (2000 rows on 18 row groups: 6 x 20 = 120 rows, but 7 x 16 = 112).
+        const int64_t groups_fit = std::max<int64_t>(1, 148LL * 16 / n_strips);
+        double best = INFINITY;
+        int best_k = K;
+        for (int cand : {20, 16, 12, 8}) {
+            if (cand > K) continue;
+            const int64_t nb = (E + cand - 1) / cand;
+            const double cost = (double)((nb + groups_fit - 1) / groups_fit) * (cand + 4.2);
+            if (cost < best - 1.0e-9) { best = cost; best_k = cand; }
+        }
+        K = best_k;
+    }
     const int n_blocks = (int)((E + K - 1) / K);
     if (K != 32 && (rc = run_xoff(K))) return rc;
     pl->strip_reason = 3;
