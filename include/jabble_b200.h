@@ -209,6 +209,12 @@ int jb_plan_grad_all(jb_plan *plan, double *grad_all, int64_t n_params);
  * device pointers of the fit vector (n_fit doubles; the array may be NULL to keep the parameters)
  * and of the output (1 + n_fit doubles: loss, gradient); jb_batch_eval_device enqueues one
  * evaluation of all plans on `stream` (NULL = the batch's own stream) without synchronising.
+ * Once two calls in a row enqueue the same launches (same plans, fit state, row order and stream) the
+ * sequence is recorded as a CUDA graph and replayed from then on -- one launch per evaluation; the same
+ * holds for jb_group_eval_device (its ncclAllReduce included) and for the rounds of jb_lbfgs.  Anything
+ * that changes a plan's launch parameters drops the recording; the environment variable JB_GRAPHS=0
+ * turns recording off.  A stream that is being captured by the caller is left alone (the launches
+ * join the caller's capture).
  */
 typedef struct jb_batch jb_batch;
 int jb_batch_create(jb_plan *const *plans, int32_t n_plans, jb_batch **out);
