@@ -141,10 +141,12 @@ OPTIMIZER = "device"
 def optimize_many(models, loss, datas, device_store=None, device_op=None, batch_size=None, options={}):
     """``Model.optimize`` (model.py:195-238) for many independent models at once -- the echelle orders /
     chunks the reference fits in a ``multiprocessing.Pool(jax.device_count())``
-    (notebooks/02-51peg.py:66-78).  Every model keeps its own scipy L-BFGS-B (same ``options``, same
-    iterates, same ``results`` record and ``_unpack`` as ``optimize``); the optimisers run in threads
-    and their evaluations go to the GPU together, one launch per kernel for all models that are still
-    iterating (``engine.LockstepEvaluator``).  ``loss`` is one loss for all models (copied per model:
+    (notebooks/02-51peg.py:66-78).  Every model gets its own L-BFGS-B (same ``options``, same iterates,
+    same ``results`` record and ``_unpack`` as ``optimize`` on it alone): with ``OPTIMIZER = "device"``
+    ONE ``jb_lbfgs`` drives them all (a block per model in the optimiser's kernel, one batched
+    evaluation per round for the models still iterating); with ``"scipy"``, or options the device
+    optimiser does not take, one scipy optimiser per model in threads whose evaluations go to the GPU
+    together (``engine.LockstepEvaluator``).  ``loss`` is one loss for all models (copied per model:
     regularisers keep per-model index sets) or one per model.  Returns the list of ``(x, f, d)``.
     """
     import threading
@@ -229,7 +231,9 @@ class Model:
     def optimize(self, loss, data, device_store=None, device_op=None, batch_size=None, options={}):
         """model.py:195-238 -- L-BFGS-B over every parameter in fit mode.
 
-        Same contract as the reference: blockify the data, hand scipy ``func`` and ``fprime``,
+        Same contract as the reference: blockify the data, minimise with L-BFGS-B under scipy's
+        ``fmin_l_bfgs_b`` options (``jb_lbfgs``: the optimiser's state on the device; scipy itself with
+        ``OPTIMIZER = "scipy"`` or for ``bounds`` / ``callback`` / ``approx_grad``),
         append one record to ``self.results`` and write the solution back with ``_unpack``;
         returns ``(x, f, d)``.  ``func`` and ``fprime`` share ONE fused CUDA evaluation per
         parameter vector (the reference runs a forward for ``func`` and a second forward plus a
